@@ -1,0 +1,183 @@
+/* svslam.h — dependency-free C ABI of the B200-native StereoVision-SLAM hot path.
+ *
+ * This is the drop-in boundary: each entry point replaces what
+ * one third-party call site inside the reference's private Frontend / Backend / DenseReconstruction
+ * methods computes.  Plain pointers and sizes only; every function returns 0 (SVS_OK) or a
+ * negative svs_status and never throws; svs_last_error() returns the message of the last failure
+ * on that context.  All pointers are caller-owned HOST memory unless the parameter name ends in
+ * `_dev`.  A context is single-threaded; distinct contexts are independent (the reference's
+ * frontend thread and backend thread each own one) and each owns one CUDA stream.
+ *
+ * There is NO CPU fallback: without a CUDA device svs_create() fails.
+ *
+ * Conventions
+ *   pose / extrinsic  double[7] = qx qy qz qw tx ty tz   (Sophus::SE3d: unit quaternion + translation, T_cw)
+ *   intrinsics        double[4] = fx fy cx cy            (Camera::K(), src/camera.cpp:14-21)
+ *   pixel coordinates float (x, y) interleaved
+ *   "ragged" batches  CSR offsets: item i of problem b lives at [off[b], off[b+1])
+ */
+#ifndef SVSLAM_H
+#define SVSLAM_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVS_API __attribute__((visibility("default")))
+
+typedef enum {
+    SVS_OK = 0,
+    SVS_ERR_CUDA = -1,       /* CUDA runtime error (message has the cudaError string) */
+    SVS_ERR_ARG = -2,        /* invalid argument */
+    SVS_ERR_CAPACITY = -3,   /* an internal capacity was exceeded (message says which) */
+    SVS_ERR_NODEVICE = -4    /* no CUDA device / wrong architecture */
+} svs_status;
+
+typedef struct svs_ctx svs_ctx;
+typedef struct svs_frameset svs_frameset;
+
+/* ---------------------------------------------------------------- context */
+SVS_API svs_ctx *svs_create(int device);                 /* NULL on failure (see svs_create_error) */
+SVS_API const char *svs_create_error(void);
+SVS_API void svs_destroy(svs_ctx *ctx);
+SVS_API const char *svs_last_error(svs_ctx *ctx);
+SVS_API int svs_version(void);
+SVS_API int svs_sync(svs_ctx *ctx);                       /* cudaStreamSynchronize on the context stream */
+SVS_API void *svs_stream(svs_ctx *ctx);                   /* the cudaStream_t, for event timing */
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+SVS_API long long svs_launch_count(svs_ctx *ctx);
+/* pinned host memory helpers (for callers without their own pinned allocator) */
+SVS_API void *svs_host_alloc(size_t bytes);
+SVS_API void svs_host_free(void *p);
+
+/* ---------------------------------------------------------------- frame sets
+ * A frame set holds, on the device, for each of n_streams independent stereo streams:
+ * the current and the previous LEFT image pyramid and the current RIGHT image pyramid
+ * (level 0 = the processed image).  Replaces Dataset::NextFrame's two cv::resize calls
+ * (src/dataset.cpp:126-134) and the pyramids cv::calcOpticalFlowPyrLK builds internally
+ * (src/frontend.cpp:105, :353).
+ *   half != 0 : processed image = 0.5x nearest of the input, size (rint(w/2), rint(h/2))
+ *   half == 0 : processed image = input
+ */
+SVS_API svs_frameset *svs_frameset_create(svs_ctx *ctx, int n_streams, int in_w, int in_h, int half,
+                                          int lk_win, int lk_max_level);
+SVS_API void svs_frameset_destroy(svs_ctx *ctx, svs_frameset *fs);
+SVS_API int svs_frameset_size(const svs_frameset *fs, int *w, int *h, int *n_levels);
+/* Push one new stereo pair for every stream: previous <- current, then resize + pyramids.
+ * left/right: n_streams images, image b at ptr + b*img_stride_bytes, rows row_stride bytes apart.
+ * on_device != 0: the pointers are device pointers (inputs already resident in HBM). */
+SVS_API int svs_frameset_push(svs_ctx *ctx, svs_frameset *fs, const uint8_t *left, const uint8_t *right,
+                              size_t row_stride, size_t img_stride_bytes, int on_device);
+/* Copy a pyramid level back (tests).  which: 0 = current left, 1 = previous left, 2 = current right */
+SVS_API int svs_frameset_download(svs_ctx *ctx, svs_frameset *fs, int stream, int which, int level,
+                                  uint8_t *out, int out_stride);
+
+/* ---------------------------------------------------------------- a0 : half-resolution resize
+ * Replaces cv::resize(src, dst, Size(), 0.5, 0.5, INTER_NEAREST) at src/dataset.cpp:128-129. */
+SVS_API int svs_half_nearest(svs_ctx *ctx, const uint8_t *src, int w, int h, int stride, int n_images,
+                             size_t img_stride_bytes, uint8_t *dst /* n * rint(h/2) * rint(w/2) */);
+
+/* ---------------------------------------------------------------- a1 : GFTT
+ * Replaces kp_detector_->detect(img, keypoints, mask) at src/frontend.cpp:51 (detector created at :24 as
+ * cv::GFTTDetector::create(num_features, 0.01, 20)) together with the mask Frontend::DetectFeatures
+ * draws at :42-47.  The mask is given either as an image (mask != NULL, 0 = excluded) or as the list of
+ * box centres (occupied_xy: the positions of the existing left features; the excluded box is
+ * [rint(x-10), rint(x+10)] x [rint(y-10), rint(y+10)], f32 subtraction, round-half-even).
+ * oracle_simd_granule: SIMD granule of the OpenCV build being matched (its Sobel-dy row filter uses a
+ * fused multiply-add for columns < g*floor(w/g) and separate mul+add for the tail; 32 = AVX-512 build,
+ * 0 = unfused everywhere).  Output: strongest-first (x, y) with integer values and the corner response. */
+SVS_API int svs_gftt_detect(svs_ctx *ctx, const uint8_t *img, int w, int h, int stride,
+                            const uint8_t *mask, int mask_stride,
+                            const float *occupied_xy, int n_occupied,
+                            int max_corners, double quality, double min_distance, int oracle_simd_granule,
+                            float *out_xy /* 2*max_corners */, float *out_response /* max_corners */, int *out_n);
+/* The corner-response map alone (cv::cornerMinEigenVal(img, 3, 3)); tests and profiling. */
+SVS_API int svs_corner_min_eig(svs_ctx *ctx, const uint8_t *img, int w, int h, int stride,
+                               int oracle_simd_granule, float *out /* h*w */);
+/* Batched over the CURRENT LEFT images of selected streams of a frame set. */
+SVS_API int svs_gftt_detect_batch(svs_ctx *ctx, svs_frameset *fs, const int32_t *stream_ids, int n_sel,
+                                  const int32_t *occ_off /* n_sel+1 */, const float *occupied_xy,
+                                  int max_corners, double quality, double min_distance, int oracle_simd_granule,
+                                  float *out_xy /* n_sel*2*max */, float *out_response /* n_sel*max */,
+                                  int32_t *out_n /* n_sel */);
+
+/* ---------------------------------------------------------------- a2 / a3 : pyramidal LK
+ * Replaces cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, Size(win,win), max_level,
+ * TermCriteria(COUNT+EPS, max_iter, eps), OPTFLOW_USE_INITIAL_FLOW) at src/frontend.cpp:105-109 (left ->
+ * right) and :353-357 (last -> current).  next_xy is in/out (initial flow in, result out); err is not
+ * produced (the reference never reads it) but its side effect on status is. */
+SVS_API int svs_lk_track(svs_ctx *ctx, const uint8_t *prev, const uint8_t *next, int w, int h, int stride,
+                         const float *prev_xy, float *next_xy, int n, int win, int max_level, int max_iter,
+                         double eps, uint8_t *status);
+/* Batched over the streams of a frame set.  pair: 0 = previous left -> current left (TrackLastFrame),
+ * 1 = current left -> current right (FindFeaturesInRight).  Points of stream b: [off[b], off[b+1]). */
+SVS_API int svs_lk_track_batch(svs_ctx *ctx, svs_frameset *fs, int pair, const int32_t *off /* n_streams+1 */,
+                               const float *prev_xy, float *next_xy, int max_iter, double eps, uint8_t *status);
+
+/* ---------------------------------------------------------------- a4 : triangulation
+ * Replaces slam::triangulation(poses, points, pworld) (include/StereoVisionSLAM/algorithm.h:10-87) as called
+ * at src/frontend.cpp:174 and :286 with Camera::pixel2camera (src/camera.cpp:58-72) for a rectified pair:
+ * left extrinsic identity, right extrinsic [I | (-baseline, 0, 0)].  out_ok = sigma4/sigma3 < 1e-2. */
+SVS_API int svs_triangulate(svs_ctx *ctx, const float *left_xy, const float *right_xy, int n,
+                            const double K_left[4], const double K_right[4], double baseline,
+                            double *out_xyz /* 3n */, uint8_t *out_ok /* n */);
+
+/* ---------------------------------------------------------------- a5 : pose-only LM
+ * Replaces the g2o block of Frontend::EstimateCurrentPose (src/frontend.cpp:408-527): one VertexPose,
+ * m EdgeProjectionPoseOnly (g2o_types.h:94-174), Huber(1.0), `rounds` x optimize(`iters`) with the
+ * chi2 > chi2_th outlier re-classification between rounds and the robust kernel dropped after round
+ * index 2.  Batched: problem b owns edges [off[b], off[b+1]). */
+typedef struct {
+    int32_t iterations, trials, linearizations, solves;
+    double lambda, chi2;
+} svs_lm_stats;
+SVS_API int svs_pose_only_lm(svs_ctx *ctx, int n_prob, const int32_t *off, const double *pts_w /* 3*M */,
+                             const double *uv /* 2*M */, const double *K /* 4*n_prob */,
+                             const double *T0 /* 7*n_prob */, double chi2_th, int rounds, int iters,
+                             double *T_out /* 7*n_prob */, uint8_t *outlier_out /* M */,
+                             int32_t *n_inlier /* n_prob */, svs_lm_stats *stats /* n_prob or NULL */);
+
+/* ---------------------------------------------------------------- a7 : bundle adjustment
+ * Replaces the g2o block of Backend::Optimize (src/backend.cpp:22-164): VertexPose per keyframe,
+ * marginalised VertexXYZ per landmark, EdgeProjection (g2o_types.h:176-229) per observation with
+ * Huber(huber_delta), Levenberg-Marquardt with Schur complement and a dense pivoted LDLT of the
+ * reduced camera system, max_iter iterations, no vertex fixed.  The chi2 post-pass
+ * (src/backend.cpp:167-213) stays with the caller and uses edge_chi2_out.
+ * jacobian_mode: 0 analytic, 1 central differences with delta = 1e-9 (g2o's default for this edge).
+ * Batched: problem b owns keyframes [kf_off[b],kf_off[b+1]), landmarks [lm_off..), edges [e_off..);
+ * edge_kf / edge_lm are indices LOCAL to the problem.  Keyframes/landmarks in ascending id order. */
+typedef struct {
+    int32_t iterations, trials, linearizations, solves;
+    double lambda, chi2, chi2_init;
+} svs_ba_stats;
+SVS_API int svs_ba_optimize(svs_ctx *ctx, int n_prob, const int32_t *kf_off, double *poses /* 7*sumN in/out */,
+                            const int32_t *lm_off, double *lms /* 3*sumL in/out */,
+                            const int32_t *e_off, const int32_t *edge_kf, const int32_t *edge_lm,
+                            const uint8_t *edge_cam /* 0 left, 1 right */, const double *edge_uv,
+                            const double K_left[4], const double K_right[4],
+                            const double ext_left[7], const double ext_right[7],
+                            double huber_delta, int max_iter, int jacobian_mode,
+                            double *edge_chi2_out /* sumE */, svs_ba_stats *stats /* n_prob or NULL */);
+
+/* ---------------------------------------------------------------- a10 : dense stereo
+ * svs_stereo_bm replaces stereo_depth_est_->compute(l, r, disp) (src/dense_reconstruction.cpp:114) for
+ * cv::StereoBM::create(ndisp, block) with OpenCV's defaults (XSOBEL prefilter cap 31, texture 10,
+ * uniqueness 15, min disparity 0, no speckle filter): int16 disparity*16, invalid = -16.
+ * svs_backproject replaces src/dense_reconstruction.cpp:116-173: disp/16 -> depth = fx*baseline/d (f32),
+ * every pixel with depth >= 1 back-projected with Camera::pixel2world (src/camera.cpp:82-86), x-outer /
+ * y-inner order, colour from the BGR image. */
+SVS_API int svs_stereo_bm(svs_ctx *ctx, const uint8_t *left, const uint8_t *right, int w, int h, int stride,
+                          int n_images, size_t img_stride_bytes, int ndisp, int block,
+                          int16_t *disp_out /* n*h*w */);
+SVS_API int svs_backproject(svs_ctx *ctx, const int16_t *disp, const uint8_t *bgr /* h*w*3 */, int w, int h,
+                            const double K[4], double baseline, const double cam_pose_inv[7],
+                            const double T_cw[7], float *xyz_out /* 3*h*w */, uint8_t *rgb_out /* 3*h*w */,
+                            int32_t *n_out);
+SVS_API int svs_bgr2gray(svs_ctx *ctx, const uint8_t *bgr, int w, int h, int n_images, uint8_t *gray);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVSLAM_H */

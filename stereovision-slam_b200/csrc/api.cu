@@ -1,0 +1,332 @@
+// C-ABI glue for include/svslam.h: context, frame sets and the image-stage entry points
+// (a0 half-resolution resize, a1 GFTT, a2/a3 pyramidal LK).  Host pointers in, host pointers out;
+// staging through pinned buffers owned by the context; one CUDA stream per context.
+#include "svs_internal.h"
+#include <cmath>
+#include <cstring>
+#include <new>
+
+int svs_i_gftt_overflow(svs_ctx *c, int n_img, int *flag_host);
+
+static std::string g_create_err;
+
+extern "C" {
+
+int svs_version(void) { return 100; }
+const char *svs_create_error(void) { return g_create_err.c_str(); }
+
+svs_ctx *svs_create(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { g_create_err = "device index out of range"; return nullptr; }
+    cudaDeviceProp p;
+    if ((e = cudaGetDeviceProperties(&p, device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return nullptr; }
+    if (p.major != 10) {
+        g_create_err = "this library is built for sm_100a (B200) only; found compute capability " +
+                       std::to_string(p.major) + "." + std::to_string(p.minor);
+        return nullptr;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return nullptr; }
+    svs_ctx *c = new (std::nothrow) svs_ctx();
+    if (!c) { g_create_err = "out of memory"; return nullptr; }
+    c->device = device;
+    c->sm_count = p.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void svs_destroy(svs_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *d[] = {&c->d_in, &c->d_in2, &c->d_out, &c->d_out2, &c->d_tmp, &c->d_tmp2, &c->d_tmp3, &c->d_tmp4, &c->d_tmp5, &c->d_tmp6};
+    for (DevBuf *b : d) b->release();
+    c->h_in.release(); c->h_out.release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *svs_last_error(svs_ctx *c) { return c ? c->err.c_str() : "null context"; }
+int svs_sync(svs_ctx *c) { SVS_CUDA(c, cudaStreamSynchronize(c->stream)); return SVS_OK; }
+void *svs_stream(svs_ctx *c) { return (void *)c->stream; }
+long long svs_launch_count(svs_ctx *c) { return c->launches; }
+void *svs_host_alloc(size_t bytes) { void *p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }
+void svs_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------ frame sets
+svs_frameset *svs_frameset_create(svs_ctx *c, int n_streams, int in_w, int in_h, int half, int lk_win, int lk_max_level)
+{
+    if (!c) return nullptr;
+    if (n_streams <= 0 || in_w < 6 || in_h < 6 || lk_max_level < 0) { c->err = "frameset: bad arguments"; return nullptr; }
+    cudaSetDevice(c->device);
+    svs_frameset *fs = new (std::nothrow) svs_frameset();
+    if (!fs) { c->err = "out of memory"; return nullptr; }
+    fs->B = n_streams; fs->in_w = in_w; fs->in_h = in_h; fs->half = half; fs->win = lk_win;
+    fs->W = half ? (int)std::nearbyint(in_w * 0.5) : in_w;
+    fs->H = half ? (int)std::nearbyint(in_h * 0.5) : in_h;
+    size_t per = 0;
+    PyrDesc d;
+    svs_i_make_pyr_desc(&d, fs->W, fs->H, lk_win, lk_max_level, &per);
+    fs->nlev = d.nlev;
+    for (int i = 0; i < 3; i++) {
+        if (fs->pyr[i].reserve(per * n_streams) != cudaSuccess) {
+            c->err = "frameset: cudaMalloc failed";
+            svs_frameset_destroy(c, fs);
+            return nullptr;
+        }
+        cudaMemsetAsync(fs->pyr[i].p, 0, per * n_streams, c->stream);
+    }
+    fs->L[0] = d; fs->L[0].base = fs->pyr[0].as<uint8_t>();
+    fs->L[1] = d; fs->L[1].base = fs->pyr[1].as<uint8_t>();
+    fs->R = d; fs->R.base = fs->pyr[2].as<uint8_t>();
+    return fs;
+}
+
+void svs_frameset_destroy(svs_ctx *c, svs_frameset *fs)
+{
+    if (!fs) return;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    for (int i = 0; i < 3; i++) fs->pyr[i].release();
+    fs->staging.release();
+    delete fs;
+}
+
+int svs_frameset_size(const svs_frameset *fs, int *w, int *h, int *n_levels)
+{
+    if (!fs) return SVS_ERR_ARG;
+    if (w) *w = fs->W;
+    if (h) *h = fs->H;
+    if (n_levels) *n_levels = fs->nlev;
+    return SVS_OK;
+}
+
+int svs_frameset_push(svs_ctx *c, svs_frameset *fs, const uint8_t *left, const uint8_t *right, size_t row_stride,
+                      size_t img_stride, int on_device)
+{
+    if (!c || !fs || !left || !right) return SVS_ERR_ARG;
+    if (row_stride < (size_t)fs->in_w || img_stride < row_stride * fs->in_h) SVS_FAIL(c, SVS_ERR_ARG, "frameset_push: bad strides");
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    const uint8_t *dl = left, *dr = right;
+    size_t rs = row_stride, is = img_stride;
+    if (!on_device) {
+        size_t dense = (size_t)fs->in_w * fs->in_h;
+        SVS_CUDA(c, fs->staging.reserve(2 * dense * fs->B));
+        uint8_t *sl = fs->staging.as<uint8_t>(), *sr = sl + dense * fs->B;
+        if (row_stride == (size_t)fs->in_w && img_stride == dense) {
+            SVS_CUDA(c, cudaMemcpyAsync(sl, left, dense * fs->B, cudaMemcpyHostToDevice, c->stream));
+            SVS_CUDA(c, cudaMemcpyAsync(sr, right, dense * fs->B, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            for (int b = 0; b < fs->B; b++) {
+                SVS_CUDA(c, cudaMemcpy2DAsync(sl + dense * b, fs->in_w, left + img_stride * b, row_stride, fs->in_w, fs->in_h, cudaMemcpyHostToDevice, c->stream));
+                SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right + img_stride * b, row_stride, fs->in_w, fs->in_h, cudaMemcpyHostToDevice, c->stream));
+            }
+        }
+        dl = sl; dr = sr; rs = fs->in_w; is = dense;
+    }
+    fs->cur ^= 1;
+    fs->pushes++;
+    PyrDesc &Lc = fs->L[fs->cur];
+    if (fs->half) {
+        SVS_TRY(svs_i_half_nearest(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc.base + Lc.off[0], fs->W, fs->H, Lc.stride[0], Lc.img_pitch));
+        SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R.base + fs->R.off[0], fs->W, fs->H, fs->R.stride[0], fs->R.img_pitch));
+    } else {
+        SVS_TRY(svs_i_copy_level0(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc));
+        SVS_TRY(svs_i_copy_level0(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R));
+    }
+    SVS_TRY(svs_i_build_pyramid(c, Lc, fs->B));
+    SVS_TRY(svs_i_build_pyramid(c, fs->R, fs->B));
+    return SVS_OK;
+}
+
+int svs_frameset_download(svs_ctx *c, svs_frameset *fs, int stream, int which, int level, uint8_t *out, int out_stride)
+{
+    if (!c || !fs || stream < 0 || stream >= fs->B || level < 0 || level >= fs->nlev || which < 0 || which > 2) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    const PyrDesc &d = which == 0 ? fs->L[fs->cur] : which == 1 ? fs->L[fs->cur ^ 1] : fs->R;
+    SVS_CUDA(c, cudaMemcpy2DAsync(out, out_stride, d.base + (size_t)stream * d.img_pitch + d.off[level], d.stride[level],
+                                  d.w[level], d.h[level], cudaMemcpyDeviceToHost, c->stream));
+    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SVS_OK;
+}
+
+// ------------------------------------------------------------------ a0
+int svs_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, int stride, int n, size_t img_stride, uint8_t *dst)
+{
+    if (!c || !src || !dst || w < 1 || h < 1 || n < 0 || stride < w) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    int dw = (int)std::nearbyint(w * 0.5), dh = (int)std::nearbyint(h * 0.5);
+    size_t in_bytes = img_stride * (size_t)n, out_bytes = (size_t)dw * dh * n;
+    SVS_CUDA(c, c->d_in.reserve(in_bytes));
+    SVS_CUDA(c, c->d_out.reserve(out_bytes));
+    SVS_CUDA(c, cudaMemcpyAsync(c->d_in.p, src, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    SVS_TRY(svs_i_half_nearest(c, c->d_in.as<uint8_t>(), w, h, stride, img_stride, n, c->d_out.as<uint8_t>(), dw, dh, dw, (size_t)dw * dh));
+    SVS_CUDA(c, cudaMemcpyAsync(dst, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SVS_OK;
+}
+
+// ------------------------------------------------------------------ a1
+static int gftt_common(svs_ctx *c, const uint8_t *img_dev, int w, int h, int stride, size_t img_pitch, int n_img,
+                       const int32_t *ids_host, const uint8_t *mask_host, int mask_stride,
+                       const int32_t *occ_off_host, const float *occ_xy_host, int max_corners, double quality,
+                       double min_distance, int granule, float *out_xy, float *out_resp, int32_t *out_n)
+{
+    if (max_corners <= 0) SVS_FAIL(c, SVS_ERR_ARG, "gftt: max_corners must be > 0");
+    int n_occ = occ_off_host ? occ_off_host[n_img] : 0;
+    // device inputs: [ids][occ_off][occ_xy] in d_in2 ; mask in d_tmp5
+    size_t ids_b = align_up((size_t)n_img * 4, 16), off_b = align_up((size_t)(n_img + 1) * 4, 16), xy_b = (size_t)n_occ * 8;
+    SVS_CUDA(c, c->d_in2.reserve(ids_b + off_b + xy_b + 16));
+    SVS_CUDA(c, c->h_in.reserve(ids_b + off_b + xy_b + 16));
+    uint8_t *hb = c->h_in.as<uint8_t>(), *db = c->d_in2.as<uint8_t>();
+    const int32_t *ids_dev = nullptr, *off_dev = nullptr;
+    const float *xy_dev = nullptr;
+    if (ids_host) { memcpy(hb, ids_host, (size_t)n_img * 4); ids_dev = reinterpret_cast<int32_t *>(db); }
+    if (occ_off_host && n_occ > 0) {
+        memcpy(hb + ids_b, occ_off_host, (size_t)(n_img + 1) * 4);
+        memcpy(hb + ids_b + off_b, occ_xy_host, xy_b);
+        off_dev = reinterpret_cast<int32_t *>(db + ids_b);
+        xy_dev = reinterpret_cast<float *>(db + ids_b + off_b);
+    }
+    SVS_CUDA(c, cudaMemcpyAsync(db, hb, ids_b + off_b + xy_b, cudaMemcpyHostToDevice, c->stream));
+    const uint8_t *mask_dev = nullptr;
+    if (mask_host) {
+        SVS_CUDA(c, c->d_tmp5.reserve((size_t)w * h * n_img));
+        SVS_CUDA(c, cudaMemcpy2DAsync(c->d_tmp5.p, w, mask_host, mask_stride, w, (size_t)h * n_img, cudaMemcpyHostToDevice, c->stream));
+        mask_dev = c->d_tmp5.as<uint8_t>();
+    }
+    size_t oxy_b = (size_t)n_img * max_corners * 8, orp_b = (size_t)n_img * max_corners * 4, on_b = (size_t)n_img * 4;
+    SVS_CUDA(c, c->d_out.reserve(oxy_b + orp_b + on_b));
+    SVS_CUDA(c, c->h_out.reserve(oxy_b + orp_b + on_b + 16));
+    uint8_t *dob = c->d_out.as<uint8_t>();
+    SVS_TRY(svs_i_gftt(c, img_dev, w, h, stride, img_pitch, n_img, ids_dev, mask_dev, off_dev, xy_dev, n_occ, max_corners,
+                       quality, min_distance, granule, reinterpret_cast<float *>(dob), reinterpret_cast<float *>(dob + oxy_b),
+                       reinterpret_cast<int32_t *>(dob + oxy_b + orp_b), nullptr));
+    uint8_t *hob = c->h_out.as<uint8_t>();
+    SVS_CUDA(c, cudaMemcpyAsync(hob, dob, oxy_b + orp_b + on_b, cudaMemcpyDeviceToHost, c->stream));
+    int *ovf = reinterpret_cast<int *>(hob + align_up(oxy_b + orp_b + on_b, 4));
+    SVS_TRY(svs_i_gftt_overflow(c, n_img, ovf));
+    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (*ovf) SVS_FAIL(c, SVS_ERR_CAPACITY, "gftt: more local-maximum candidates than the candidate buffer holds (w*h/4)");
+    memcpy(out_xy, hob, oxy_b);
+    if (out_resp) memcpy(out_resp, hob + oxy_b, orp_b);
+    memcpy(out_n, hob + oxy_b + orp_b, on_b);
+    return SVS_OK;
+}
+
+int svs_gftt_detect(svs_ctx *c, const uint8_t *img, int w, int h, int stride, const uint8_t *mask, int mask_stride,
+                    const float *occupied_xy, int n_occupied, int max_corners, double quality, double min_distance,
+                    int granule, float *out_xy, float *out_response, int *out_n)
+{
+    if (!c || !img || !out_xy || !out_n || stride < w) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    int dstride = (int)align_up((size_t)w, 16);
+    SVS_CUDA(c, c->d_in.reserve((size_t)dstride * h));
+    SVS_CUDA(c, cudaMemcpy2DAsync(c->d_in.p, dstride, img, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+    int32_t off[2] = {0, n_occupied};
+    int32_t n = 0;
+    int r = gftt_common(c, c->d_in.as<uint8_t>(), w, h, dstride, 0, 1, nullptr, mask, mask_stride,
+                        (occupied_xy && n_occupied > 0) ? off : nullptr, occupied_xy, max_corners, quality, min_distance,
+                        granule, out_xy, out_response, &n);
+    *out_n = n;
+    return r;
+}
+
+int svs_corner_min_eig(svs_ctx *c, const uint8_t *img, int w, int h, int stride, int granule, float *out)
+{
+    if (!c || !img || !out || stride < w) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    int dstride = (int)align_up((size_t)w, 16);
+    SVS_CUDA(c, c->d_in.reserve((size_t)dstride * h));
+    SVS_CUDA(c, c->d_out2.reserve((size_t)w * h * 4));
+    SVS_CUDA(c, cudaMemcpy2DAsync(c->d_in.p, dstride, img, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+    SVS_TRY(svs_i_gftt(c, c->d_in.as<uint8_t>(), w, h, dstride, 0, 1, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.01, 1.0,
+                       granule, nullptr, nullptr, nullptr, c->d_out2.as<float>()));
+    SVS_CUDA(c, cudaMemcpyAsync(out, c->d_out2.p, (size_t)w * h * 4, cudaMemcpyDeviceToHost, c->stream));
+    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SVS_OK;
+}
+
+int svs_gftt_detect_batch(svs_ctx *c, svs_frameset *fs, const int32_t *stream_ids, int n_sel, const int32_t *occ_off,
+                          const float *occupied_xy, int max_corners, double quality, double min_distance, int granule,
+                          float *out_xy, float *out_response, int32_t *out_n)
+{
+    if (!c || !fs || !stream_ids || !out_xy || !out_n || n_sel < 0) return SVS_ERR_ARG;
+    if (n_sel == 0) return SVS_OK;
+    for (int i = 0; i < n_sel; i++) if (stream_ids[i] < 0 || stream_ids[i] >= fs->B) SVS_FAIL(c, SVS_ERR_ARG, "gftt_batch: stream id out of range");
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    const PyrDesc &L = fs->L[fs->cur];
+    return gftt_common(c, L.base + L.off[0], fs->W, fs->H, L.stride[0], L.img_pitch, n_sel, stream_ids, nullptr, 0, occ_off,
+                       occupied_xy, max_corners, quality, min_distance, granule, out_xy, out_response, out_n);
+}
+
+// ------------------------------------------------------------------ a2 / a3
+static int lk_common(svs_ctx *c, const PyrDesc &prev, const PyrDesc &next, int n_img, const int32_t *off_host,
+                     const float *prev_xy, float *next_xy, int win, int max_iter, double eps, uint8_t *status)
+{
+    int n = off_host[n_img];
+    if (n <= 0) return SVS_OK;
+    size_t id_b = align_up((size_t)n * 4, 16), xy_b = (size_t)n * 8;
+    SVS_CUDA(c, c->h_in.reserve(id_b + 2 * xy_b));
+    SVS_CUDA(c, c->d_in2.reserve(id_b + 2 * xy_b));
+    SVS_CUDA(c, c->d_out.reserve(n));
+    SVS_CUDA(c, c->h_out.reserve(xy_b + n));
+    uint8_t *hb = c->h_in.as<uint8_t>(), *db = c->d_in2.as<uint8_t>();
+    int32_t *ids = reinterpret_cast<int32_t *>(hb);
+    for (int b = 0; b < n_img; b++) for (int i = off_host[b]; i < off_host[b + 1]; i++) ids[i] = b;
+    memcpy(hb + id_b, prev_xy, xy_b);
+    memcpy(hb + id_b + xy_b, next_xy, xy_b);
+    SVS_CUDA(c, cudaMemcpyAsync(db, hb, id_b + 2 * xy_b, cudaMemcpyHostToDevice, c->stream));
+    float *nxt_dev = reinterpret_cast<float *>(db + id_b + xy_b);
+    SVS_TRY(svs_i_lk(c, prev, next, reinterpret_cast<int32_t *>(db), reinterpret_cast<float *>(db + id_b), nxt_dev, n, win,
+                     max_iter, eps, c->d_out.as<uint8_t>()));
+    uint8_t *ho = c->h_out.as<uint8_t>();
+    SVS_CUDA(c, cudaMemcpyAsync(ho, nxt_dev, xy_b, cudaMemcpyDeviceToHost, c->stream));
+    SVS_CUDA(c, cudaMemcpyAsync(ho + xy_b, c->d_out.p, n, cudaMemcpyDeviceToHost, c->stream));
+    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(next_xy, ho, xy_b);
+    memcpy(status, ho + xy_b, n);
+    return SVS_OK;
+}
+
+int svs_lk_track(svs_ctx *c, const uint8_t *prev, const uint8_t *next, int w, int h, int stride, const float *prev_xy,
+                 float *next_xy, int n, int win, int max_level, int max_iter, double eps, uint8_t *status)
+{
+    if (!c || !prev || !next || n < 0 || stride < w || (n > 0 && (!prev_xy || !next_xy || !status))) return SVS_ERR_ARG;
+    if (n == 0) return SVS_OK;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    PyrDesc dp, dn;
+    size_t per = 0;
+    svs_i_make_pyr_desc(&dp, w, h, win, max_level, &per);
+    dn = dp;
+    SVS_CUDA(c, c->d_tmp6.reserve(2 * per));
+    dp.base = c->d_tmp6.as<uint8_t>();
+    dn.base = dp.base + per;
+    SVS_CUDA(c, cudaMemcpy2DAsync(dp.base, dp.stride[0], prev, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+    SVS_CUDA(c, cudaMemcpy2DAsync(dn.base, dn.stride[0], next, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+    SVS_TRY(svs_i_build_pyramid(c, dp, 1));
+    SVS_TRY(svs_i_build_pyramid(c, dn, 1));
+    int32_t off[2] = {0, n};
+    return lk_common(c, dp, dn, 1, off, prev_xy, next_xy, win, max_iter, eps, status);
+}
+
+int svs_lk_track_batch(svs_ctx *c, svs_frameset *fs, int pair, const int32_t *off, const float *prev_xy, float *next_xy,
+                       int max_iter, double eps, uint8_t *status)
+{
+    if (!c || !fs || !off || (pair != 0 && pair != 1)) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    const PyrDesc &prev = pair == 0 ? fs->L[fs->cur ^ 1] : fs->L[fs->cur];
+    const PyrDesc &next = pair == 0 ? fs->L[fs->cur] : fs->R;
+    return lk_common(c, prev, next, fs->B, off, prev_xy, next_xy, fs->win, max_iter, eps, status);
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+// Pyramidal Lucas-Kanade tracking (rows a2/a3): what cv::calcOpticalFlowPyrLK computes at reference
+// src/frontend.cpp:105-109 (left -> right) and :353-357 (last -> current), with
+// OPTFLOW_USE_INITIAL_FLOW.  Algorithm per SURVEY.md Appendix A.4/A.5.
+//
+// One warp per keypoint; the warp walks the pyramid levels coarse -> fine inside the kernel.
+// Per level the (win+3)^2 patch of the previous image is staged in shared memory, the Scharr
+// derivative patch is derived from it, each lane keeps its <=ceil(win^2/32) window samples
+// (I, Ix, Iy as int16 values) in registers, and every iteration stages the (win+1)^2 patch of the
+// next image and reduces the two mismatch sums with redux.sync.  All window sums are exact
+// integers (OpenCV accumulates the same integers in f32 lanes), the 2x2 solve is f32 with the
+// exact operation order of OpenCV — compile with --fmad=false.
+#include "svs_internal.h"
+#include <cfloat>
+
+__device__ __forceinline__ int lk_refl101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+    return i;
+}
+__device__ __forceinline__ long long warp_sum_i32_exact(int s)
+{   // exact 64-bit sum of 32 int32 partials via two hardware 32-bit reductions
+    int lo = s & 0xFFFF, hi = s >> 16;
+    int slo = __reduce_add_sync(0xffffffffu, lo);
+    int shi = __reduce_add_sync(0xffffffffu, hi);
+    return (long long)shi * 65536ll + (long long)slo;
+}
+__device__ __forceinline__ int cvfloor(float v) { return __float2int_rd(v); }
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+#define LK_WARPS 4
+
+template <int WIN>
+__global__ void __launch_bounds__(LK_WARPS * 32)
+k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const float *__restrict__ prev_xy,
+           float *__restrict__ next_xy, int n_pts, int max_iter, double eps2, uint8_t *__restrict__ status)
+{
+    constexpr int PW = WIN + 3;                 // previous-image patch (window + bilinear + Scharr halo)
+    constexpr int DW = WIN + 1;                 // derivative / next-image patch
+    constexpr int PP = (PW + 3) & ~3;           // smem row pitch (bytes)
+    constexpr int NPL = (WIN * WIN + 31) / 32;  // window samples per lane
+    __shared__ uint8_t sI[LK_WARPS][PW * PP];
+    __shared__ short2 sD[LK_WARPS][DW * DW];
+    __shared__ uint8_t sJ[LK_WARPS][DW * PP];
+    const int W_BITS = 14;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const float half = (WIN - 1) * 0.5f;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int pt = blockIdx.x * LK_WARPS + warp;
+    if (pt >= n_pts) return;
+    int img = pt_img[pt];
+    float px0 = prev_xy[2 * pt], py0 = prev_xy[2 * pt + 1];
+    float nxt_x = next_xy[2 * pt], nxt_y = next_xy[2 * pt + 1];
+    bool st = true;
+    uint8_t *mI = sI[warp], *mJ = sJ[warp];
+    short2 *mD = sD[warp];
+    int nlev = min(prev.nlev, next.nlev);
+
+    for (int level = nlev - 1; level >= 0; level--) {
+        const uint8_t *I = prev.base + (size_t)img * prev.img_pitch + prev.off[level];
+        const uint8_t *J = next.base + (size_t)img * next.img_pitch + next.off[level];
+        int Iw = prev.w[level], Ih = prev.h[level], Is = prev.stride[level];
+        int Jw = next.w[level], Jh = next.h[level], Js = next.stride[level];
+        float lscale = (float)(1. / (1 << level));
+        float ppx = __fmul_rn(px0, lscale), ppy = __fmul_rn(py0, lscale);
+        if (level == nlev - 1) { nxt_x = __fmul_rn(nxt_x, lscale); nxt_y = __fmul_rn(nxt_y, lscale); }
+        else { nxt_x = __fmul_rn(nxt_x, 2.f); nxt_y = __fmul_rn(nxt_y, 2.f); }
+        ppx = __fsub_rn(ppx, half); ppy = __fsub_rn(ppy, half);
+        int ix = cvfloor(ppx), iy = cvfloor(ppy);
+        if (ix < -WIN || ix >= Iw || iy < -WIN || iy >= Ih) { if (level == 0) st = false; continue; }
+        float a = __fsub_rn(ppx, (float)ix), b = __fsub_rn(ppy, (float)iy);
+        int w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
+        int w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
+        int w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), (float)(1 << W_BITS)));
+        int w11 = (1 << W_BITS) - w00 - w01 - w10;
+
+        __syncwarp();
+        // stage the previous-image patch: mI[j][i] = I(ix-1+i, iy-1+j), reflect-101 outside
+        for (int k = lane; k < PW * PW; k += 32) {
+            int j = k / PW, i = k - j * PW;
+            mI[j * PP + i] = __ldg(I + (size_t)lk_refl101(iy - 1 + j, Ih) * Is + lk_refl101(ix - 1 + i, Iw));
+        }
+        __syncwarp();
+        // Scharr derivative patch (zero outside the image: BORDER_CONSTANT on the derivative buffer)
+        for (int k = lane; k < DW * DW; k += 32) {
+            int j = k / DW, i = k - j * DW;
+            int X = ix + i, Y = iy + j;
+            short2 d = make_short2(0, 0);
+            if (X >= 0 && X < Iw && Y >= 0 && Y < Ih) {
+                const uint8_t *p = mI + j * PP + i;   // top-left of the 3x3 neighbourhood
+                int v00 = p[0], v01 = p[1], v02 = p[2];
+                int v10 = p[PP], v11 = p[PP + 1], v12 = p[PP + 2];
+                int v20 = p[2 * PP], v21 = p[2 * PP + 1], v22 = p[2 * PP + 2];
+                int s0l = (v00 + v20) * 3 + v10 * 10, s0r = (v02 + v22) * 3 + v12 * 10;
+                int s1l = v20 - v00, s1c = v21 - v01, s1r = v22 - v02;
+                d.x = (short)(s0r - s0l);
+                d.y = (short)((s1l + s1r) * 3 + s1c * 10);
+                (void)v11;
+            }
+            mD[k] = d;
+        }
+        __syncwarp();
+        int Iv[NPL], Ixv[NPL], Iyv[NPL];
+        int pA11 = 0, pA12 = 0, pA22 = 0;
+#pragma unroll
+        for (int q = 0; q < NPL; q++) {
+            int k = lane + 32 * q;
+            Iv[q] = 0; Ixv[q] = 0; Iyv[q] = 0;
+            if (k < WIN * WIN) {
+                int y = k / WIN, x = k - y * WIN;
+                const uint8_t *p = mI + (y + 1) * PP + (x + 1);
+                int ival = descale(p[0] * w00 + p[1] * w01 + p[PP] * w10 + p[PP + 1] * w11, W_BITS - 5);
+                short2 d00 = mD[y * DW + x], d01 = mD[y * DW + x + 1], d10 = mD[(y + 1) * DW + x], d11 = mD[(y + 1) * DW + x + 1];
+                int ixv = descale(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, W_BITS);
+                int iyv = descale(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, W_BITS);
+                Iv[q] = (short)ival; Ixv[q] = (short)ixv; Iyv[q] = (short)iyv;
+                pA11 += Ixv[q] * Ixv[q]; pA12 += Ixv[q] * Iyv[q]; pA22 += Iyv[q] * Iyv[q];
+            }
+        }
+        float A11 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pA11)), FLT_SCALE);
+        float A12 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pA12)), FLT_SCALE);
+        float A22 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pA22)), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        float dd = __fsub_rn(A11, A22);
+        float rad = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * WIN * WIN));
+        if ((double)minEig < 1e-4 || D < FLT_EPSILON) { if (level == 0) st = false; continue; }
+        D = __fdiv_rn(1.f, D);
+        float nx = __fsub_rn(nxt_x, half), ny = __fsub_rn(nxt_y, half);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < max_iter; j++) {
+            int jx = cvfloor(nx), jy = cvfloor(ny);
+            if (jx < -WIN || jx >= Jw || jy < -WIN || jy >= Jh) { if (level == 0) st = false; break; }
+            a = __fsub_rn(nx, (float)jx); b = __fsub_rn(ny, (float)jy);
+            w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
+            w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
+            w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), (float)(1 << W_BITS)));
+            w11 = (1 << W_BITS) - w00 - w01 - w10;
+            __syncwarp();
+            for (int k = lane; k < DW * DW; k += 32) {
+                int r = k / DW, i = k - r * DW;
+                mJ[r * PP + i] = __ldg(J + (size_t)lk_refl101(jy + r, Jh) * Js + lk_refl101(jx + i, Jw));
+            }
+            __syncwarp();
+            int pb1 = 0, pb2 = 0;
+#pragma unroll
+            for (int q = 0; q < NPL; q++) {
+                int k = lane + 32 * q;
+                if (k < WIN * WIN) {
+                    int y = k / WIN, x = k - y * WIN;
+                    const uint8_t *p = mJ + y * PP + x;
+                    int diff = descale(p[0] * w00 + p[1] * w01 + p[PP] * w10 + p[PP + 1] * w11, W_BITS - 5) - Iv[q];
+                    pb1 += diff * Ixv[q]; pb2 += diff * Iyv[q];
+                }
+            }
+            float b1 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pb1)), FLT_SCALE);
+            float b2 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pb2)), FLT_SCALE);
+            float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            nxt_x = __fadd_rn(nx, half); nxt_y = __fadd_rn(ny, half);
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= eps2) break;
+            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                nxt_x = __fsub_rn(nxt_x, __fmul_rn(dx, 0.5f)); nxt_y = __fsub_rn(nxt_y, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (st && level == 0) {   // OpenCV's error pass re-checks the final position
+            int jx = cvfloor(__fsub_rn(nxt_x, half)), jy = cvfloor(__fsub_rn(nxt_y, half));
+            if (jx < -WIN || jx >= Jw || jy < -WIN || jy >= Jh) st = false;
+        }
+    }
+    if (lane == 0) {
+        next_xy[2 * pt] = nxt_x; next_xy[2 * pt + 1] = nxt_y;
+        status[pt] = st ? 1 : 0;
+    }
+}
+
+int svs_i_lk(svs_ctx *c, const PyrDesc &prev, const PyrDesc &next, const int32_t *pt_img, const float *prev_xy,
+             float *next_xy, int n_pts, int win, int max_iter, double eps, uint8_t *status)
+{
+    if (n_pts <= 0) return SVS_OK;
+    if (max_iter > 100) max_iter = 100;
+    if (max_iter < 0) max_iter = 0;
+    if (eps < 0) eps = 0;
+    if (eps > 10) eps = 10;
+    double eps2 = eps * eps;
+    int blocks = (n_pts + LK_WARPS - 1) / LK_WARPS;
+#define LK_CASE(WN)                                                                                          \
+    case WN:                                                                                                 \
+        k_lk_track<WN><<<blocks, LK_WARPS * 32, 0, c->stream>>>(prev, next, pt_img, prev_xy, next_xy, n_pts, \
+                                                                max_iter, eps2, status);                     \
+        break;
+    switch (win) {
+        LK_CASE(5) LK_CASE(7) LK_CASE(9) LK_CASE(11) LK_CASE(13) LK_CASE(15) LK_CASE(21)
+    default:
+        SVS_FAIL(c, SVS_ERR_ARG, "lk: window size must be one of 5,7,9,11,13,15,21");
+    }
+#undef LK_CASE
+    SVS_LAUNCH_CHECK(c);
+    return SVS_OK;
+}

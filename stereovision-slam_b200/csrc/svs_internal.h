@@ -1,0 +1,108 @@
+// Internal declarations shared by the CUDA translation units behind include/svslam.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/svslam.h"
+
+#define SVS_MAX_LEVELS 8
+
+// Device image pyramid batch: image b, level l, row y at base + b*img_pitch + off[l] + y*stride[l].
+struct PyrDesc {
+    uint8_t *base;
+    size_t img_pitch;
+    int nlev;
+    int w[SVS_MAX_LEVELS], h[SVS_MAX_LEVELS], stride[SVS_MAX_LEVELS];
+    size_t off[SVS_MAX_LEVELS];
+};
+
+// Grow-only device / pinned-host buffers.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct svs_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    // scratch (named by user)
+    DevBuf d_in, d_in2, d_out, d_out2, d_tmp, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_tmp6;
+    PinBuf h_in, h_out;
+};
+
+struct svs_frameset {
+    int B = 0, in_w = 0, in_h = 0, half = 0, W = 0, H = 0, win = 11, nlev = 1;
+    PyrDesc L[2], R;   // L[cur], L[cur^1] = previous
+    int cur = 0;
+    long long pushes = 0;
+    DevBuf pyr[3];     // storage of L[0], L[1], R
+    DevBuf staging;    // raw input images when pushed from the host
+};
+
+#define SVS_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);            \
+            return SVS_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+#define SVS_FAIL(ctx, code, msg)                                                         \
+    do { (ctx)->err = (msg); return (code); } while (0)
+#define SVS_TRY(call)                                                                    \
+    do { int r__ = (call); if (r__ != SVS_OK) return r__; } while (0)
+#define SVS_LAUNCH_CHECK(ctx)                                                            \
+    do { (ctx)->launches++; SVS_CUDA(ctx, cudaGetLastError()); } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- internal device-level entry points (all asynchronous on ctx->stream) ----
+// images.cu
+int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t *bytes_per_image);
+int svs_i_half_nearest(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
+                       int n, uint8_t *dst_dev, int dw, int dh, int dst_stride, size_t dst_img_pitch);
+int svs_i_copy_level0(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
+                      int n, const PyrDesc &d);
+int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images);
+// gftt.cu
+int svs_i_gftt(svs_ctx *c, const uint8_t *img_dev, int w, int h, int stride, size_t img_pitch, int n_img,
+               const int32_t *img_ids_dev /* may be null: identity */,
+               const uint8_t *mask_dev /* n_img*h*w or null */,
+               const int32_t *occ_off_dev, const float *occ_xy_dev /* or null */, int n_occ_total,
+               int max_corners, double quality, double min_distance, int granule,
+               float *out_xy_dev, float *out_resp_dev, int32_t *out_n_dev, float *eig_out_dev /* optional */);
+// lk.cu
+int svs_i_lk(svs_ctx *c, const PyrDesc &prev, const PyrDesc &next, const int32_t *pt_img_dev /* per point */,
+             const float *prev_xy_dev, float *next_xy_dev, int n_pts, int win, int max_iter, double eps,
+             uint8_t *status_dev);

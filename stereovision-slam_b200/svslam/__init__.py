@@ -1,0 +1,227 @@
+"""Python binding (ctypes) of the C ABI in include/svslam.h.
+
+This is plumbing for tests and bench.py: NumPy arrays in, NumPy arrays out, every call goes
+straight into libsvslam.so (hand-written sm_100a CUDA).  There is no CPU fallback: if the shared
+library is missing or no B200 is visible, construction raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_ROOT, "libsvslam.so")
+_lib = None
+
+
+class SvsError(RuntimeError):
+    pass
+
+
+class LmStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("trials", C.c_int32), ("linearizations", C.c_int32),
+                ("solves", C.c_int32), ("lambda_", C.c_double), ("chi2", C.c_double)]
+
+
+class BaStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("trials", C.c_int32), ("linearizations", C.c_int32),
+                ("solves", C.c_int32), ("lambda_", C.c_double), ("chi2", C.c_double),
+                ("chi2_init", C.c_double)]
+
+
+def load_library():
+    """dlopen libsvslam.so (no device needed).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SvsError("libsvslam.so is not built (run `python stereovision-slam_b200/build.py`); "
+                       "there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.svs_create.restype = C.c_void_p
+    lib.svs_create.argtypes = [C.c_int]
+    lib.svs_create_error.restype = C.c_char_p
+    lib.svs_last_error.restype = C.c_char_p
+    lib.svs_last_error.argtypes = [C.c_void_p]
+    lib.svs_destroy.argtypes = [C.c_void_p]
+    lib.svs_stream.restype = C.c_void_p
+    lib.svs_stream.argtypes = [C.c_void_p]
+    lib.svs_launch_count.restype = C.c_longlong
+    lib.svs_launch_count.argtypes = [C.c_void_p]
+    lib.svs_host_alloc.restype = C.c_void_p
+    lib.svs_host_alloc.argtypes = [C.c_size_t]
+    lib.svs_host_free.argtypes = [C.c_void_p]
+    lib.svs_frameset_create.restype = C.c_void_p
+    lib.svs_frameset_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+class FrameSet:
+    def __init__(self, ctx, n_streams, in_w, in_h, half=True, lk_win=11, lk_max_level=3):
+        self.ctx = ctx
+        self.h = ctx.lib.svs_frameset_create(ctx.h, n_streams, in_w, in_h, int(bool(half)), lk_win, lk_max_level)
+        if not self.h:
+            raise SvsError(ctx.last_error())
+        w, hh, nl = C.c_int(), C.c_int(), C.c_int()
+        ctx.lib.svs_frameset_size(C.c_void_p(self.h), C.byref(w), C.byref(hh), C.byref(nl))
+        self.n_streams, self.in_w, self.in_h = n_streams, in_w, in_h
+        self.w, self.hgt, self.n_levels = w.value, hh.value, nl.value
+
+    def push(self, left, right):
+        """left/right: uint8 [n_streams, in_h, in_w] host arrays."""
+        left, right = _u8(left), _u8(right)
+        assert left.shape == (self.n_streams, self.in_h, self.in_w) == right.shape
+        self.ctx._chk(self.ctx.lib.svs_frameset_push(
+            C.c_void_p(self.ctx.h), C.c_void_p(self.h), _p(left), _p(right), C.c_size_t(self.in_w),
+            C.c_size_t(self.in_w * self.in_h), 0))
+
+    def push_ptr(self, left_ptr, right_ptr, on_device):
+        self.ctx._chk(self.ctx.lib.svs_frameset_push(
+            C.c_void_p(self.ctx.h), C.c_void_p(self.h), C.c_void_p(left_ptr), C.c_void_p(right_ptr),
+            C.c_size_t(self.in_w), C.c_size_t(self.in_w * self.in_h), int(on_device)))
+
+    def download(self, stream, which, level):
+        w, h = self.w, self.hgt
+        for _ in range(level):
+            w, h = (w + 1) // 2, (h + 1) // 2
+        out = np.zeros((h, w), np.uint8)
+        self.ctx._chk(self.ctx.lib.svs_frameset_download(
+            C.c_void_p(self.ctx.h), C.c_void_p(self.h), stream, which, level, _p(out), w))
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.svs_frameset_destroy(C.c_void_p(self.ctx.h), C.c_void_p(self.h))
+            self.h = None
+
+
+class Context:
+    """One svs_ctx (one CUDA stream).  Raises SvsError when no B200 is available."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = self.lib.svs_create(device)
+        if not self.h:
+            raise SvsError("svs_create failed: " + self.lib.svs_create_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.svs_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def last_error(self):
+        return self.lib.svs_last_error(C.c_void_p(self.h)).decode()
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise SvsError("svs error %d: %s" % (rc, self.last_error()))
+
+    def sync(self):
+        self._chk(self.lib.svs_sync(C.c_void_p(self.h)))
+
+    def stream_ptr(self):
+        return self.lib.svs_stream(C.c_void_p(self.h))
+
+    def launch_count(self):
+        return int(self.lib.svs_launch_count(C.c_void_p(self.h)))
+
+    def frameset(self, *a, **k):
+        return FrameSet(self, *a, **k)
+
+    # ---- a0
+    def half_nearest(self, imgs):
+        imgs = _u8(imgs)
+        single = imgs.ndim == 2
+        if single:
+            imgs = imgs[None]
+        n, h, w = imgs.shape
+        dw, dh = int(np.rint(w * 0.5)), int(np.rint(h * 0.5))
+        out = np.zeros((n, dh, dw), np.uint8)
+        self._chk(self.lib.svs_half_nearest(C.c_void_p(self.h), _p(imgs), w, h, w, n, C.c_size_t(w * h), _p(out)))
+        return out[0] if single else out
+
+    # ---- a1
+    def corner_min_eig(self, img, granule=32):
+        img = _u8(img)
+        h, w = img.shape
+        out = np.zeros((h, w), np.float32)
+        self._chk(self.lib.svs_corner_min_eig(C.c_void_p(self.h), _p(img), w, h, w, granule, _p(out)))
+        return out
+
+    def gftt_detect(self, img, mask=None, occupied_xy=None, max_corners=150, quality=0.01, min_distance=20.0,
+                    granule=32):
+        img = _u8(img)
+        h, w = img.shape
+        m = _u8(mask) if mask is not None else None
+        occ = _f32(occupied_xy).reshape(-1, 2) if occupied_xy is not None else None
+        xy = np.zeros((max_corners, 2), np.float32)
+        resp = np.zeros(max_corners, np.float32)
+        n = C.c_int(0)
+        self._chk(self.lib.svs_gftt_detect(
+            C.c_void_p(self.h), _p(img), w, h, w, _p(m), w, _p(occ), 0 if occ is None else len(occ), max_corners,
+            C.c_double(quality), C.c_double(min_distance), granule, _p(xy), _p(resp), C.byref(n)))
+        return xy[:n.value].copy(), resp[:n.value].copy()
+
+    def gftt_detect_batch(self, fs, stream_ids, occupied, max_corners=150, quality=0.01, min_distance=20.0,
+                          granule=32):
+        """occupied: list (per selected stream) of [k,2] float arrays.  Returns list of (xy, resp)."""
+        ids = _i32(stream_ids)
+        n_sel = len(ids)
+        off = np.zeros(n_sel + 1, np.int32)
+        for i, o in enumerate(occupied):
+            off[i + 1] = off[i] + len(o)
+        occ = _f32(np.concatenate([np.asarray(o, np.float32).reshape(-1, 2) for o in occupied])
+                   if off[-1] > 0 else np.zeros((0, 2), np.float32))
+        xy = np.zeros((n_sel, max_corners, 2), np.float32)
+        resp = np.zeros((n_sel, max_corners), np.float32)
+        n = np.zeros(n_sel, np.int32)
+        self._chk(self.lib.svs_gftt_detect_batch(
+            C.c_void_p(self.h), C.c_void_p(fs.h), _p(ids), n_sel, _p(off), _p(occ), max_corners, C.c_double(quality),
+            C.c_double(min_distance), granule, _p(xy), _p(resp), _p(n)))
+        return [(xy[i, :n[i]].copy(), resp[i, :n[i]].copy()) for i in range(n_sel)]
+
+    # ---- a2 / a3
+    def lk_track(self, prev, nxt, prev_xy, init_xy, win=11, max_level=3, max_iter=30, eps=0.01):
+        prev, nxt = _u8(prev), _u8(nxt)
+        h, w = prev.shape
+        pxy = _f32(prev_xy).reshape(-1, 2)
+        nxy = np.array(init_xy, np.float32).reshape(-1, 2).copy()
+        st = np.zeros(len(pxy), np.uint8)
+        self._chk(self.lib.svs_lk_track(C.c_void_p(self.h), _p(prev), _p(nxt), w, h, w, _p(pxy), _p(nxy), len(pxy),
+                                        win, max_level, max_iter, C.c_double(eps), _p(st)))
+        return nxy, st
+
+    def lk_track_batch(self, fs, pair, prev_list, init_list, max_iter=30, eps=0.01):
+        off = np.zeros(fs.n_streams + 1, np.int32)
+        for i, p in enumerate(prev_list):
+            off[i + 1] = off[i] + len(p)
+        tot = int(off[-1])
+        pxy = _f32(np.concatenate([np.asarray(p, np.float32).reshape(-1, 2) for p in prev_list])) if tot else np.zeros((0, 2), np.float32)
+        nxy = np.array(np.concatenate([np.asarray(p, np.float32).reshape(-1, 2) for p in init_list]), np.float32) if tot else np.zeros((0, 2), np.float32)
+        st = np.zeros(max(tot, 1), np.uint8)
+        self._chk(self.lib.svs_lk_track_batch(C.c_void_p(self.h), C.c_void_p(fs.h), pair, _p(off), _p(pxy), _p(nxy),
+                                              max_iter, C.c_double(eps), _p(st)))
+        return [(nxy[off[i]:off[i + 1]].copy(), st[off[i]:off[i + 1]].copy()) for i in range(fs.n_streams)]

@@ -1,0 +1,137 @@
+"""GPU parity for the image stages (rows a0, a1, a2/a3) through the C ABI, against the CPU oracle
+and — where the third-party routine is importable — against cv2 itself."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import cv_stages as o
+from oracle import geom
+from util import texture, moved_pair, lk_points
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("h,w", [(376, 1241), (370, 1226), (47, 100), (65, 333), (6, 7)])
+def test_half_nearest(ctx, h, w):
+    imgs = np.stack([texture(h, w, s, rects=3) for s in range(3)])
+    got = ctx.half_nearest(imgs)
+    for i in range(3):
+        assert np.array_equal(got[i], o.half_nearest(imgs[i]))
+        assert np.array_equal(got[i], cv2.resize(imgs[i], None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST))
+
+
+@pytest.mark.parametrize("h,w", [(188, 620), (185, 613), (47, 100), (64, 333), (376, 1241), (3, 3), (5, 29)])
+@pytest.mark.parametrize("g", [None, 0, 16])
+def test_min_eig_bit_exact(ctx, granule, h, w, g):
+    gg = granule if g is None else g
+    img = texture(h, w, h + w, rects=5)
+    got = ctx.corner_min_eig(img, gg)
+    want = o.min_eig_map(img, gg)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    if g is None:
+        assert np.array_equal(got.view(np.uint32), cv2.cornerMinEigenVal(img, 3, ksize=3).view(np.uint32))
+
+
+@pytest.mark.parametrize("h,w", [(188, 620), (185, 613), (376, 1241)])
+@pytest.mark.parametrize("min_dist,n", [(20, 150), (5, 2000), (1.4, 500), (0.5, 300), (7.3, 400)])
+def test_gftt_identical(ctx, granule, h, w, min_dist, n):
+    img = texture(h, w, 7)
+    rng = np.random.RandomState(7)
+    pts = np.stack([rng.rand(40) * w, rng.rand(40) * h], 1).astype(np.float32)
+    pts[0] = (0.5, 0.5); pts[1] = (w - 1, h - 1); pts[2] = (w + 30, 5); pts[3] = (10.5, 20.5)
+    mask = o.feature_mask((h, w), pts)
+    # (1) mask given as box centres (the drop-in form), (2) mask given as an image
+    xy1, r1 = ctx.gftt_detect(img, occupied_xy=pts, max_corners=n, min_distance=min_dist, granule=granule)
+    xy2, r2 = ctx.gftt_detect(img, mask=mask, max_corners=n, min_distance=min_dist, granule=granule)
+    wxy, wr = o.gftt_detect(img, mask, n, 0.01, min_dist, granule)
+    assert len(wxy) > 0
+    assert np.array_equal(xy1, wxy) and np.array_equal(r1, wr)
+    assert np.array_equal(xy2, wxy) and np.array_equal(r2, wr)
+    kps = cv2.GFTTDetector_create(n, 0.01, min_dist).detect(img, mask)
+    assert np.array_equal(np.array([k.pt for k in kps], np.float32).reshape(-1, 2), xy1)
+    assert np.array_equal(np.array([k.response for k in kps], np.float32), r1)
+
+
+def test_gftt_edge_cases(ctx, granule):
+    img = texture(64, 100, 2)
+    xy, _ = ctx.gftt_detect(img, mask=np.zeros((64, 100), np.uint8), max_corners=50, granule=granule)
+    assert len(xy) == 0                                   # everything masked
+    flat = np.full((40, 60), 77, np.uint8)
+    xy, _ = ctx.gftt_detect(flat, max_corners=50, granule=granule)
+    assert len(xy) == len(o.gftt_detect(flat, None, 50, 0.01, 20, granule)[0]) == 0
+    noise = np.random.RandomState(0).randint(0, 256, (120, 160), np.uint8)   # many candidates
+    xy, r = ctx.gftt_detect(noise, max_corners=5000, min_distance=2, granule=granule)
+    wxy, wr = o.gftt_detect(noise, None, 5000, 0.01, 2, granule)
+    assert np.array_equal(xy, wxy) and np.array_equal(r, wr)
+    big_noise = np.random.RandomState(1).randint(0, 256, (376, 1241), np.uint8)   # > smem sort capacity
+    xy, r = ctx.gftt_detect(big_noise, max_corners=3000, min_distance=3, granule=granule)
+    wxy, wr = o.gftt_detect(big_noise, None, 3000, 0.01, 3, granule)
+    assert np.array_equal(xy, wxy) and np.array_equal(r, wr)
+
+
+def test_frameset_pyramids_and_batched_gftt(ctx, granule):
+    B, H, W = 5, 370, 1226
+    left = np.stack([texture(H, W, 10 + s) for s in range(B)])
+    right = np.stack([texture(H, W, 20 + s) for s in range(B)])
+    fs = ctx.frameset(B, W, H, half=True)
+    try:
+        fs.push(left, right)
+        assert (fs.w, fs.hgt, fs.n_levels) == (613, 185, 4)
+        for b in (0, B - 1):
+            for which, src in ((0, left), (2, right)):
+                pyr = o.build_pyramid(o.half_nearest(src[b]))
+                for lvl in range(4):
+                    assert np.array_equal(fs.download(b, which, lvl), pyr[lvl]), (b, which, lvl)
+        left2 = np.stack([texture(H, W, 30 + s) for s in range(B)])
+        fs.push(left2, right)
+        assert np.array_equal(fs.download(1, 1, 2), o.build_pyramid(o.half_nearest(left[1]))[2])   # previous
+        assert np.array_equal(fs.download(1, 0, 0), o.half_nearest(left2[1]))                        # current
+        rng = np.random.RandomState(3)
+        sel = [3, 0, 4]
+        occ = [np.stack([rng.rand(k) * 613, rng.rand(k) * 185], 1).astype(np.float32) for k in (25, 0, 60)]
+        res = ctx.gftt_detect_batch(fs, sel, occ, max_corners=150, granule=granule)
+        for (xy, r), s, oc in zip(res, sel, occ):
+            img = o.half_nearest(left2[s])
+            wxy, wr = o.gftt_detect(img, o.feature_mask(img.shape, oc), 150, 0.01, 20, granule)
+            assert np.array_equal(xy, wxy) and np.array_equal(r, wr)
+    finally:
+        fs.close()
+
+
+@pytest.mark.parametrize("h,w,seed", [(188, 620, 1), (185, 613, 2), (376, 1241, 3), (30, 40, 4)])
+def test_lk_bit_identical_to_oracle(ctx, h, w, seed):
+    a, b = moved_pair(h, w, seed)
+    p0, init = lk_points(a, 5) if h > 40 else (np.array([[10, 10], [20, 15], [35, 25], [5, 28]], np.float32),
+                                               np.array([[11, 11], [21, 16], [36, 26], [6, 29]], np.float32))
+    q, s = ctx.lk_track(a, b, p0, init)
+    wq, ws, _ = geom.lk_track(o.build_pyramid(a), o.build_pyramid(b), p0, init)
+    assert np.array_equal(s, ws)
+    assert np.array_equal(q.view(np.uint32), wq.view(np.uint32))        # integer-exact restatement: bit-identical
+    p1, st, _ = cv2.calcOpticalFlowPyrLK(a, b, p0, init.copy(), winSize=(11, 11), maxLevel=3,
+                                         criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01),
+                                         flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+    assert np.array_equal(st.ravel(), s)
+    ok = s == 1
+    assert np.abs(p1[ok] - q[ok]).max() < 1e-3       # cv2 sums the same integers in f32 lanes
+
+
+def test_lk_batch_pairs(ctx):
+    B, H, W = 3, 188, 620
+    frames = [moved_pair(H, W, 40 + s) for s in range(B)]
+    rights = [moved_pair(H, W, 40 + s)[0][:, ::1] for s in range(B)]
+    fs = ctx.frameset(B, W, H, half=False)
+    try:
+        fs.push(np.stack([f[0] for f in frames]), np.stack(rights))
+        fs.push(np.stack([f[1] for f in frames]), np.stack([np.roll(f[1], -4, 1) for f in frames]))
+        pts = [lk_points(f[0], 5, n_corner=50 + 40 * i, n_rand=10) for i, f in enumerate(frames)]
+        pts[1] = (pts[1][0][:0], pts[1][1][:0])      # a stream with no points
+        res = ctx.lk_track_batch(fs, 0, [p[0] for p in pts], [p[1] for p in pts])
+        for (q, s), f, p in zip(res, frames, pts):
+            wq, ws, _ = geom.lk_track(o.build_pyramid(f[0]), o.build_pyramid(f[1]), p[0], p[1])
+            assert np.array_equal(s, ws) and np.array_equal(q.view(np.uint32), wq.view(np.uint32))
+        res = ctx.lk_track_batch(fs, 1, [p[0] for p in pts], [p[0] for p in pts])     # left -> right
+        for (q, s), f, p in zip(res, frames, pts):
+            wq, ws, _ = geom.lk_track(o.build_pyramid(f[1]), o.build_pyramid(np.roll(f[1], -4, 1)), p[0], p[0])
+            assert np.array_equal(s, ws) and np.array_equal(q.view(np.uint32), wq.view(np.uint32))
+    finally:
+        fs.close()
