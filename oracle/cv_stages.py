@@ -16,6 +16,8 @@ tests/test_oracle_cv.py, with the reference's exact arguments:
 * feature_mask      <- cv::rectangle mask of tracked features     src/frontend.cpp:42-47
 * pyr_down          <- cv::pyrDown inside calcOpticalFlowPyrLK    src/frontend.cpp:105,353
 * stereo_bm         <- cv::StereoBM(128,15)::compute              src/dense_reconstruction.cpp:89,114
+* bgr2gray          <- cv::cvtColor(BGR2GRAY)                    src/dense_reconstruction.cpp:111-113
+* backproject       <- disparity -> depth -> pixel2world loop    src/dense_reconstruction.cpp:116-173
 
 (LK itself, triangulation, pose-only LM and BA are restated in oracle/geom.c.)
 """
@@ -326,3 +328,31 @@ def stereo_bm(left, right, ndisp=128, block=15, cap=31, texture=10, uniq=15):
     val = (((ndisp - 1 - mind) * 256 + q + 15) >> 4).astype(np.int16)
     disp[y_lo:y_hi, x_lo:x_hi] = np.where(valid, val, np.int16(-16))
     return disp
+
+
+def bgr2gray(bgr):
+    """cv::cvtColor(BGR2GRAY) for 8-bit images (src/dense_reconstruction.cpp:111-113): fixed point, shift 15."""
+    b, g, r = (bgr[..., i].astype(np.int64) for i in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def backproject(disp16, bgr, K4, baseline, cam_pose_inv, T_cw, se3_act, se3_inv):
+    """src/dense_reconstruction.cpp:116-173: disparity/16 (f32) -> depth = fx*b/d (f32) -> for x outer, y inner,
+    every pixel with depth >= 1: Camera::pixel2world (src/camera.cpp:58-86) in f64, stored as f32 + RGB."""
+    h, w = disp16.shape
+    d = disp16.astype(F32) * F32(1.0 / 16.0)
+    fb = F32(F32(K4[0]) * F32(baseline))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        z = np.where(d > 0, (fb / np.where(d > 0, d, F32(1))).astype(F32), F32(0))
+    Twc = se3_inv(T_cw)
+    pts, cols = [], []
+    for x in range(w):
+        for y in range(h):
+            if z[y, x] < 1:
+                continue
+            depth = float(z[y, x])
+            pc = np.array([(x - K4[2]) * depth / K4[0], (y - K4[3]) * depth / K4[1], depth])
+            pw = se3_act(Twc, se3_act(cam_pose_inv, pc))
+            pts.append(pw.astype(F32))
+            cols.append(bgr[y, x, ::-1])
+    return (np.asarray(pts, F32).reshape(-1, 3), np.asarray(cols, np.uint8).reshape(-1, 3))

@@ -1,0 +1,630 @@
+// Sliding-window bundle adjustment (row a7): the g2o block of Backend::Optimize, reference
+// src/backend.cpp:22-164 — VertexPose per keyframe, marginalised VertexXYZ per landmark, EdgeProjection
+// (include/StereoVisionSLAM/g2o_types.h:176-229) per observation, Huber(delta), Levenberg-Marquardt with Schur
+// complement and a dense pivoted LDLT of the reduced 6N x 6N camera system, no vertex fixed.
+// Solver semantics: SURVEY.md Appendix B (upstream g2o; un-vendored, parity unpinned).
+//
+// k_ba_window: ONE persistent CTA per window problem runs the whole LM loop on-device (no host round trips):
+//   linearise   landmark-parallel: residuals, 2x6 / 2x3 Jacobian blocks, Huber weights -> Hll (3x3), bl, Hpl (6x3/edge)
+//               pose-parallel (warp per keyframe, butterfly reduction) -> Hpp (6x6), bp
+//   schur       landmark-parallel V^-1 = (Hll + lambda I)^-1, W V^-1 per edge; then every 6x6 block (i,j) of the
+//               reduced system is OWNED by 36 threads that sum their precomputed (edge,edge) pair list in a fixed
+//               order -> no atomics, bitwise deterministic
+//   solve       pivoted LDLT (Eigen::LDLT order of operations) in shared memory, 4 lanes per row
+//   back-subst  landmark-parallel; trial chi2; g2o's rho test / lambda schedule on thread 0
+// The reduced system lives in shared memory (<= ~200 KB, i.e. N <= 26 keyframes); larger windows fall back
+// to an L2-resident global buffer through the same code path.
+#include "svs_internal.h"
+#include "geom_dev.cuh"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+struct BaProb {
+    int NA, L, E, nblk;
+    int pose0;      // first pose (global index into poses[7*])
+    int act0;       // act_pose[act0 + a] = local keyframe index of active pose a
+    int lm0, e0;    // first landmark / edge (global)
+    int loff0;      // l_off[loff0 + l .. ] (L+1 entries), values relative to e0
+    int poff0;      // p_off[poff0 + a ..] (NA+1 entries), values relative to e0
+    int blk0;       // blk_i/blk_j/blk_off[blk0 + b] ; blk_off has nblk+1 entries at blk0 + prob index shift (see host)
+    int boff0;
+    int pair0;      // pair_e1/pair_e2[pair0 + ...], values are edge indices relative to e0
+    long long S_off;  // offset (doubles) into the global reduced-system scratch, or -1 when it fits shared memory
+};
+
+struct BaArgs {
+    const BaProb *probs;
+    double *poses, *lms;            // in/out
+    const int32_t *act_pose;
+    const int32_t *edge_p, *edge_l; // compact active-pose index, local landmark index
+    const uint8_t *edge_cam;
+    const double *edge_uv;
+    const int32_t *l_off, *l_edges, *p_off, *p_edges;
+    const int32_t *blk_i, *blk_j, *blk_off, *pair_e1, *pair_e2;
+    double *Hpl, *WD;               // 18 / edge
+    double *Hll, *Dinv;             // 9 / landmark
+    double *bl, *xl, *lmT;          // 3 / landmark
+    double *S_glob;
+    double *edge_chi2;
+    svs_ba_stats *stats;
+    double K[2][4], ext[2][7];
+    double huber_delta;
+    int max_iter, jac_mode;
+};
+
+#define BA_T 256
+
+__device__ __forceinline__ double block_sum(double v, double *red)
+{   // deterministic tree reduction; result broadcast to all threads
+    int tid = threadIdx.x;
+    red[tid] = v;
+    __syncthreads();
+    for (int s = BA_T / 2; s > 0; s >>= 1) {
+        if (tid < s) red[tid] += red[tid + s];
+        __syncthreads();
+    }
+    double r = red[0];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double *red)
+{
+    int tid = threadIdx.x;
+    red[tid] = v;
+    __syncthreads();
+    for (int s = BA_T / 2; s > 0; s >>= 1) {
+        if (tid < s) red[tid] = fmax(red[tid], red[tid + s]);
+        __syncthreads();
+    }
+    double r = red[0];
+    __syncthreads();
+    return r;
+}
+
+// Pivoted LDLT of the symmetric n x n matrix S (lower triangle used, row pitch `pitch`), then solve S x = g.
+// Returns Eigen::LDLT::isPositive().  All threads of the CTA must call it.
+__device__ bool block_ldlt_solve(double *S, int pitch, int n, const double *g, double *x, int *tr, double *tmp, int *s_piv)
+{
+    int tid = threadIdx.x, lane = tid & 31;
+    int sign = 0;
+    for (int k = 0; k < n; k++) {
+        if (tid < 32) {
+            double best = -1.0;
+            int bi = k;
+            for (int i = k + lane; i < n; i += 32) { double v = fabs(S[i * pitch + i]); if (v > best) { best = v; bi = i; } }
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { *s_piv = bi; tr[k] = bi; }
+        }
+        __syncthreads();
+        int piv = *s_piv;
+        if (piv != k) {
+            // disjoint element swaps: [0,k) row part, (piv,n) column part, (k,piv) cross part, diagonal
+            for (int t = tid; t < n + 1; t += BA_T) {
+                if (t < k) { double a = S[k * pitch + t]; S[k * pitch + t] = S[piv * pitch + t]; S[piv * pitch + t] = a; }
+                else if (t == k) { double a = S[k * pitch + k]; S[k * pitch + k] = S[piv * pitch + piv]; S[piv * pitch + piv] = a; }
+                else if (t < piv) { double a = S[t * pitch + k]; S[t * pitch + k] = S[piv * pitch + t]; S[piv * pitch + t] = a; }
+                else if (t > piv && t < n) { double a = S[t * pitch + k]; S[t * pitch + k] = S[t * pitch + piv]; S[t * pitch + piv] = a; }
+            }
+            __syncthreads();
+        }
+        for (int j = tid; j < k; j += BA_T) tmp[j] = S[j * pitch + j] * S[k * pitch + j];
+        __syncthreads();
+        if (k > 0) {
+            // 4 lanes per row: interleaved partial dot products combined in a fixed order
+            int sub = tid & 3;
+            int trips = (n - k + (BA_T >> 2) - 1) / (BA_T >> 2);   // uniform trip count (shuffles below)
+            for (int m = 0; m < trips; m++) {
+                int i = k + (tid >> 2) + m * (BA_T >> 2);
+                double acc = 0;
+                if (i < n) for (int j = sub; j < k; j += 4) acc += S[i * pitch + j] * tmp[j];
+                double a1 = __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += a1;
+                double a2 = __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += a2;
+                if (i < n && sub == 0) S[i * pitch + k] -= acc;
+            }
+            __syncthreads();
+        }
+        double akk = S[k * pitch + k];
+        bool valid = fabs(akk) > 0.0;
+        if (k == 0 && !valid) { for (int j = tid; j < n; j += BA_T) tr[j] = j; sign = 0; __syncthreads(); break; }
+        if (valid) for (int i = k + 1 + tid; i < n; i += BA_T) S[i * pitch + k] /= akk;
+        if (sign == 1) { if (akk < 0) sign = 2; }
+        else if (sign == -1) { if (akk > 0) sign = 2; }
+        else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = -1; }
+        __syncthreads();
+    }
+    bool ok = (sign == 1 || sign == 0);
+    if (ok && tid < 32) {   // triangular solves on one warp (column-oriented = same rounding as the row-oriented loop)
+        for (int i = lane; i < n; i += 32) x[i] = g[i];
+        __syncwarp();
+        if (lane == 0) for (int k = 0; k < n; k++) if (tr[k] != k) { double t = x[k]; x[k] = x[tr[k]]; x[tr[k]] = t; }
+        __syncwarp();
+        for (int i = 0; i < n; i++) {
+            double xi = x[i];
+            for (int j = i + 1 + lane; j < n; j += 32) x[j] -= S[j * pitch + i] * xi;
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) { double d = S[i * pitch + i]; x[i] = (fabs(d) > DBL_MIN) ? x[i] / d : 0.0; }
+        __syncwarp();
+        for (int i = n - 1; i >= 0; i--) {
+            double xi = x[i];
+            for (int j = lane; j < i; j += 32) x[j] -= S[i * pitch + j] * xi;
+            __syncwarp();
+        }
+        if (lane == 0) for (int k = n - 1; k >= 0; k--) if (tr[k] != k) { double t = x[k]; x[k] = x[tr[k]]; x[tr[k]] = t; }
+    }
+    __syncthreads();
+    return ok;
+}
+
+__global__ void __launch_bounds__(BA_T)
+k_ba_window(BaArgs A)
+{
+    extern __shared__ double smd[];
+    const BaProb P = A.probs[blockIdx.x];
+    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NA = P.NA, L = P.L, E = P.E, np = 6 * NA, pitch = np | 1;
+    // ---- shared memory carve-up
+    double *red = smd;                       // BA_T
+    double *poseA = red + BA_T;              // 7*NA accepted
+    double *poseT = poseA + 7 * NA;          // 7*NA trial
+    double *Hpp = poseT + 7 * NA;            // 36*NA
+    double *bp = Hpp + 36 * NA;              // np
+    double *g = bp + np;                     // np
+    double *xp = g + np;                     // np
+    double *tmp = xp + np;                   // np
+    int *tr = reinterpret_cast<int *>(tmp + np);   // np ints
+    double *Ssm = reinterpret_cast<double *>(tr + ((np + 1) & ~1));
+    double *S = (P.S_off >= 0) ? A.S_glob + P.S_off : Ssm;
+    __shared__ int s_piv, s_flag, s_q;
+    __shared__ double s_lambda, s_ni, s_cur, s_rho;
+
+    const int32_t *l_off = A.l_off + P.loff0, *l_edges = A.l_edges + P.e0;
+    const int32_t *p_off = A.p_off + P.poff0, *p_edges = A.p_edges + P.e0;
+    const int32_t *edge_p = A.edge_p + P.e0, *edge_l = A.edge_l + P.e0;
+    const uint8_t *edge_cam = A.edge_cam + P.e0;
+    const double *edge_uv = A.edge_uv + 2 * (size_t)P.e0;
+    double *lms = A.lms + 3 * (size_t)P.lm0, *lmT = A.lmT + 3 * (size_t)P.lm0;
+    double *Hll = A.Hll + 9 * (size_t)P.lm0, *Dinv = A.Dinv + 9 * (size_t)P.lm0;
+    double *bl = A.bl + 3 * (size_t)P.lm0, *xl = A.xl + 3 * (size_t)P.lm0;
+    double *Hpl = A.Hpl + 18 * (size_t)P.e0, *WD = A.WD + 18 * (size_t)P.e0;
+    const double hd = A.huber_delta;
+
+    for (int i = tid; i < 7 * NA; i += BA_T) {
+        int a = i / 7;
+        double v = A.poses[7 * (size_t)(P.pose0 + A.act_pose[P.act0 + a]) + (i - 7 * a)];
+        poseA[i] = v; poseT[i] = v;
+    }
+    for (int i = tid; i < 3 * L; i += BA_T) lmT[i] = lms[i];
+    __syncthreads();
+
+    // robust chi2 of a state (poses in shared memory, landmarks in global)
+    auto chi2_of = [&](const double *pz, const double *lz) -> double {
+        double acc = 0;
+        for (int l = tid; l < L; l += BA_T) {
+            for (int s = l_off[l]; s < l_off[l + 1]; s++) {
+                int e = l_edges[s], cam = edge_cam[e];
+                double er[2], a[3], c[3];
+                gd::ba_error(pz + 7 * edge_p[e], A.ext[cam], A.K[cam], lz + 3 * l, edge_uv + 2 * e, er, a, c);
+                double e2 = er[0] * er[0] + er[1] * er[1], r0, r1;
+                gd::huber(e2, hd, r0, r1);
+                acc += r0;
+            }
+        }
+        return block_sum(acc, red);
+    };
+
+    int st_it = 0, st_tr = 0, st_lin = 0, st_sol = 0;
+    double chi_init = 0;
+    if (tid == 0) { s_lambda = 0; s_ni = 2; }
+    bool stop = (E == 0 || NA == 0);
+    for (int it = 0; it < A.max_iter && !stop; it++) {
+        // ================= linearise at the accepted state =================
+        double acc = 0;
+        for (int l = tid; l < L; l += BA_T) {
+            int s0 = l_off[l], s1 = l_off[l + 1];
+            if (s0 == s1) continue;
+            double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b3[3] = {0, 0, 0};
+            const double *pl = lms + 3 * l;
+            for (int s = s0; s < s1; s++) {
+                int e = l_edges[s], cam = edge_cam[e];
+                const double *T = poseA + 7 * edge_p[e];
+                double er[2], a[3], c[3], Jp[12], Jl[6];
+                gd::ba_error(T, A.ext[cam], A.K[cam], pl, edge_uv + 2 * e, er, a, c);
+                if (A.jac_mode == 1) gd::ba_jac_numeric(T, A.ext[cam], A.K[cam], pl, edge_uv + 2 * e, Jp, Jl);
+                else gd::ba_jac_analytic(T, A.ext[cam], A.K[cam], a, c, Jp, Jl);
+                double e2 = er[0] * er[0] + er[1] * er[1], r0, r1;
+                gd::huber(e2, hd, r0, r1);
+                acc += r0;
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                    b3[x] -= r1 * (Jl[x] * er[0] + Jl[3 + x] * er[1]);
+#pragma unroll
+                    for (int y = 0; y < 3; y++) H[x * 3 + y] += r1 * (Jl[x] * Jl[y] + Jl[3 + x] * Jl[3 + y]);
+                }
+                double *W = Hpl + 18 * (size_t)e;
+#pragma unroll
+                for (int x = 0; x < 6; x++)
+#pragma unroll
+                    for (int y = 0; y < 3; y++) W[x * 3 + y] = r1 * (Jp[x] * Jl[y] + Jp[6 + x] * Jl[3 + y]);
+            }
+#pragma unroll
+            for (int x = 0; x < 9; x++) Hll[9 * (size_t)l + x] = H[x];
+#pragma unroll
+            for (int x = 0; x < 3; x++) bl[3 * (size_t)l + x] = b3[x];
+        }
+        double cur = block_sum(acc, red);
+        if (it == 0) chi_init = cur;
+        for (int a = warp; a < NA; a += BA_T / 32) {
+            double H[21], b6[6];
+#pragma unroll
+            for (int x = 0; x < 21; x++) H[x] = 0;
+#pragma unroll
+            for (int x = 0; x < 6; x++) b6[x] = 0;
+            const double *T = poseA + 7 * a;
+            for (int s = p_off[a] + lane; s < p_off[a + 1]; s += 32) {
+                int e = p_edges[s], cam = edge_cam[e];
+                const double *pl = lms + 3 * (size_t)edge_l[e];
+                double er[2], aa[3], c[3], Jp[12], Jl[6];
+                gd::ba_error(T, A.ext[cam], A.K[cam], pl, edge_uv + 2 * e, er, aa, c);
+                if (A.jac_mode == 1) gd::ba_jac_numeric(T, A.ext[cam], A.K[cam], pl, edge_uv + 2 * e, Jp, Jl);
+                else gd::ba_jac_analytic(T, A.ext[cam], A.K[cam], aa, c, Jp, Jl);
+                double e2 = er[0] * er[0] + er[1] * er[1], r0, r1;
+                gd::huber(e2, hd, r0, r1);
+                int k = 0;
+#pragma unroll
+                for (int x = 0; x < 6; x++) {
+                    b6[x] -= r1 * (Jp[x] * er[0] + Jp[6 + x] * er[1]);
+#pragma unroll
+                    for (int y = x; y < 6; y++) H[k++] += r1 * (Jp[x] * Jp[y] + Jp[6 + x] * Jp[6 + y]);
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 21; x++) H[x] = gd::warp_sum(H[x]);
+#pragma unroll
+            for (int x = 0; x < 6; x++) b6[x] = gd::warp_sum(b6[x]);
+            if (lane == 0) {
+                int k = 0;
+#pragma unroll
+                for (int x = 0; x < 6; x++) {
+                    bp[6 * a + x] = b6[x];
+#pragma unroll
+                    for (int y = x; y < 6; y++) { Hpp[36 * a + x * 6 + y] = H[k]; Hpp[36 * a + y * 6 + x] = H[k]; k++; }
+                }
+            }
+        }
+        __syncthreads();
+        st_lin++;
+        if (it == 0) {   // lambda_init = tau * max diagonal over all active vertices
+            double md = 0;
+            for (int i = tid; i < np; i += BA_T) md = fmax(md, fabs(Hpp[36 * (i / 6) + 7 * (i % 6)]));
+            for (int l = tid; l < L; l += BA_T)
+                if (l_off[l] != l_off[l + 1]) md = fmax(md, fmax(fabs(Hll[9 * (size_t)l]), fmax(fabs(Hll[9 * (size_t)l + 4]), fabs(Hll[9 * (size_t)l + 8]))));
+            md = block_max(md, red);
+            if (tid == 0) { s_lambda = 1e-5 * md; s_ni = 2; }
+            __syncthreads();
+        }
+        // ================= trial loop =================
+        int q = 0;
+        double rho = 0;
+        do {
+            double lambda = s_lambda;
+            // ---- reduced system: S = Hpp + lambda I (block diagonal), g = bp
+            for (int i = tid; i < np * pitch; i += BA_T) S[i] = 0.0;
+            if (tid == 0) s_flag = 1;
+            __syncthreads();
+            for (int i = tid; i < 36 * NA; i += BA_T) {
+                int a = i / 36, r = (i % 36) / 6, c2 = i % 6;
+                S[(6 * a + r) * pitch + 6 * a + c2] = Hpp[i] + (r == c2 ? lambda : 0.0);
+            }
+            // ---- V^-1 and W V^-1
+            for (int l = tid; l < L; l += BA_T) {
+                int s0 = l_off[l], s1 = l_off[l + 1];
+                if (s0 == s1) continue;
+                double D[9], Di[9];
+#pragma unroll
+                for (int x = 0; x < 9; x++) D[x] = Hll[9 * (size_t)l + x];
+                D[0] += lambda; D[4] += lambda; D[8] += lambda;
+                if (!gd::inv3(D, Di)) s_flag = 0;
+#pragma unroll
+                for (int x = 0; x < 9; x++) Dinv[9 * (size_t)l + x] = Di[x];
+                for (int s = s0; s < s1; s++) {
+                    int e = l_edges[s];
+                    const double *W = Hpl + 18 * (size_t)e;
+                    double *O = WD + 18 * (size_t)e;
+#pragma unroll
+                    for (int x = 0; x < 6; x++)
+#pragma unroll
+                        for (int y = 0; y < 3; y++) O[x * 3 + y] = W[x * 3] * Di[y] + W[x * 3 + 1] * Di[3 + y] + W[x * 3 + 2] * Di[6 + y];
+                }
+            }
+            __syncthreads();
+            // ---- S_ij -= sum over the block's (e1,e2) pairs of (W V^-1)_e1 W_e2^T   (36 threads own a block)
+            const int32_t *blk_i = A.blk_i + P.blk0, *blk_j = A.blk_j + P.blk0, *blk_off = A.blk_off + P.boff0;
+            const int32_t *pe1 = A.pair_e1 + P.pair0, *pe2 = A.pair_e2 + P.pair0;
+            for (int t = tid; t < P.nblk * 36; t += BA_T) {
+                int bk = t / 36, ent = t - 36 * bk, r = ent / 6, c2 = ent - 6 * r;
+                double sum = 0;
+                for (int s = blk_off[bk]; s < blk_off[bk + 1]; s++) {
+                    const double *X = WD + 18 * (size_t)pe1[s] + 3 * r;
+                    const double *Y = Hpl + 18 * (size_t)pe2[s] + 3 * c2;
+                    sum += X[0] * Y[0] + X[1] * Y[1] + X[2] * Y[2];
+                }
+                int i = blk_i[bk], j = blk_j[bk];
+                double v = S[(6 * i + r) * pitch + 6 * j + c2] - sum;
+                S[(6 * i + r) * pitch + 6 * j + c2] = v;
+                if (i != j) S[(6 * j + c2) * pitch + 6 * i + r] = v;
+            }
+            // ---- g_i = bp_i - sum_e (W V^-1)_e bl
+            for (int a = warp; a < NA; a += BA_T / 32) {
+                double s6[6] = {0, 0, 0, 0, 0, 0};
+                for (int s = p_off[a] + lane; s < p_off[a + 1]; s += 32) {
+                    int e = p_edges[s];
+                    const double *O = WD + 18 * (size_t)e, *b3 = bl + 3 * (size_t)edge_l[e];
+#pragma unroll
+                    for (int x = 0; x < 6; x++) s6[x] += O[x * 3] * b3[0] + O[x * 3 + 1] * b3[1] + O[x * 3 + 2] * b3[2];
+                }
+#pragma unroll
+                for (int x = 0; x < 6; x++) s6[x] = gd::warp_sum(s6[x]);
+                if (lane == 0)
+#pragma unroll
+                    for (int x = 0; x < 6; x++) g[6 * a + x] = bp[6 * a + x] - s6[x];
+            }
+            __syncthreads();
+            bool ok = s_flag != 0;
+            if (ok) ok = block_ldlt_solve(S, pitch, np, g, xp, tr, tmp, &s_piv);
+            st_sol++;
+            if (!ok) { for (int i = tid; i < np; i += BA_T) xp[i] = 0.0; __syncthreads(); }
+            // ---- back-substitution, trial state, scale term
+            double sc = 0;
+            for (int l = tid; l < L; l += BA_T) {
+                int s0 = l_off[l], s1 = l_off[l + 1];
+                if (s0 == s1) continue;
+                double c3[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
+                double x3[3] = {0, 0, 0};
+                if (ok) {
+                    for (int s = s0; s < s1; s++) {
+                        int e = l_edges[s];
+                        const double *W = Hpl + 18 * (size_t)e, *xx = xp + 6 * edge_p[e];
+#pragma unroll
+                        for (int y = 0; y < 3; y++) {
+                            double sm2 = 0;
+#pragma unroll
+                            for (int x = 0; x < 6; x++) sm2 += W[x * 3 + y] * xx[x];
+                            c3[y] -= sm2;
+                        }
+                    }
+                    const double *Di = Dinv + 9 * (size_t)l;
+#pragma unroll
+                    for (int x = 0; x < 3; x++) x3[x] = Di[x * 3] * c3[0] + Di[x * 3 + 1] * c3[1] + Di[x * 3 + 2] * c3[2];
+                }
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                    xl[3 * (size_t)l + x] = x3[x];
+                    lmT[3 * (size_t)l + x] = lms[3 * (size_t)l + x] + x3[x];
+                    sc += x3[x] * (lambda * x3[x] + bl[3 * (size_t)l + x]);
+                }
+            }
+            for (int a = tid; a < NA; a += BA_T) gd::se3_oplus(poseA + 7 * a, xp + 6 * a, poseT + 7 * a);
+            double scl = block_sum(sc, red);     // also orders the trial-state writes before chi2_of reads them
+            double tmpchi = chi2_of(poseT, lmT);
+            if (tid == 0) {
+                double scp = 0;
+                for (int i = 0; i < np; i++) scp += xp[i] * (lambda * xp[i] + bp[i]);
+                double scale = scp + scl + 1e-3;
+                double tc = ok ? tmpchi : DBL_MAX;
+                double r = (cur - tc) / scale;
+                gd::LmCtl lm = {s_lambda, s_ni};
+                int acc2 = gd::lm_accept(lm, r, tc) ? 1 : 0;
+                s_lambda = lm.lambda; s_ni = lm.ni; s_rho = r; s_q = acc2;
+                if (acc2) s_cur = tc;
+            }
+            __syncthreads();
+            rho = s_rho;
+            if (s_q) {
+                cur = s_cur;
+                for (int i = tid; i < 7 * NA; i += BA_T) poseA[i] = poseT[i];
+                for (int i = tid; i < 3 * L; i += BA_T) lms[i] = lmT[i];
+            }
+            __syncthreads();
+            q++; st_tr++;
+        } while (rho < 0 && q < 10);
+        st_it++;
+        if (q == 10 || rho == 0) stop = true;
+        if (tid == 0) s_cur = cur;
+        __syncthreads();
+    }
+    // ---- outputs: per-edge chi2 as g2o leaves it (errors of the LAST evaluated state, possibly a rejected trial)
+    for (int e = tid; e < E; e += BA_T) {
+        int cam = edge_cam[e];
+        double er[2], a[3], c[3];
+        gd::ba_error(poseT + 7 * edge_p[e], A.ext[cam], A.K[cam], lmT + 3 * (size_t)edge_l[e], edge_uv + 2 * e, er, a, c);
+        A.edge_chi2[P.e0 + e] = er[0] * er[0] + er[1] * er[1];
+    }
+    for (int i = tid; i < 7 * NA; i += BA_T) {
+        int a = i / 7;
+        A.poses[7 * (size_t)(P.pose0 + A.act_pose[P.act0 + a]) + (i - 7 * a)] = poseA[i];
+    }
+    if (tid == 0 && A.stats) {
+        svs_ba_stats &s = A.stats[blockIdx.x];
+        s.iterations = st_it; s.trials = st_tr; s.linearizations = st_lin; s.solves = st_sol;
+        s.lambda = s_lambda; s.chi2 = (st_it > 0) ? s_cur : 0.0; s.chi2_init = chi_init;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+static size_t ba_smem_bytes(int NA, bool with_S)
+{
+    size_t np = 6 * (size_t)NA, pitch = np | 1;
+    size_t d = BA_T + 14 * (size_t)NA + 36 * (size_t)NA + 4 * np;
+    size_t bytes = d * 8 + ((np + 1) & ~(size_t)1) * 4;
+    if (with_S) bytes += np * pitch * 8;
+    return bytes + 16;
+}
+
+extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, double *poses, const int32_t *lm_off, double *lms,
+                               const int32_t *e_off, const int32_t *edge_kf, const int32_t *edge_lm, const uint8_t *edge_cam,
+                               const double *edge_uv, const double K_left[4], const double K_right[4], const double ext_left[7],
+                               const double ext_right[7], double huber_delta, int max_iter, int jacobian_mode,
+                               double *edge_chi2_out, svs_ba_stats *stats)
+{
+    if (!c || n_prob < 0 || !kf_off || !lm_off || !e_off || !K_left || !K_right || !ext_left || !ext_right) return SVS_ERR_ARG;
+    if (n_prob == 0) return SVS_OK;
+    const int sumN = kf_off[n_prob], sumL = lm_off[n_prob], sumE = e_off[n_prob];
+    if (sumE > 0 && (!edge_kf || !edge_lm || !edge_cam || !edge_uv || !edge_chi2_out || !poses || !lms)) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+
+    // ---- host-side structure: active poses, CSR by landmark / pose, per-block pair lists
+    std::vector<BaProb> probs(n_prob);
+    std::vector<int32_t> act_pose, edge_p(sumE), l_off, l_edges(sumE), p_off, p_edges(sumE), blk_i, blk_j, blk_off, pe1, pe2;
+    const size_t smem_cap = 200 * 1024;
+    size_t max_smem = 0;
+    long long S_tot = 0;
+    for (int b = 0; b < n_prob; b++) {
+        int N = kf_off[b + 1] - kf_off[b], L = lm_off[b + 1] - lm_off[b], E = e_off[b + 1] - e_off[b], e0 = e_off[b];
+        BaProb &P = probs[b];
+        std::vector<int> pidx(N, -1);
+        for (int e = 0; e < E; e++) {
+            int k = edge_kf[e0 + e], l = edge_lm[e0 + e];
+            if (k < 0 || k >= N || l < 0 || l >= L) SVS_FAIL(c, SVS_ERR_ARG, "ba: edge index out of range");
+            pidx[k] = 0;
+        }
+        P.act0 = (int)act_pose.size();
+        int NA = 0;
+        for (int k = 0; k < N; k++) if (pidx[k] == 0) { pidx[k] = NA++; act_pose.push_back(k); }
+        P.NA = NA; P.L = L; P.E = E; P.pose0 = kf_off[b]; P.lm0 = lm_off[b]; P.e0 = e0;
+        for (int e = 0; e < E; e++) edge_p[e0 + e] = pidx[edge_kf[e0 + e]];
+        // CSR by landmark (creation order inside a landmark)
+        P.loff0 = (int)l_off.size();
+        std::vector<int> cnt(L + 1, 0);
+        for (int e = 0; e < E; e++) cnt[edge_lm[e0 + e] + 1]++;
+        for (int l = 0; l < L; l++) cnt[l + 1] += cnt[l];
+        for (int l = 0; l <= L; l++) l_off.push_back(cnt[l]);
+        { std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+          for (int e = 0; e < E; e++) l_edges[e0 + fill[edge_lm[e0 + e]]++] = e; }
+        // CSR by active pose
+        P.poff0 = (int)p_off.size();
+        std::vector<int> pc(NA + 1, 0);
+        for (int e = 0; e < E; e++) pc[edge_p[e0 + e] + 1]++;
+        for (int a = 0; a < NA; a++) pc[a + 1] += pc[a];
+        for (int a = 0; a <= NA; a++) p_off.push_back(pc[a]);
+        { std::vector<int> fill(pc.begin(), pc.end() - 1);
+          for (int e = 0; e < E; e++) p_edges[e0 + fill[edge_p[e0 + e]]++] = e; }
+        // pair lists per upper block (i <= j): counting sort on block id i*NA + j
+        P.blk0 = (int)blk_i.size(); P.boff0 = (int)blk_off.size(); P.pair0 = (int)pe1.size();
+        std::vector<int> bcount((size_t)NA * NA + 1, 0);
+        const int32_t *lo = l_off.data() + P.loff0;
+        for (int l = 0; l < L; l++)
+            for (int s1 = lo[l]; s1 < lo[l + 1]; s1++)
+                for (int s2 = lo[l]; s2 < lo[l + 1]; s2++) {
+                    int i = edge_p[e0 + l_edges[e0 + s1]], j = edge_p[e0 + l_edges[e0 + s2]];
+                    if (i <= j) bcount[(size_t)i * NA + j + 1]++;
+                }
+        std::vector<int> bmap((size_t)NA * NA, -1);
+        int nblk = 0, run = 0;
+        blk_off.push_back(0);
+        std::vector<int> bstart((size_t)NA * NA, 0);
+        for (size_t k = 0; k < (size_t)NA * NA; k++) {
+            int cn = bcount[k + 1];
+            if (cn > 0) {
+                bmap[k] = nblk++; bstart[k] = run; run += cn;
+                blk_i.push_back((int)(k / NA)); blk_j.push_back((int)(k % NA));
+                blk_off.push_back(run);
+            }
+        }
+        P.nblk = nblk;
+        size_t pbase = pe1.size();
+        pe1.resize(pbase + run); pe2.resize(pbase + run);
+        std::vector<int> bfill(bstart);
+        for (int l = 0; l < L; l++)
+            for (int s1 = lo[l]; s1 < lo[l + 1]; s1++)
+                for (int s2 = lo[l]; s2 < lo[l + 1]; s2++) {
+                    int ea = l_edges[e0 + s1], eb = l_edges[e0 + s2];
+                    int i = edge_p[e0 + ea], j = edge_p[e0 + eb];
+                    if (i <= j) { int pos = bfill[(size_t)i * NA + j]++; pe1[pbase + pos] = ea; pe2[pbase + pos] = eb; }
+                }
+        size_t with = ba_smem_bytes(NA, true);
+        if (with <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, with); }
+        else { P.S_off = S_tot; size_t np = 6 * (size_t)NA; S_tot += (long long)(np * (np | 1)); max_smem = std::max(max_smem, ba_smem_bytes(NA, false)); }
+    }
+    if (max_smem > 220 * 1024) SVS_FAIL(c, SVS_ERR_CAPACITY, "ba: window too large for the single-CTA solver");
+
+    // ---- pack host -> device
+    struct Seg { const void *src; size_t bytes; size_t off; };
+    std::vector<Seg> segs;
+    size_t tot = 0;
+    auto add = [&](const void *p, size_t bytes) { size_t o = tot; segs.push_back({p, bytes, o}); tot = align_up(tot + bytes, 16); return o; };
+    size_t o_probs = add(probs.data(), probs.size() * sizeof(BaProb));
+    size_t o_act = add(act_pose.data(), act_pose.size() * 4);
+    size_t o_ep = add(edge_p.data(), (size_t)sumE * 4);
+    size_t o_el = add(edge_lm, (size_t)sumE * 4);
+    size_t o_ec = add(edge_cam, (size_t)sumE);
+    size_t o_uv = add(edge_uv, (size_t)sumE * 16);
+    size_t o_lo = add(l_off.data(), l_off.size() * 4);
+    size_t o_le = add(l_edges.data(), (size_t)sumE * 4);
+    size_t o_po = add(p_off.data(), p_off.size() * 4);
+    size_t o_pe = add(p_edges.data(), (size_t)sumE * 4);
+    size_t o_bi = add(blk_i.data(), blk_i.size() * 4);
+    size_t o_bj = add(blk_j.data(), blk_j.size() * 4);
+    size_t o_bo = add(blk_off.data(), blk_off.size() * 4);
+    size_t o_p1 = add(pe1.data(), pe1.size() * 4);
+    size_t o_p2 = add(pe2.data(), pe2.size() * 4);
+    size_t o_pose = add(poses, (size_t)sumN * 56);
+    size_t o_lm = add(lms, (size_t)sumL * 24);
+    SVS_CUDA(c, c->h_in.reserve(tot + 16));
+    SVS_CUDA(c, c->d_in2.reserve(tot + 16));
+    uint8_t *hb = c->h_in.as<uint8_t>(), *db = c->d_in2.as<uint8_t>();
+    for (const Seg &s : segs) if (s.bytes) memcpy(hb + s.off, s.src, s.bytes);
+    SVS_CUDA(c, cudaMemcpyAsync(db, hb, tot, cudaMemcpyHostToDevice, c->stream));
+    // scratch
+    size_t sc_b = ((size_t)sumE * 36 + (size_t)sumL * 27 + (size_t)S_tot) * 8 + 64;
+    SVS_CUDA(c, c->d_tmp.reserve(sc_b));
+    size_t out_b = (size_t)sumE * 8 + (size_t)n_prob * sizeof(svs_ba_stats);
+    SVS_CUDA(c, c->d_out.reserve(out_b + 16));
+    SVS_CUDA(c, c->h_out.reserve(out_b + (size_t)sumN * 56 + (size_t)sumL * 24 + 64));
+    double *scr = c->d_tmp.as<double>();
+    BaArgs A;
+    A.probs = reinterpret_cast<BaProb *>(db + o_probs);
+    A.poses = reinterpret_cast<double *>(db + o_pose); A.lms = reinterpret_cast<double *>(db + o_lm);
+    A.act_pose = reinterpret_cast<int32_t *>(db + o_act);
+    A.edge_p = reinterpret_cast<int32_t *>(db + o_ep); A.edge_l = reinterpret_cast<int32_t *>(db + o_el);
+    A.edge_cam = db + o_ec; A.edge_uv = reinterpret_cast<double *>(db + o_uv);
+    A.l_off = reinterpret_cast<int32_t *>(db + o_lo); A.l_edges = reinterpret_cast<int32_t *>(db + o_le);
+    A.p_off = reinterpret_cast<int32_t *>(db + o_po); A.p_edges = reinterpret_cast<int32_t *>(db + o_pe);
+    A.blk_i = reinterpret_cast<int32_t *>(db + o_bi); A.blk_j = reinterpret_cast<int32_t *>(db + o_bj);
+    A.blk_off = reinterpret_cast<int32_t *>(db + o_bo);
+    A.pair_e1 = reinterpret_cast<int32_t *>(db + o_p1); A.pair_e2 = reinterpret_cast<int32_t *>(db + o_p2);
+    A.Hpl = scr; A.WD = A.Hpl + (size_t)sumE * 18;
+    A.Hll = A.WD + (size_t)sumE * 18; A.Dinv = A.Hll + (size_t)sumL * 9;
+    A.bl = A.Dinv + (size_t)sumL * 9; A.xl = A.bl + (size_t)sumL * 3; A.lmT = A.xl + (size_t)sumL * 3;
+    A.S_glob = A.lmT + (size_t)sumL * 3;
+    A.edge_chi2 = c->d_out.as<double>();
+    A.stats = reinterpret_cast<svs_ba_stats *>(c->d_out.as<uint8_t>() + (size_t)sumE * 8);
+    for (int i = 0; i < 4; i++) { A.K[0][i] = K_left[i]; A.K[1][i] = K_right[i]; }
+    for (int i = 0; i < 7; i++) { A.ext[0][i] = ext_left[i]; A.ext[1][i] = ext_right[i]; }
+    A.huber_delta = huber_delta; A.max_iter = max_iter; A.jac_mode = jacobian_mode;
+    static size_t attr_set = 0;
+    if (max_smem > attr_set) {
+        SVS_CUDA(c, cudaFuncSetAttribute(k_ba_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        attr_set = max_smem;
+    }
+    k_ba_window<<<n_prob, BA_T, max_smem, c->stream>>>(A);
+    SVS_LAUNCH_CHECK(c);
+    uint8_t *ho = c->h_out.as<uint8_t>();
+    SVS_CUDA(c, cudaMemcpyAsync(ho, c->d_out.p, out_b, cudaMemcpyDeviceToHost, c->stream));
+    size_t ho_pose = align_up(out_b, 16), ho_lm = ho_pose + (size_t)sumN * 56;
+    SVS_CUDA(c, cudaMemcpyAsync(ho + ho_pose, A.poses, (size_t)sumN * 56, cudaMemcpyDeviceToHost, c->stream));
+    if (sumL) SVS_CUDA(c, cudaMemcpyAsync(ho + ho_lm, A.lms, (size_t)sumL * 24, cudaMemcpyDeviceToHost, c->stream));
+    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (sumE) memcpy(edge_chi2_out, ho, (size_t)sumE * 8);
+    if (stats) memcpy(stats, ho + (size_t)sumE * 8, (size_t)n_prob * sizeof(svs_ba_stats));
+    memcpy(poses, ho + ho_pose, (size_t)sumN * 56);
+    if (sumL) memcpy(lms, ho + ho_lm, (size_t)sumL * 24);
+    return SVS_OK;
+}

@@ -225,3 +225,96 @@ class Context:
         self._chk(self.lib.svs_lk_track_batch(C.c_void_p(self.h), C.c_void_p(fs.h), pair, _p(off), _p(pxy), _p(nxy),
                                               max_iter, C.c_double(eps), _p(st)))
         return [(nxy[off[i]:off[i + 1]].copy(), st[off[i]:off[i + 1]].copy()) for i in range(fs.n_streams)]
+
+
+# ---------------------------------------------------------------- geometry / dense (methods added to Context)
+def _triangulate(self, left_xy, right_xy, K_left, K_right, baseline):
+    l, r = _f32(left_xy).reshape(-1, 2), _f32(right_xy).reshape(-1, 2)
+    n = len(l)
+    xyz = np.zeros((max(n, 1), 3))
+    ok = np.zeros(max(n, 1), np.uint8)
+    self._chk(self.lib.svs_triangulate(C.c_void_p(self.h), _p(l), _p(r), n, _p(_f64(K_left)), _p(_f64(K_right)),
+                                       C.c_double(baseline), _p(xyz), _p(ok)))
+    return xyz[:n], ok[:n]
+
+
+def _pose_only_lm(self, problems, chi2_th=5.991, rounds=4, iters=10):
+    """problems: list of (pts_w [m,3], uv [m,2], K4, T0[7]).  Returns list of (T, outlier, n_inlier, stats)."""
+    n = len(problems)
+    off = np.zeros(n + 1, np.int32)
+    for i, p in enumerate(problems):
+        off[i + 1] = off[i] + len(p[0])
+    M = int(off[-1])
+    pts = _f64(np.concatenate([np.asarray(p[0], np.float64).reshape(-1, 3) for p in problems])) if M else np.zeros((0, 3))
+    uv = _f64(np.concatenate([np.asarray(p[1], np.float64).reshape(-1, 2) for p in problems])) if M else np.zeros((0, 2))
+    K = _f64(np.stack([np.asarray(p[2], np.float64) for p in problems]))
+    T0 = _f64(np.stack([np.asarray(p[3], np.float64) for p in problems]))
+    T = np.zeros((n, 7))
+    outl = np.zeros(max(M, 1), np.uint8)
+    ninl = np.zeros(n, np.int32)
+    st = (LmStats * n)()
+    self._chk(self.lib.svs_pose_only_lm(C.c_void_p(self.h), n, _p(off), _p(pts), _p(uv), _p(K), _p(T0), C.c_double(chi2_th),
+                                        rounds, iters, _p(T), _p(outl), _p(ninl), st))
+    return [(T[i].copy(), outl[off[i]:off[i + 1]].copy(), int(ninl[i]), st[i]) for i in range(n)]
+
+
+def _ba_optimize(self, problems, K_left, K_right, ext_left, ext_right, huber_delta=5.991, max_iter=10, jac_mode=0):
+    """problems: list of dicts(poses [N,7], lms [L,3], edge_kf, edge_lm, edge_cam, edge_uv).
+    Returns list of (poses, lms, chi2, stats)."""
+    n = len(problems)
+    ko, lo, eo = (np.zeros(n + 1, np.int32) for _ in range(3))
+    for i, p in enumerate(problems):
+        ko[i + 1] = ko[i] + len(p["poses"]); lo[i + 1] = lo[i] + len(p["lms"]); eo[i + 1] = eo[i] + len(p["edge_kf"])
+    cat = lambda k, dt, shp: np.ascontiguousarray(np.concatenate([np.asarray(p[k], dt).reshape(shp) for p in problems]), dt)
+    poses, lms = cat("poses", np.float64, (-1, 7)), cat("lms", np.float64, (-1, 3))
+    ekf, elm = cat("edge_kf", np.int32, (-1,)), cat("edge_lm", np.int32, (-1,))
+    ecam, euv = cat("edge_cam", np.uint8, (-1,)), cat("edge_uv", np.float64, (-1, 2))
+    chi2 = np.zeros(max(int(eo[-1]), 1))
+    st = (BaStats * n)()
+    self._chk(self.lib.svs_ba_optimize(
+        C.c_void_p(self.h), n, _p(ko), _p(poses), _p(lo), _p(lms), _p(eo), _p(ekf), _p(elm), _p(ecam), _p(euv),
+        _p(_f64(K_left)), _p(_f64(K_right)), _p(_f64(ext_left)), _p(_f64(ext_right)), C.c_double(huber_delta), max_iter,
+        jac_mode, _p(chi2), st))
+    return [(poses[ko[i]:ko[i + 1]].copy(), lms[lo[i]:lo[i + 1]].copy(), chi2[eo[i]:eo[i + 1]].copy(), st[i]) for i in range(n)]
+
+
+def _stereo_bm(self, left, right, ndisp=128, block=15):
+    left, right = _u8(left), _u8(right)
+    single = left.ndim == 2
+    if single:
+        left, right = left[None], right[None]
+    n, h, w = left.shape
+    out = np.zeros((n, h, w), np.int16)
+    self._chk(self.lib.svs_stereo_bm(C.c_void_p(self.h), _p(left), _p(right), w, h, w, n, C.c_size_t(w * h), ndisp, block, _p(out)))
+    return out[0] if single else out
+
+
+def _bgr2gray(self, bgr):
+    bgr = _u8(bgr)
+    single = bgr.ndim == 3
+    if single:
+        bgr = bgr[None]
+    n, h, w, _ = bgr.shape
+    out = np.zeros((n, h, w), np.uint8)
+    self._chk(self.lib.svs_bgr2gray(C.c_void_p(self.h), _p(bgr), w, h, n, _p(out)))
+    return out[0] if single else out
+
+
+def _backproject(self, disp, bgr, K, baseline, cam_pose_inv, T_cw):
+    disp = np.ascontiguousarray(disp, np.int16)
+    bgr = _u8(bgr)
+    h, w = disp.shape
+    xyz = np.zeros((h * w, 3), np.float32)
+    rgb = np.zeros((h * w, 3), np.uint8)
+    n = C.c_int32(0)
+    self._chk(self.lib.svs_backproject(C.c_void_p(self.h), _p(disp), _p(bgr), w, h, _p(_f64(K)), C.c_double(baseline),
+                                       _p(_f64(cam_pose_inv)), _p(_f64(T_cw)), _p(xyz), _p(rgb), C.byref(n)))
+    return xyz[:n.value].copy(), rgb[:n.value].copy()
+
+
+Context.triangulate = _triangulate
+Context.pose_only_lm = _pose_only_lm
+Context.ba_optimize = _ba_optimize
+Context.stereo_bm = _stereo_bm
+Context.bgr2gray = _bgr2gray
+Context.backproject = _backproject

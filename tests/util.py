@@ -49,3 +49,129 @@ def stereo_pair(h, w, seed, dmin=2.0, dmax=120.0):
     ys = (np.arange(h)[:, None] * np.ones((1, w))).astype(np.float32)
     r = cv2.remap(big, xs.astype(np.float32), ys, cv2.INTER_LINEAR)
     return big[:, :w].copy(), r
+
+
+# ---------------------------------------------------------------------------------------------
+# Geometry problems (KITTI seq-05 half-resolution calibration)
+K05 = np.array([707.0912 * 0.5, 707.0912 * 0.5, 601.8873 * 0.5, 183.1104 * 0.5])
+BASELINE = 0.5371657
+EXT_L = np.array([0, 0, 0, 1, 0, 0, 0.0])
+EXT_R = np.array([0, 0, 0, 1, -BASELINE, 0, 0.0])
+W05, H05 = 613, 185
+
+
+def quat_from_rotvec(w):
+    th = np.linalg.norm(w)
+    if th < 1e-12:
+        return np.array([0.5 * w[0], 0.5 * w[1], 0.5 * w[2], 1.0])
+    return np.concatenate([np.sin(th / 2) * w / th, [np.cos(th / 2)]])
+
+
+def quat_to_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def pose_Tcw(center, rotvec):
+    """T_cw from a camera centre and a world->camera rotation vector."""
+    q = quat_from_rotvec(np.asarray(rotvec, float))
+    R = quat_to_R(q)
+    return np.concatenate([q, -R @ np.asarray(center, float)])
+
+
+def project(T, p, K=K05, ext=EXT_L):
+    pc = quat_to_R(T[:4]) @ p + T[4:]
+    pc = quat_to_R(ext[:4]) @ pc + ext[4:]
+    return np.array([K[0] * pc[0] / pc[2] + K[2], K[1] * pc[1] / pc[2] + K[3]]), pc[2]
+
+
+def pose_problem(seed, m=150, noise=0.5, outlier_frac=0.1, perturb=(0.05, 0.01)):
+    """A pose-only problem like Frontend::EstimateCurrentPose sees: m landmarks, noisy pixels, gross outliers."""
+    rng = np.random.RandomState(seed)
+    T_true = pose_Tcw(rng.randn(3) * 0.3, rng.randn(3) * 0.05)
+    pts, uv = [], []
+    while len(pts) < m:
+        z = rng.uniform(4, 60)
+        u, v = rng.uniform(5, W05 - 5), rng.uniform(5, H05 - 5)
+        pc = np.array([(u - K05[2]) * z / K05[0], (v - K05[3]) * z / K05[1], z])
+        R = quat_to_R(T_true[:4])
+        pw = R.T @ (pc - T_true[4:])
+        pts.append(pw)
+        uv.append([u, v])
+    pts, uv = np.array(pts).reshape(-1, 3), np.array(uv).reshape(-1, 2) + rng.randn(m, 2) * noise
+    nout = int(m * outlier_frac)
+    uv[:nout] += rng.uniform(-30, 30, (nout, 2))
+    T0 = pose_Tcw(-quat_to_R(T_true[:4]).T @ T_true[4:] + rng.randn(3) * perturb[0], rng.randn(3) * perturb[1] * 0 )
+    # perturbed initial pose: same construction with a noisy rotation
+    q0 = quat_from_rotvec(rng.randn(3) * perturb[1])
+    T0 = np.concatenate([q0, T_true[4:] + rng.randn(3) * perturb[0]])
+    # compose the small rotation on the left of T_true's rotation
+    Rn = quat_to_R(q0) @ quat_to_R(T_true[:4])
+    T0[:4] = R_to_quat(Rn)
+    return pts, uv, K05.copy(), T0, T_true
+
+
+def R_to_quat(R):
+    w = np.sqrt(max(0.0, 1 + R[0, 0] + R[1, 1] + R[2, 2])) / 2
+    x = (R[2, 1] - R[1, 2]) / (4 * w)
+    y = (R[0, 2] - R[2, 0]) / (4 * w)
+    z = (R[1, 0] - R[0, 1]) / (4 * w)
+    q = np.array([x, y, z, w])
+    return q / np.linalg.norm(q)
+
+
+def ba_problem(seed, n_kf=10, n_lm=300, noise=0.5, outlier_frac=0.02, pose_sigma=(0.02, 0.0035), lm_sigma=0.1,
+               max_follow=6, unused_kf=False, unused_lm=0):
+    """A sliding-window BA problem shaped like Backend::Optimize's graph (SURVEY.md §8d config 4 recipe, scaled)."""
+    rng = np.random.RandomState(seed)
+    poses_true = []
+    for k in range(n_kf):
+        ang = 0.02 * k
+        center = np.array([4.0 * np.sin(ang * 3), 0.02 * rng.randn(), 1.0 * k])
+        poses_true.append(pose_Tcw(center, [0.0, -ang, 0.0]))
+    poses_true = np.array(poses_true)
+    lms_true, ekf, elm, ecam, euv = [], [], [], [], []
+    for l in range(n_lm):
+        birth = rng.randint(0, n_kf)
+        for _ in range(50):
+            z = rng.uniform(5, 80)
+            u, v = rng.uniform(20, W05 - 20), rng.uniform(10, H05 - 10)
+            pc = np.array([(u - K05[2]) * z / K05[0], (v - K05[3]) * z / K05[1], z])
+            T = poses_true[birth]
+            pw = quat_to_R(T[:4]).T @ (pc - T[4:])
+            obs = []
+            for (k, cam) in [(birth, 0), (birth, 1)] + [(k, 0) for k in range(birth + 1, min(n_kf, birth + 1 + rng.randint(1, max_follow + 1)))]:
+                px, depth = project(poses_true[k], pw, K05, EXT_R if cam else EXT_L)
+                if depth > 1 and 0 <= px[0] < W05 and 0 <= px[1] < H05:
+                    obs.append((k, cam, px))
+            if len(obs) >= 2:
+                break
+        lms_true.append(pw)
+        for (k, cam, px) in obs:
+            ekf.append(k); elm.append(l); ecam.append(cam)
+            n2 = rng.randn(2) * noise
+            if rng.rand() < outlier_frac:
+                n2 += rng.uniform(-20, 20, 2)
+            euv.append(px + n2)
+    lms_true = np.array(lms_true)
+    poses0 = poses_true.copy()
+    for k in range(n_kf):
+        q0 = quat_from_rotvec(rng.randn(3) * pose_sigma[1])
+        poses0[k, :4] = R_to_quat(quat_to_R(q0) @ quat_to_R(poses_true[k, :4]))
+        poses0[k, 4:] += rng.randn(3) * pose_sigma[0]
+    lms0 = lms_true + rng.randn(*lms_true.shape) * lm_sigma
+    prob = dict(poses=poses0, lms=lms0, edge_kf=np.array(ekf, np.int32), edge_lm=np.array(elm, np.int32),
+                edge_cam=np.array(ecam, np.uint8), edge_uv=np.array(euv))
+    if unused_kf:       # a keyframe with no edges (inactive vertex) at index 0
+        prob["poses"] = np.concatenate([pose_Tcw([9, 9, 9], [0.1, 0.2, 0.3])[None], prob["poses"]])
+        prob["edge_kf"] = prob["edge_kf"] + 1
+    if unused_lm:
+        prob["lms"] = np.concatenate([prob["lms"], rng.randn(unused_lm, 3) * 10])
+    return prob, poses_true, lms_true
+
+
+def rel_to_norm(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(b, axis=-1), 1e-12)
