@@ -70,6 +70,10 @@ SVS_API int svs_frameset_size(const svs_frameset *fs, int *w, int *h, int *n_lev
  * on_device != 0: the pointers are device pointers (inputs already resident in HBM). */
 SVS_API int svs_frameset_push(svs_ctx *ctx, svs_frameset *fs, const uint8_t *left, const uint8_t *right,
                               size_t row_stride, size_t img_stride_bytes, int on_device);
+/* Same, with one pointer per stream (left[b], right[b]): dense rows `row_stride` apart.  Host pointers should be
+ * pinned (svs_host_alloc) for full PCIe bandwidth. */
+SVS_API int svs_frameset_push_ptrs(svs_ctx *ctx, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right,
+                                   size_t row_stride, int on_device);
 /* Copy a pyramid level back (tests).  which: 0 = current left, 1 = previous left, 2 = current right */
 SVS_API int svs_frameset_download(svs_ctx *ctx, svs_frameset *fs, int stream, int which, int level,
                                   uint8_t *out, int out_stride);
@@ -176,6 +180,41 @@ SVS_API int svs_backproject(svs_ctx *ctx, const int16_t *disp, const uint8_t *bg
                             const double T_cw[7], float *xyz_out /* 3*h*w */, uint8_t *rgb_out /* 3*h*w */,
                             int32_t *n_out);
 SVS_API int svs_bgr2gray(svs_ctx *ctx, const uint8_t *bgr, int w, int h, int n_images, uint8_t *gray);
+
+/* ---------------------------------------------------------------- a6 / a8 / a9 : the pipeline
+ * svs_slam steps n_streams independent stereo streams in lock-step through the host-side mirror of the reference's
+ * Frontend / Backend / Map classes (stereovision-slam_b200/host/slam.h), i.e. it is Frontend::AddFrame
+ * (src/frontend.cpp:690-721) for a batch of streams: every third-party seam becomes one batched svs_* call per step.
+ * Bundle adjustment runs on the synchronous schedule (inside Backend::UpdateMap).  Config fields mirror
+ * config/stereo_slam_configs/default.yaml plus the constants hard-coded at src/frontend.cpp:24,107-108 and
+ * src/backend.cpp:164. */
+typedef struct {
+    int32_t num_features, num_features_init, num_features_tracking, num_features_tracking_bad;
+    int32_t num_features_needed_for_keyframe, num_active_keyframes, backend_on;
+    int32_t lk_win, lk_max_level, lk_max_iter, ba_max_iter, ba_jacobian_mode, oracle_simd_granule;
+    double max_triangulation_depth, chi2_th, gftt_quality, gftt_min_distance, lk_eps;
+} svs_slam_config;
+typedef struct svs_slam svs_slam;
+SVS_API void svs_slam_default_config(svs_slam_config *cfg);
+/* K = intrinsics of the PROCESSED image (already halved when half != 0, src/dataset.cpp:73); right camera extrinsic
+ * is the pure translation (-baseline, 0, 0) (src/dataset.cpp:63-77). */
+SVS_API svs_slam *svs_slam_create(svs_ctx *ctx, int n_streams, int in_w, int in_h, int half, const svs_slam_config *cfg,
+                                  const double K[4], double baseline);
+SVS_API void svs_slam_destroy(svs_slam *s);
+/* One Frontend::AddFrame for every stream.  status: 0 INITING, 1 TRACKING_GOOD, 2 TRACKING_BAD, 3 LOST. */
+SVS_API int svs_slam_add_frames(svs_slam *s, const uint8_t *const *left, const uint8_t *const *right, size_t row_stride,
+                                int on_device, double *poses_out /* 7*n */, int32_t *status_out, int32_t *keyframe_out,
+                                int32_t *inliers_out);
+SVS_API int svs_slam_get_features(svs_slam *s, int stream, int right, float *xy, int64_t *map_point_ids, uint8_t *valid,
+                                  int cap, int *n);
+SVS_API int svs_slam_get_keyframes(svs_slam *s, int stream, int active_only, int64_t *kf_ids, int64_t *frame_ids,
+                                   double *poses, int cap, int *n);
+SVS_API int svs_slam_get_landmarks(svs_slam *s, int stream, int active_only, int64_t *ids, double *xyz,
+                                   int32_t *observed_times, int cap, int *n);
+/* phase_seconds[8]: push, track-LK, pose LM, detect, right-LK, triangulate, BA, host bookkeeping (wall clock, includes
+ * device time).  counters[6]: frames, keyframes, BA problems, BA iterations, BA trials, BA edges. */
+SVS_API int svs_slam_get_counters(svs_slam *s, double *phase_seconds, long long *counters);
+SVS_API svs_frameset *svs_slam_frameset(svs_slam *s);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,9 @@ static std::string g_create_err;
 
 extern "C" {
 
+static int frameset_finish_push(svs_ctx *c, svs_frameset *fs, const uint8_t *dl, const uint8_t *dr, size_t rs, size_t is,
+                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4);
+
 int svs_version(void) { return 100; }
 const char *svs_create_error(void) { return g_create_err.c_str(); }
 
@@ -98,6 +101,8 @@ void svs_frameset_destroy(svs_ctx *c, svs_frameset *fs)
     if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
     for (int i = 0; i < 3; i++) fs->pyr[i].release();
     fs->staging.release();
+    fs->ptr_table.release();
+    fs->ptr_table_h.release();
     delete fs;
 }
 
@@ -133,19 +138,62 @@ int svs_frameset_push(svs_ctx *c, svs_frameset *fs, const uint8_t *left, const u
         }
         dl = sl; dr = sr; rs = fs->in_w; is = dense;
     }
+    return frameset_finish_push(c, fs, dl, dr, rs, is, nullptr, nullptr, 0);
+}
+
+static int frameset_finish_push(svs_ctx *c, svs_frameset *fs, const uint8_t *dl, const uint8_t *dr, size_t rs, size_t is,
+                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4)
+{
     fs->cur ^= 1;
     fs->pushes++;
     PyrDesc &Lc = fs->L[fs->cur];
     if (fs->half) {
-        SVS_TRY(svs_i_half_nearest(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc.base + Lc.off[0], fs->W, fs->H, Lc.stride[0], Lc.img_pitch));
-        SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R.base + fs->R.off[0], fs->W, fs->H, fs->R.stride[0], fs->R.img_pitch));
+        SVS_TRY(svs_i_half_nearest(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc.base + Lc.off[0], fs->W, fs->H, Lc.stride[0], Lc.img_pitch, pl, aligned4));
+        SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R.base + fs->R.off[0], fs->W, fs->H, fs->R.stride[0], fs->R.img_pitch, pr, aligned4));
     } else {
-        SVS_TRY(svs_i_copy_level0(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc));
-        SVS_TRY(svs_i_copy_level0(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R));
+        SVS_TRY(svs_i_copy_level0(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc, pl));
+        SVS_TRY(svs_i_copy_level0(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R, pr));
     }
     SVS_TRY(svs_i_build_pyramid(c, Lc, fs->B));
     SVS_TRY(svs_i_build_pyramid(c, fs->R, fs->B));
     return SVS_OK;
+}
+
+int svs_frameset_push_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right, size_t row_stride,
+                           int on_device)
+{
+    if (!c || !fs || !left || !right) return SVS_ERR_ARG;
+    if (row_stride < (size_t)fs->in_w) SVS_FAIL(c, SVS_ERR_ARG, "frameset_push_ptrs: bad row stride");
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    const int B = fs->B;
+    if (on_device) {
+        SVS_CUDA(c, fs->ptr_table.reserve((size_t)2 * B * sizeof(void *)));
+        SVS_CUDA(c, fs->ptr_table_h.reserve((size_t)2 * B * sizeof(void *)));
+        const uint8_t **hp = fs->ptr_table_h.as<const uint8_t *>();
+        int aligned4 = 1;
+        // the previous push's table copy must have been consumed before the pinned table is overwritten
+        SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int b = 0; b < B; b++) {
+            hp[b] = left[b]; hp[B + b] = right[b];
+            if ((reinterpret_cast<uintptr_t>(left[b]) | reinterpret_cast<uintptr_t>(right[b])) & 3) aligned4 = 0;
+        }
+        SVS_CUDA(c, cudaMemcpyAsync(fs->ptr_table.p, hp, (size_t)2 * B * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+        const uint8_t *const *dp = fs->ptr_table.as<const uint8_t *>();
+        return frameset_finish_push(c, fs, nullptr, nullptr, row_stride, 0, dp, dp + B, aligned4);
+    }
+    size_t dense = (size_t)fs->in_w * fs->in_h;
+    SVS_CUDA(c, fs->staging.reserve(2 * dense * B));
+    uint8_t *sl = fs->staging.as<uint8_t>(), *sr = sl + dense * B;
+    for (int b = 0; b < B; b++) {
+        if (row_stride == (size_t)fs->in_w) {
+            SVS_CUDA(c, cudaMemcpyAsync(sl + dense * b, left[b], dense, cudaMemcpyHostToDevice, c->stream));
+            SVS_CUDA(c, cudaMemcpyAsync(sr + dense * b, right[b], dense, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            SVS_CUDA(c, cudaMemcpy2DAsync(sl + dense * b, fs->in_w, left[b], row_stride, fs->in_w, fs->in_h, cudaMemcpyHostToDevice, c->stream));
+            SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right[b], row_stride, fs->in_w, fs->in_h, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    return frameset_finish_push(c, fs, sl, sr, fs->in_w, dense, nullptr, nullptr, 0);
 }
 
 int svs_frameset_download(svs_ctx *c, svs_frameset *fs, int stream, int which, int level, uint8_t *out, int out_stride)

@@ -33,17 +33,18 @@ int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t
 
 // ---------------------------------------------------------------------------------------------
 // dst[y][x] = src[min(2y,h-1)][min(2x,w-1)]; each thread produces 4 output pixels.
-__global__ void k_half_nearest(const uint8_t *__restrict__ src, int w, int h, size_t row_stride, size_t img_stride,
-                               uint8_t *__restrict__ dst, int dw, int dh, int dst_stride, size_t dst_img_pitch,
-                               int vec_ok)
+__global__ void k_half_nearest(const uint8_t *__restrict__ src, const uint8_t *const *__restrict__ src_ptrs, int w, int h,
+                               size_t row_stride, size_t img_stride, uint8_t *__restrict__ dst, int dw, int dh, int dst_stride,
+                               size_t dst_img_pitch, int vec_ok)
 {
     int img = blockIdx.z;
+    if (src_ptrs) { src = src_ptrs[img]; img_stride = 0; }
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (y >= dh || x4 >= dw) return;
     int sy = min(2 * y, h - 1);
     const uint8_t *srow = src + (size_t)img * img_stride + (size_t)sy * row_stride;
-    uint8_t *drow = dst + (size_t)img * dst_img_pitch + (size_t)y * dst_stride;
+    uint8_t *drow = dst + (size_t)blockIdx.z * dst_img_pitch + (size_t)y * dst_stride;
     if (vec_ok && x4 + 4 <= dw && 2 * x4 + 8 <= w) {
         const uint32_t *s32 = reinterpret_cast<const uint32_t *>(srow + 2 * x4);
         uint32_t a = __ldg(s32), b = __ldg(s32 + 1);
@@ -55,37 +56,41 @@ __global__ void k_half_nearest(const uint8_t *__restrict__ src, int w, int h, si
 }
 
 int svs_i_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_stride, size_t img_stride,
-                       int n, uint8_t *dst, int dw, int dh, int dst_stride, size_t dst_img_pitch)
+                       int n, uint8_t *dst, int dw, int dh, int dst_stride, size_t dst_img_pitch,
+                       const uint8_t *const *src_ptrs_dev, int ptrs_aligned4)
 {
     if (n <= 0) return SVS_OK;
     int vec_ok = ((reinterpret_cast<uintptr_t>(src) | (2 * row_stride) | img_stride) & 3) == 0 &&
                  ((reinterpret_cast<uintptr_t>(dst) | (size_t)dst_stride | dst_img_pitch) & 3) == 0;
+    if (src_ptrs_dev) vec_ok = ptrs_aligned4 && ((2 * row_stride) & 3) == 0 &&
+                               ((reinterpret_cast<uintptr_t>(dst) | (size_t)dst_stride | dst_img_pitch) & 3) == 0;
     dim3 blk(32, 8);
     dim3 grd((dw + 4 * 32 - 1) / (4 * 32), (dh + 7) / 8, n);
-    k_half_nearest<<<grd, blk, 0, c->stream>>>(src, w, h, row_stride, img_stride, dst, dw, dh, dst_stride,
+    k_half_nearest<<<grd, blk, 0, c->stream>>>(src, src_ptrs_dev, w, h, row_stride, img_stride, dst, dw, dh, dst_stride,
                                                dst_img_pitch, vec_ok);
     SVS_LAUNCH_CHECK(c);
     return SVS_OK;
 }
 
-__global__ void k_copy2d(const uint8_t *__restrict__ src, int w, int h, size_t row_stride, size_t img_stride,
-                         uint8_t *__restrict__ dst, int dst_stride, size_t dst_img_pitch)
+__global__ void k_copy2d(const uint8_t *__restrict__ src, const uint8_t *const *__restrict__ src_ptrs, int w, int h,
+                         size_t row_stride, size_t img_stride, uint8_t *__restrict__ dst, int dst_stride, size_t dst_img_pitch)
 {
     int img = blockIdx.z;
+    if (src_ptrs) { src = src_ptrs[img]; img_stride = 0; }
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= h || x >= w) return;
-    dst[(size_t)img * dst_img_pitch + (size_t)y * dst_stride + x] =
+    dst[(size_t)blockIdx.z * dst_img_pitch + (size_t)y * dst_stride + x] =
         __ldg(src + (size_t)img * img_stride + (size_t)y * row_stride + x);
 }
 
 int svs_i_copy_level0(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_stride, size_t img_stride, int n,
-                      const PyrDesc &d)
+                      const PyrDesc &d, const uint8_t *const *src_ptrs_dev)
 {
     if (n <= 0) return SVS_OK;
     dim3 blk(64, 4);
     dim3 grd((w + 63) / 64, (h + 3) / 4, n);
-    k_copy2d<<<grd, blk, 0, c->stream>>>(src, w, h, row_stride, img_stride, d.base + d.off[0], d.stride[0],
+    k_copy2d<<<grd, blk, 0, c->stream>>>(src, src_ptrs_dev, w, h, row_stride, img_stride, d.base + d.off[0], d.stride[0],
                                          d.img_pitch);
     SVS_LAUNCH_CHECK(c);
     return SVS_OK;

@@ -68,6 +68,8 @@ struct svs_frameset {
     long long pushes = 0;
     DevBuf pyr[3];     // storage of L[0], L[1], R
     DevBuf staging;    // raw input images when pushed from the host
+    DevBuf ptr_table;  // per-stream device pointers (push_ptrs with on_device)
+    PinBuf ptr_table_h;
 };
 
 #define SVS_CUDA(ctx, call)                                                              \
@@ -91,9 +93,10 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // images.cu
 int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t *bytes_per_image);
 int svs_i_half_nearest(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
-                       int n, uint8_t *dst_dev, int dw, int dh, int dst_stride, size_t dst_img_pitch);
+                       int n, uint8_t *dst_dev, int dw, int dh, int dst_stride, size_t dst_img_pitch,
+                       const uint8_t *const *src_ptrs_dev = nullptr, int ptrs_aligned4 = 0);
 int svs_i_copy_level0(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
-                      int n, const PyrDesc &d);
+                      int n, const PyrDesc &d, const uint8_t *const *src_ptrs_dev = nullptr);
 int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images);
 // gftt.cu
 int svs_i_gftt(svs_ctx *c, const uint8_t *img_dev, int w, int h, int stride, size_t img_pitch, int n_img,

@@ -1,0 +1,239 @@
+// Host-side mirror of the reference's classes on the hot path, written above the C ABI of
+// include/svslam.h (the reference is compiled C++, so the host side is C++ too).  Same class,
+// method and field names as the reference so its call sites read the same:
+//
+//   slam::Camera    include/StereoVisionSLAM/camera.h:9-57,   src/camera.cpp:6-86
+//   slam::Feature   include/StereoVisionSLAM/feature.h:14-35
+//   slam::Frame     include/StereoVisionSLAM/frame.h:9-78,    src/frame.cpp:10-35
+//   slam::MapPoint  include/StereoVisionSLAM/mappoint.h:14-53, src/mappoint.cpp:9-98
+//   slam::Map       include/StereoVisionSLAM/map.h:10-59,     src/map.cpp:6-209
+//   slam::Frontend  include/StereoVisionSLAM/frontend.h,      src/frontend.cpp:10-768
+//   slam::Backend   include/StereoVisionSLAM/backend.h,       src/backend.cpp:9-346
+//
+// Differences that are deliberate:
+//  * Eigen / Sophus / OpenCV types are replaced by the tiny fixed-size types below (those libraries are
+//    not available here); SE3 keeps Sophus' representation (unit quaternion + translation) and formulas.
+//  * Every third-party call site (GFTT detect, calcOpticalFlowPyrLK, triangulation, the two g2o blocks)
+//    is split into a prepare_* / finish_* pair so that many independent streams can be stepped in
+//    lock-step and each seam becomes ONE batched svs_* call over all streams (slam::StreamBatch).
+//  * Bundle adjustment runs on the synchronous schedule (inside UpdateMap), SURVEY.md §5.
+//  * Hash-map iteration orders that the reference leaves unspecified are fixed to ascending id.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <vector>
+
+namespace slam {
+
+// ------------------------------------------------------------------ math
+struct Vec2 { double x = 0, y = 0; };
+struct Vec3 {
+    double x = 0, y = 0, z = 0;
+    Vec3() {}
+    Vec3(double a, double b, double c) : x(a), y(b), z(c) {}
+    Vec3 operator+(const Vec3 &o) const { return {x + o.x, y + o.y, z + o.z}; }
+    Vec3 operator-(const Vec3 &o) const { return {x - o.x, y - o.y, z - o.z}; }
+    double norm() const { return std::sqrt(x * x + y * y + z * z); }
+};
+
+// Sophus::SE3d: unit quaternion (x,y,z,w) + translation; d = [qx qy qz qw tx ty tz] is the C-ABI layout.
+struct SE3 {
+    double d[7] = {0, 0, 0, 1, 0, 0, 0};
+    SE3() {}
+    static SE3 fromArray(const double *p) { SE3 T; for (int i = 0; i < 7; i++) T.d[i] = p[i]; return T; }
+    static SE3 fromTranslation(const Vec3 &t) { SE3 T; T.d[4] = t.x; T.d[5] = t.y; T.d[6] = t.z; return T; }
+    Vec3 rotate(const Vec3 &p) const;
+    Vec3 operator*(const Vec3 &p) const;           // point action
+    SE3 operator*(const SE3 &o) const;             // composition (Sophus renormalisation included)
+    SE3 inverse() const;
+    Vec3 translation() const { return {d[4], d[5], d[6]}; }
+    static SE3 exp(const double *tangent6);         // (upsilon, omega)
+    void log(double *tangent6) const;
+};
+
+// ------------------------------------------------------------------ camera
+class Camera {
+public:
+    typedef std::shared_ptr<Camera> Ptr;
+    double fx_ = 0, fy_ = 0, cx_ = 0, cy_ = 0, baseline_ = 0;
+    SE3 pose_, pose_inv_;   // extrinsic: stereo-system frame -> this camera
+    Camera() {}
+    Camera(double fx, double fy, double cx, double cy, double baseline, const SE3 &pose)
+        : fx_(fx), fy_(fy), cx_(cx), cy_(cy), baseline_(baseline), pose_(pose) { pose_inv_ = pose_.inverse(); }
+    SE3 pose() const { return pose_; }
+    void K(double k4[4]) const { k4[0] = fx_; k4[1] = fy_; k4[2] = cx_; k4[3] = cy_; }
+    Vec3 world2camera(const Vec3 &p_w, const SE3 &T_c_w) const { return pose_ * (T_c_w * p_w); }
+    Vec3 camera2world(const Vec3 &p_c, const SE3 &T_c_w) const { return T_c_w.inverse() * (pose_inv_ * p_c); }
+    Vec2 camera2pixel(const Vec3 &p_c) const { return {fx_ * p_c.x / p_c.z + cx_, fy_ * p_c.y / p_c.z + cy_}; }
+    Vec3 pixel2camera(const Vec2 &p_p, double depth = 1) const { return {(p_p.x - cx_) * depth / fx_, (p_p.y - cy_) * depth / fy_, depth}; }
+    Vec2 world2pixel(const Vec3 &p_w, const SE3 &T_c_w) const { return camera2pixel(world2camera(p_w, T_c_w)); }
+    Vec3 pixel2world(const Vec2 &p_p, const SE3 &T_c_w, double depth = 1) const { return camera2world(pixel2camera(p_p, depth), T_c_w); }
+};
+
+// ------------------------------------------------------------------ data model
+struct Feature {                // feature.h:23-30 (cv::KeyPoint reduced to what the path reads)
+    float x = 0, y = 0;         // position_.pt
+    float size = 0, response = 0;
+    long map_point_ = -1;       // weak_ptr<MapPoint> -> landmark id, -1 = expired / none
+    bool outlier_ = false;
+    bool is_on_left_image_ = true;
+    bool valid = true;          // false = the nullptr entries of Frame::feature_right_
+};
+
+class Frame {
+public:
+    typedef std::shared_ptr<Frame> Ptr;
+    unsigned long id_ = 0, keyframe_id_ = 0;
+    bool is_keyframe_ = false;
+    SE3 pose_;                  // T_cw
+    double time_stamp_ = 0;
+    std::vector<Feature> feature_left_, feature_right_;
+    long prev_keyframe_ = -1;   // keyframe id of the previous keyframe
+    SE3 relative_pose_pkf_;
+    SE3 Pose() const { return pose_; }
+    void SetPose(const SE3 &p) { pose_ = p; }
+};
+
+struct Observation {            // weak_ptr<Feature> of a keyframe feature
+    Frame *frame = nullptr;
+    bool left = true;
+    int index = 0;
+    bool operator==(const Observation &o) const { return frame == o.frame && left == o.left && index == o.index; }
+    Feature &feature() const { return left ? frame->feature_left_[index] : frame->feature_right_[index]; }
+};
+
+class MapPoint {
+public:
+    unsigned long id_ = 0;
+    bool is_outlier_ = false;
+    Vec3 pos_;
+    int observed_times_ = 0;
+    std::vector<Observation> observations_;   // std::list in the reference; insertion order kept
+    Vec3 Pos() const { return pos_; }
+    void SetPos(const Vec3 &p) { pos_ = p; }
+    void AddObservation(const Observation &o) { observations_.push_back(o); observed_times_++; }   // mappoint.cpp:22-36
+    void RemoveObservation(const Observation &o);                                                  // mappoint.cpp:38-78
+    const std::vector<Observation> &GetObs() const { return observations_; }
+};
+
+class Map {
+public:
+    typedef std::shared_ptr<Map> Ptr;
+    typedef std::map<unsigned long, MapPoint *> LandmarksType;     // ascending id (reference: unordered_map)
+    typedef std::map<unsigned long, Frame::Ptr> KeyframesType;
+    explicit Map(int num_active_keyframes) : num_active_keyframes_(num_active_keyframes) {}
+    void CleanMap();                                  // map.cpp:21-40
+    void InsertKeyFrame(Frame::Ptr frame);            // map.cpp:53-67
+    MapPoint *CreateNewMappoint();                    // mappoint.cpp:88-97 (id factory is per map = per stream)
+    void InsertMapPoint(MapPoint *mp);                // map.cpp:69-74
+    MapPoint *GetMapPoint(long id) { return id >= 0 ? landmarks_store_[(size_t)id].get() : nullptr; }
+    const LandmarksType &GetAllMapPoints() const { return landmarks_; }
+    const KeyframesType &GetAllKeyFrames() const { return keyframes_; }
+    const LandmarksType &GetActiveMapPoints() const { return active_landmarks_; }
+    const KeyframesType &GetActiveKeyFrames() const { return active_keyframes_; }
+private:
+    void RemoveOldKeyframe();                         // map.cpp:76-181
+    std::vector<std::unique_ptr<MapPoint>> landmarks_store_;
+    LandmarksType landmarks_, active_landmarks_;
+    KeyframesType keyframes_, active_keyframes_;
+    Frame::Ptr current_frame_;
+    int num_active_keyframes_ = 9;
+};
+
+// ------------------------------------------------------------------ configuration (Appendix C of SURVEY.md)
+struct Config {
+    int num_features = 150, num_features_init = 50, num_features_tracking = 50, num_features_tracking_bad = 20;
+    int num_features_needed_for_keyframe = 80;
+    double max_triangulation_depth = 300.0;
+    int num_active_keyframes = 10;
+    int backend_on = 1;
+    double chi2_th = 5.991;
+    // hard-coded constants of the reference, exposed so the synthetic config 4 can override them
+    double gftt_quality = 0.01, gftt_min_distance = 20.0;        // src/frontend.cpp:24
+    int lk_win = 11, lk_max_level = 3, lk_max_iter = 30;         // src/frontend.cpp:107-108
+    double lk_eps = 0.01;
+    int ba_max_iter = 10, ba_jacobian_mode = 0;                  // src/backend.cpp:164
+    int oracle_simd_granule = 32;
+};
+
+enum class FrontendStatus { INITING, TRACKING_GOOD, TRACKING_BAD, LOST };
+
+// Ragged request/response buffers of one stream for one batched seam call.
+struct LkRequest { std::vector<float> prev_xy, next_xy; std::vector<uint8_t> status; };
+struct PoseRequest { std::vector<double> pts_w, uv; double K[4]; double T0[7]; double T[7]; std::vector<uint8_t> outlier; int n_inlier = 0; std::vector<int> feat_index; };
+struct DetectRequest { std::vector<float> occupied_xy; std::vector<float> out_xy, out_resp; int out_n = 0; };
+struct TriRequest { std::vector<float> left_xy, right_xy; std::vector<double> xyz; std::vector<uint8_t> ok; std::vector<int> feat_index; };
+struct BaRequest {
+    std::vector<double> poses, lms, edge_uv, chi2;
+    std::vector<int32_t> edge_kf, edge_lm;
+    std::vector<uint8_t> edge_cam;
+    std::vector<unsigned long> kf_ids, lm_ids;
+    std::vector<Observation> edge_obs;
+};
+
+class Backend {
+public:
+    Backend(const Config &cfg) : chi2_th_(cfg.chi2_th) {}
+    void SetCameras(Camera::Ptr l, Camera::Ptr r) { cam_left_ = l; cam_right_ = r; }
+    void SetMap(Map::Ptr m) { map_ = m; }
+    // Backend::Optimize (src/backend.cpp:9-248) split around the g2o block (svs_ba_optimize):
+    bool prepare_Optimize(BaRequest &rq);      // graph construction :39-158, ascending ids
+    void finish_Optimize(BaRequest &rq);       // chi2 post-pass :167-213, write-back :224-231, relative poses :235-246
+    unsigned long max_keyframe_id_in_pipeline_ = 0, min_keyframe_id_in_pipeline_ = 0;
+    int last_outliers = 0, last_inliers = 0;
+private:
+    Camera::Ptr cam_left_, cam_right_;
+    Map::Ptr map_;
+    double chi2_th_;
+};
+
+class Frontend {
+public:
+    explicit Frontend(const Config &cfg);
+    void SetMap(Map::Ptr map) { map_ = map; }
+    void SetBackend(std::shared_ptr<Backend> b) { backend_ = b; }
+    void SetCameras(Camera::Ptr l, Camera::Ptr r) { camera_left_ = l; camera_right_ = r; }
+    FrontendStatus GetStatus() const { return status_; }
+    Frame::Ptr GetLastFrame() const { return last_frame_; }
+    Frame::Ptr CreateFrame();                     // Frame::CreateFrame (id factory per stream)
+
+    // Frontend::AddFrame (src/frontend.cpp:690-721) is driven by slam::StreamBatch through these phases.
+    void begin_AddFrame(Frame::Ptr frame, int img_w, int img_h);
+    //   Track (:645-688)
+    bool wants_track() const { return phase_track_; }
+    void prepare_TrackLastFrame(LkRequest &rq);          // :331-347
+    int finish_TrackLastFrame(const LkRequest &rq);      // :361-381
+    void prepare_EstimateCurrentPose(PoseRequest &rq);   // :408-471
+    int finish_EstimateCurrentPose(const PoseRequest &rq);   // :542-556, then status :665-679 and keyframe test :587
+    //   keyframe / init branch
+    bool wants_detect() const { return phase_detect_; }
+    void prepare_DetectFeatures(DetectRequest &rq);      // :42-47
+    int finish_DetectFeatures(const DetectRequest &rq);  // :55-59
+    void prepare_FindFeaturesInRight(LkRequest &rq);     // :82-100
+    int finish_FindFeaturesInRight(const LkRequest &rq); // :113-130
+    void prepare_Triangulate(TriRequest &rq);            // BuildInitMap :155-169 / TriangulateNewPoints :267-281
+    int finish_Triangulate(const TriRequest &rq);        // :174-192 / :286-307 ; returns 1 when the backend must run
+    bool wants_backend() const { return phase_backend_; }
+    void end_AddFrame();                                 // relative_motion_ :685, last_frame_ :718
+
+    int tracking_inliers_ = 0;
+    int last_detected = 0, last_right = 0, last_triangulated = 0, last_tracked = 0;
+    Frame::Ptr current_frame_, last_frame_;
+private:
+    void SetObservationsForKeyFrame();                   // :560-574
+    void InsertKeyframe_begin();                         // :587-616
+    Config cfg_;
+    FrontendStatus status_ = FrontendStatus::INITING;
+    Frame::Ptr frontend_current_kf_, frontend_prev_kf_;
+    SE3 relative_motion_;
+    Camera::Ptr camera_left_, camera_right_;
+    Map::Ptr map_;
+    std::shared_ptr<Backend> backend_;
+    int img_w_ = 0, img_h_ = 0;
+    unsigned long frame_factory_id_ = 0, keyframe_factory_id_ = 0;
+    bool phase_track_ = false, phase_detect_ = false, phase_backend_ = false, initing_ = false, init_ok_ = false;
+};
+
+}  // namespace slam

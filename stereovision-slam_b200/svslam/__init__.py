@@ -318,3 +318,93 @@ Context.ba_optimize = _ba_optimize
 Context.stereo_bm = _stereo_bm
 Context.bgr2gray = _bgr2gray
 Context.backproject = _backproject
+
+
+# ---------------------------------------------------------------- pipeline (svs_slam_*)
+class SlamConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "num_features", "num_features_init", "num_features_tracking", "num_features_tracking_bad",
+        "num_features_needed_for_keyframe", "num_active_keyframes", "backend_on", "lk_win", "lk_max_level",
+        "lk_max_iter", "ba_max_iter", "ba_jacobian_mode", "oracle_simd_granule")] + [(n, C.c_double) for n in (
+        "max_triangulation_depth", "chi2_th", "gftt_quality", "gftt_min_distance", "lk_eps")]
+
+
+class Slam:
+    """n_streams independent stereo streams stepped in lock-step: Frontend::AddFrame for a batch of streams."""
+
+    def __init__(self, ctx, n_streams, in_w, in_h, K, baseline, half=True, **cfg):
+        self.ctx, self.n = ctx, n_streams
+        lib = ctx.lib
+        lib.svs_slam_create.restype = C.c_void_p
+        lib.svs_slam_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double]
+        lib.svs_slam_destroy.argtypes = [C.c_void_p]
+        self.cfg = SlamConfig()
+        lib.svs_slam_default_config(C.byref(self.cfg))
+        for k, v in cfg.items():
+            if not hasattr(self.cfg, k):
+                raise KeyError(k)
+            setattr(self.cfg, k, v)
+        K = _f64(K)
+        self.h = lib.svs_slam_create(ctx.h, n_streams, in_w, in_h, int(bool(half)), C.byref(self.cfg), _p(K), baseline)
+        if not self.h:
+            raise SvsError("svs_slam_create failed: " + ctx.last_error())
+        self.in_w, self.in_h = in_w, in_h
+        self._lp = (C.c_void_p * n_streams)()
+        self._rp = (C.c_void_p * n_streams)()
+        self.poses = np.zeros((n_streams, 7))
+        self.status = np.zeros(n_streams, np.int32)
+        self.is_kf = np.zeros(n_streams, np.int32)
+        self.inliers = np.zeros(n_streams, np.int32)
+
+    def add_frames_ptrs(self, left_ptrs, right_ptrs, on_device=False, row_stride=None):
+        """left_ptrs/right_ptrs: one address per stream (host pinned or device memory)."""
+        for i in range(self.n):
+            self._lp[i] = int(left_ptrs[i])
+            self._rp[i] = int(right_ptrs[i])
+        rc = self.ctx.lib.svs_slam_add_frames(C.c_void_p(self.h), self._lp, self._rp, C.c_size_t(row_stride or self.in_w),
+                                              int(on_device), _p(self.poses), _p(self.status), _p(self.is_kf), _p(self.inliers))
+        self.ctx._chk(rc)
+        return self.poses
+
+    def add_frames(self, left, right):
+        """left/right: uint8 [n_streams, in_h, in_w] host arrays."""
+        left, right = _u8(left), _u8(right)
+        assert left.shape == (self.n, self.in_h, self.in_w) == right.shape
+        sz = self.in_w * self.in_h
+        return self.add_frames_ptrs([left.ctypes.data + i * sz for i in range(self.n)],
+                                    [right.ctypes.data + i * sz for i in range(self.n)])
+
+    def features(self, stream, right=False, cap=4096):
+        xy = np.zeros((cap, 2), np.float32)
+        ids = np.zeros(cap, np.int64)
+        valid = np.zeros(cap, np.uint8)
+        n = C.c_int(0)
+        self.ctx._chk(self.ctx.lib.svs_slam_get_features(C.c_void_p(self.h), stream, int(right), _p(xy), _p(ids), _p(valid), cap, C.byref(n)))
+        return xy[:n.value].copy(), ids[:n.value].copy(), valid[:n.value].copy()
+
+    def keyframes(self, stream, active_only=False, cap=100000):
+        kid = np.zeros(cap, np.int64); fid = np.zeros(cap, np.int64); poses = np.zeros((cap, 7))
+        n = C.c_int(0)
+        self.ctx._chk(self.ctx.lib.svs_slam_get_keyframes(C.c_void_p(self.h), stream, int(active_only), _p(kid), _p(fid), _p(poses), cap, C.byref(n)))
+        return kid[:n.value].copy(), fid[:n.value].copy(), poses[:n.value].copy()
+
+    def landmarks(self, stream, active_only=False, cap=2000000):
+        ids = np.zeros(cap, np.int64); xyz = np.zeros((cap, 3)); ot = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        self.ctx._chk(self.ctx.lib.svs_slam_get_landmarks(C.c_void_p(self.h), stream, int(active_only), _p(ids), _p(xyz), _p(ot), cap, C.byref(n)))
+        return ids[:n.value].copy(), xyz[:n.value].copy(), ot[:n.value].copy()
+
+    def counters(self):
+        ph = np.zeros(8); cn = np.zeros(6, np.int64)
+        self.ctx._chk(self.ctx.lib.svs_slam_get_counters(C.c_void_p(self.h), _p(ph), _p(cn)))
+        names = ("push", "track_lk", "pose_lm", "detect", "right_lk", "triangulate", "ba", "host")
+        cnames = ("frames", "keyframes", "ba_problems", "ba_iterations", "ba_trials", "ba_edges")
+        return dict(zip(names, ph.tolist())), dict(zip(cnames, cn.tolist()))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.svs_slam_destroy(C.c_void_p(self.h))
+            self.h = None
+
+
+Context.slam = lambda self, *a, **k: Slam(self, *a, **k)

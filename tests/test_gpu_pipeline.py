@@ -1,0 +1,128 @@
+"""GPU parity of the whole per-frame path (rows a0-a9): the batched C++/CUDA pipeline (svs_slam_*) against the CPU
+oracle pipeline on the same synthetic KITTI-shaped stereo frames.  north_star bar: bit-exact keypoint indices /
+counts, poses and landmark XYZ within 1e-4 relative."""
+import numpy as np
+import pytest
+
+from oracle import pipeline as op
+from svslam import synth
+from util import rel_to_norm
+
+pytestmark = pytest.mark.gpu
+
+N_FRAMES = 36
+
+
+@pytest.fixture(scope="module")
+def clip():
+    cor = synth.Corridor("kitti05", seed=0, n_frames=80)
+    L, R, T = cor.sequence(N_FRAMES)
+    return cor, L, R, T
+
+
+def _sync(slam, b, o):
+    """Teacher forcing: copy the engine's floating-point state into the oracle (discrete structure must already agree)."""
+    xy, _, _ = slam.features(b)
+    rxy, _, rvalid = slam.features(b, right=True)
+    kid, _, kposes = slam.keyframes(b)
+    lid, lxyz, _ = slam.landmarks(b)
+    o.force_state(slam.poses[b], xy, rxy, rvalid, dict(zip(kid.tolist(), kposes)), dict(zip(lid.tolist(), lxyz)))
+
+
+@pytest.mark.parametrize("backend_on", [1, 0])
+def test_pipeline_lockstep_matches_oracle(ctx, granule, clip, backend_on):
+    """Every frame starts from a bitwise-identical state (teacher forcing, see _sync): discrete results must be
+    identical, floating-point results within the per-frame tolerances below.  (Free-running, the reference's own
+    algorithm amplifies 1e-14 summation-order noise chaotically: LM without a convergence test, LK stopping at
+    0.01 px — see test_pipeline_free_running_accuracy and DESIGN.md §6.)"""
+    cor, L, R, T = clip
+    B = 3            # three streams: two in phase, one delayed by 5 frames (different keyframe timing)
+    delay = [0, 0, 5]
+    slam = ctx.slam(B, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, backend_on=backend_on, oracle_simd_granule=granule)
+    oracles = [op.Pipeline(cor.K_half(), cor.baseline, op.Cfg(backend_on=backend_on, granule=granule), stages="oracle") for _ in range(B)]
+    try:
+        n_kf = np.zeros(B, int)
+        exact = total = 0
+        worst = dict(xy=0.0, pose=0.0, lm=0.0)
+        for i in range(N_FRAMES - 5):
+            idx = [i + d for d in delay]
+            poses = slam.add_frames(L[idx], R[idx]).copy()
+            for b in range(B):
+                want = oracles[b].add_frame(L[idx[b]], R[idx[b]])
+                o = oracles[b]
+                assert slam.status[b] == o.status, (i, b)
+                assert bool(slam.is_kf[b]) == o.is_kf, (i, b)
+                n_kf[b] += o.is_kf
+                if i > 0:
+                    assert slam.inliers[b] == o.tracking_inliers, (i, b)
+                xy, ids, _ = slam.features(b)
+                wxy, wids = o.current_features()
+                assert len(xy) == len(wxy), (i, b)
+                assert np.array_equal(ids, wids), (i, b)                     # identical counts, order, landmark links
+                exact += np.array_equal(xy.view(np.uint32), wxy.view(np.uint32)); total += 1
+                worst["xy"] = max(worst["xy"], float(np.abs(xy - wxy).max()))
+                worst["pose"] = max(worst["pose"], float(np.abs(poses[b] - want).max() / max(1.0, np.abs(want[4:]).max())))
+                assert np.abs(xy - wxy).max() < 2e-2, (i, b)                 # LK stops at 0.01 px
+                assert np.abs(poses[b] - want).max() < 1e-5 * max(1.0, np.abs(want[4:]).max()), (i, b)
+                lid, lxyz, lot = slam.landmarks(b)
+                assert list(lid) == sorted(o.lms)
+                wl = np.array([o.lms[k].pos for k in sorted(o.lms)]).reshape(-1, 3)
+                worst["lm"] = max(worst["lm"], float(rel_to_norm(lxyz, wl).max()))
+                assert rel_to_norm(lxyz, wl).max() < 1e-4, (i, b)
+                assert list(lot) == [o.lms[k].observed_times for k in sorted(o.lms)]
+                kid, fid, kposes = slam.keyframes(b)
+                assert list(kid) == sorted(o.kfs) and list(fid) == [o.kfs[k].id for k in sorted(o.kfs)]
+                akid, _, _ = slam.keyframes(b, active_only=True)
+                assert list(akid) == sorted(o.active_kfs)
+                alid, _, _ = slam.landmarks(b, active_only=True)
+                assert list(alid) == sorted(o.active_lms)
+                _sync(slam, b, o)
+        assert (n_kf >= 3).all()
+        print("bit-identical keypoint frames %d/%d; worst per-frame diffs %s" % (exact, total, worst))
+        ph, cn = slam.counters()
+        assert cn["frames"] == B * (N_FRAMES - 5) and cn["keyframes"] == n_kf.sum()
+        if backend_on:
+            assert cn["ba_problems"] == n_kf.sum() and cn["ba_iterations"] > 0
+    finally:
+        slam.close()
+
+
+def test_pipeline_window_eviction_lockstep(ctx, granule, clip):
+    """A small window (num_active_keyframes = 3) forces Map::RemoveOldKeyframe / CleanMap on every keyframe."""
+    cor, L, R, T = clip
+    slam = ctx.slam(1, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, num_active_keyframes=3, oracle_simd_granule=granule)
+    o = op.Pipeline(cor.K_half(), cor.baseline, op.Cfg(num_active_keyframes=3, granule=granule), stages="oracle")
+    try:
+        for i in range(N_FRAMES):
+            est = slam.add_frames(L[i:i + 1], R[i:i + 1])[0].copy()
+            west = o.add_frame(L[i], R[i])
+            assert slam.status[0] == o.status and bool(slam.is_kf[0]) == o.is_kf and (i == 0 or slam.inliers[0] == o.tracking_inliers), i
+            assert np.abs(est - west).max() < 1e-5 * max(1.0, np.abs(west).max()), i
+            akid, _, _ = slam.keyframes(0, active_only=True)
+            assert list(akid) == sorted(o.active_kfs) and len(akid) <= 3
+            alid, _, aot = slam.landmarks(0, active_only=True)
+            assert list(alid) == sorted(o.active_lms)
+            assert list(aot) == [o.active_lms[k].observed_times for k in sorted(o.active_lms)]
+            _sync(slam, 0, o)
+        assert len(slam.keyframes(0)[0]) >= 5
+    finally:
+        slam.close()
+
+
+def test_pipeline_free_running_accuracy(ctx, granule, clip):
+    """Without teacher forcing the two implementations drift apart chaotically but must be equally accurate:
+    ATE against the generator's ground truth and the keyframe rate agree."""
+    cor, L, R, T = clip
+    slam = ctx.slam(1, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, oracle_simd_granule=granule)
+    o = op.Pipeline(cor.K_half(), cor.baseline, op.Cfg(granule=granule), stages="oracle")
+    try:
+        est, west, nk, wnk = [], [], 0, 0
+        for i in range(N_FRAMES):
+            est.append(slam.add_frames(L[i:i + 1], R[i:i + 1])[0].copy()); nk += int(slam.is_kf[0])
+            west.append(o.add_frame(L[i], R[i])); wnk += int(o.is_kf)
+        ate, wate = synth.ate_rmse(est, T), synth.ate_rmse(west, T)
+        print("ATE engine %.4f m, oracle %.4f m over %.1f m; keyframes %d / %d" % (ate, wate, 0.8 * N_FRAMES, nk, wnk))
+        assert ate < 0.10 and wate < 0.10 and abs(ate - wate) < 0.03
+        assert abs(nk - wnk) <= 1 and slam.status[0] == 1
+    finally:
+        slam.close()
