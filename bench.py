@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py — stereo frames/s of the StereoVision-SLAM hot path on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[1] — "KITTI seq-05 full pipeline (Frontend + Backend BA,
+loop closure off), 1xB200": synthetic 1226x370 stereo pairs (no KITTI data is available offline) from the
+ray-cast corridor generator with the seq-05 calibration, processed at the reference's half resolution
+613x185, num_features 150, BA window 10, synchronous BA schedule.  One STEP = one Frontend::AddFrame for every
+one of `--streams` independent stereo streams (a batch of stereo pairs), i.e. `streams` frames.
+
+  value  frames/s with the input images already resident in HBM
+  e2e    frames/s through the public C ABI with the images in pinned HOST memory (H2D copy of every frame
+         inside the timed region; poses / statuses are read back to the host every step)
+
+`--impl reference` times the reference's CPU path instead: the OpenCV stages through cv2 (the library the
+reference calls, with its exact arguments) and the g2o blocks through the C restatement in oracle/geom.c,
+one process per host core, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "stereovision-slam_b200"))
+
+METRIC = "stereo_frames_per_sec"
+UNIT = "frames/s"
+CALIB = "kitti05"
+WORKLOAD = ("KITTI seq-05-shaped full pipeline (Frontend GFTT+LK+triangulation+pose-LM, Backend BA window 10, "
+            "loop closure off), synthetic 1226x370 stereo pairs processed at 613x185")
+
+
+def log(*a):
+    if os.environ.get("SVS_BENCH_VERBOSE", "1") != "0":
+        print("[bench %.1fs]" % (time.perf_counter() - _T0), *a, file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
+def pingpong(i, n):
+    """Play a clip forward then backward (a physically valid camera motion) so any number of steps can be run."""
+    p = i % (2 * n - 2)
+    return p if p < n else 2 * n - 2 - p
+
+
+def make_clip(n_frames):
+    from svslam import synth
+    cor = synth.Corridor(CALIB, seed=5, n_frames=n_frames)
+    L, R, T = cor.sequence(n_frames)
+    return cor, L, R, T
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_worker(args):
+    """One independent stream on one host core: the reference's CPU path on `n` frames starting at `start`."""
+    start, n, clip_path, backend_on = args
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import pipeline as op
+    from svslam import synth
+    d = np.load(clip_path)
+    L, R = d["L"], d["R"]
+    cal = synth.CALIB[CALIB]
+    K = np.array([cal[2] * 0.5, cal[2] * 0.5, cal[3] * 0.5, cal[4] * 0.5])
+    p = op.Pipeline(K, cal[5], op.Cfg(backend_on=backend_on), stages="cv2", cv2=cv2)
+    nclip = len(L)
+    t0 = time.perf_counter()
+    kfs = 0
+    for i in range(n):
+        j = pingpong(start + i, nclip)
+        p.add_frame(L[j], R[j])
+        kfs += int(p.is_kf)
+    return time.perf_counter() - t0, n, kfs, p.status
+
+
+def cpu_reference_run(clip_path, frames_per_stream, n_procs, starts=None):
+    """Aggregate frames/s of n_procs independent CPU streams (one process per core)."""
+    import multiprocessing as mp
+    from oracle import geom
+    geom.build()
+    starts = starts or [(7 * i) % 24 for i in range(n_procs)]
+    jobs = [(starts[i], frames_per_stream, clip_path, 1) for i in range(n_procs)]
+    t0 = time.perf_counter()
+    if n_procs == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(n_procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    frames = sum(r[1] for r in res)
+    busy = max(r[0] for r in res)
+    return frames / busy, frames, wall, sum(r[2] for r in res)
+
+
+def save_clip(L, R):
+    path = "/tmp/svslam_bench_clip_%d.npz" % os.getpid()
+    np.savez(path, L=L, R=R)
+    return path
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cor, L, R, T = make_clip(args.clip_frames)
+    path = save_clip(L, R)
+    fps_list = []
+    # warm-up + K "steps": each step = every core runs `cpu_frames` frames of an independent stream
+    for s in range(args.warmup + args.steps):
+        fps, frames, wall, kfs = cpu_reference_run(path, args.cpu_frames, cores, [(7 * i + 3 * s) % 24 for i in range(cores)])
+        if s >= args.warmup:
+            fps_list.append((fps, frames, wall))
+    os.remove(path)
+    frames = sum(f[1] for f in fps_list)
+    busy = sum(f[1] / f[0] for f in fps_list)
+    value = frames / busy
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * busy / max(1, len(fps_list)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cpu_frames_per_stream_per_step": args.cpu_frames, "processes": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d processes x %d frames x %d steps; OpenCV stages through cv2 %s (the library the "
+                                   "reference calls), g2o blocks through oracle/geom.c (g2o is not installable here)" % (
+                                       cores, args.cpu_frames, args.steps, __import__("cv2").__version__)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import svslam
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    G = max(1, min(args.groups, args.streams))
+    ctxs = [svslam.Context(dev) for _ in range(G)]   # raises if libsvslam.so / a B200 is missing: no fallback
+    lib = ctxs[0].lib
+    lib.svs_kernel_name.restype = C.c_char_p
+    B = args.streams
+    gsz = [B // G + (1 if g < B % G else 0) for g in range(G)]
+    goff = np.concatenate([[0], np.cumsum(gsz)]).astype(int)
+    host_threads = max(1, (os.cpu_count() or 1) // G)
+    log("rendering clip ...")
+    cor, L, R, T = make_clip(args.clip_frames)
+    log("clip ready")
+    nclip = len(L)
+    Kh = cor.K_half()
+    img_bytes = cor.W * cor.H
+
+    # inputs: the clip lives once in HBM (value) and once in pinned host memory (e2e)
+    Ld = torch.from_numpy(L).cuda(dev); Rd = torch.from_numpy(R).cuda(dev)
+    Lh = torch.from_numpy(L).pin_memory(); Rh = torch.from_numpy(R).pin_memory()
+    starts = [((7 * b) % 24 + 5 * rank) % max(1, nclip - 1) for b in range(B)]
+
+    def ptrs(base_l, base_r, step, g):
+        idx = [pingpong(starts[b] + step, nclip) for b in range(goff[g], goff[g + 1])]
+        return [base_l + j * img_bytes for j in idx], [base_r + j * img_bytes for j in idx]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run_pass(on_device, timing):
+        slams = [ctxs[g].slam(gsz[g], cor.W, cor.H, Kh, cor.baseline, half=True, backend_on=1) for g in range(G)]
+        for s in slams:
+            s.set_threads(host_threads)
+        bl, br = (Ld.data_ptr(), Rd.data_ptr()) if on_device else (Lh.data_ptr(), Rh.data_ptr())
+        mode = 1 if on_device else args.h2d_mode      # e2e: 2 = zero-copy reads of pinned host frames, 0 = staged DMA copies
+        errors = []
+
+        def loop(g, lo, hi, phase_off):
+            try:
+                for s in range(lo, hi):
+                    lp, rp = ptrs(bl, br, s + phase_off, g)
+                    slams[g].add_frames_ptrs(lp, rp, on_device=mode)
+            except Exception as e:      # surface worker failures in the main thread
+                errors.append(e)
+
+        def run_all(lo, hi, phase_off=0):
+            th = [threading.Thread(target=loop, args=(g, lo, hi, phase_off)) for g in range(G)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            if errors:
+                raise errors[0]
+
+        # priming (untimed, before the W warm-up steps): run until the sliding BA window is full so that the timed
+        # steps see steady-state problem sizes (10 keyframes, ~2.5k edges); timing a cold pipeline would overstate
+        run_all(-args.priming, 0, 100000 * (2 * nclip - 2))
+        log("primed %d steps" % args.priming)
+        run_all(0, args.warmup)
+        for c in ctxs:
+            lib.svs_kernel_timing_reset(C.c_void_p(c.h))
+            lib.svs_kernel_timing_enable(C.c_void_p(c.h), 1 if timing else 0)
+        cn0 = [s.counters() for s in slams]
+        l0 = sum(c.launch_count() for c in ctxs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        run_all(args.warmup, args.warmup + args.steps)
+        torch.cuda.synchronize(dev)
+        e1.record()
+        e1.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        log("timed region done (on_device=%s)" % on_device)
+        ms = e0.elapsed_time(e1)
+        launches = sum(c.launch_count() for c in ctxs) - l0
+        cn1 = [s.counters() for s in slams]
+        lost = int(sum((s.status == 3).sum() for s in slams))
+        kern = {}
+        for c in ctxs:
+            nk = lib.svs_kernel_timing_get(C.c_void_p(c.h), None, None, 0)
+            kms = np.zeros(nk); kcnt = np.zeros(nk, np.int64)
+            lib.svs_kernel_timing_get(C.c_void_p(c.h), kms.ctypes.data_as(C.c_void_p), kcnt.ctypes.data_as(C.c_void_p), nk)
+            lib.svs_kernel_timing_enable(C.c_void_p(c.h), 0)
+            for i in range(nk):
+                if kcnt[i]:
+                    name = lib.svs_kernel_name(i).decode()
+                    a = kern.get(name, (0.0, 0))
+                    kern[name] = (a[0] + float(kms[i]), a[1] + int(kcnt[i]))
+        for s in slams:
+            s.close()
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        phases = {k: sum(c1[0][k] - c0[0][k] for c0, c1 in zip(cn0, cn1)) for k in cn1[0][0]}
+        counts = {k: sum(c1[1][k] - c0[1][k] for c0, c1 in zip(cn0, cn1)) for k in cn1[0][1]}
+        return dict(ms=ms, wall=wall, launches=launches, phases=phases, counts=counts, kern=kern, lost=lost)
+
+    sampler = ClockSampler(dev)
+    sampler.start()
+    dev_pass = run_pass(True, True)
+    clocks = sampler.stop()
+    e2e_pass = run_pass(False, False)
+
+    frames_total = B * args.steps * world
+    value = frames_total / (dev_pass["ms"] * 1e-3)
+    e2e = frames_total / (e2e_pass["ms"] * 1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (largest share of device time in the timed region)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    kern = dev_pass["kern"]
+    dom = max(kern, key=lambda k: kern[k][0]) if kern else None
+    cnt = dev_pass["counts"]
+    P = 613 * 185
+    # ALGORITHMIC bytes per unit (DESIGN.md §4 / SURVEY.md §8d)
+    alg = {
+        "k_half_nearest": 3.0 * P * B,                               # per launch (one eye of every stream)
+        "k_pyr_down": None,
+        "k_corner_response": 5.0 * P,                                # per image
+        "k_lk_track": 3700.0,                                        # per keypoint (nominal 5 iterations/level)
+        "k_pose_only_lm": 40.0,                                      # per edge per LM trial
+        "k_ba_window": None,
+    }
+    roof = None
+    if dom:
+        ms_tot, n_l = kern[dom]
+        avg_ms = ms_tot / max(1, n_l)
+        per_launch = None
+        if dom == "k_half_nearest":
+            per_launch = alg[dom]
+        elif dom == "k_corner_response":
+            per_launch = alg[dom] * cnt["keyframes"] / max(1, n_l)
+        elif dom == "k_ba_window":
+            # 316 E + 216 L + 576 N^2 bytes per LM trial, L ~ E/2.9, N = 10
+            E = cnt["ba_edges"] / max(1, n_l)
+            trials = cnt["ba_trials"] / max(1, n_l)
+            per_launch = (316.0 * E + 216.0 * E / 2.9 + 576.0 * 100 * cnt["ba_problems"] / max(1, n_l)) * trials / max(1, cnt["ba_problems"] / max(1, n_l))
+        elif dom == "k_lk_track":
+            per_launch = alg[dom] * 180.0 * B          # ~180 tracked keypoints per stream per launch
+        elif dom == "k_pose_only_lm":
+            per_launch = 40.0 * 150 * 56 * B           # ~150 edges x ~56 trials per stream
+        if per_launch is not None:
+            ach = per_launch / (avg_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "avg_launch_ms": avg_ms, "launches": n_l, "peak_source": peak_src,
+                    "note": "latency/FP64-bound solver kernel: KBs of L2-resident state per problem, the HBM fraction is "
+                            "reported as required but the limiter is dependent FP64 latency (DESIGN.md §4)"
+                    if dom in ("k_ba_window", "k_pose_only_lm", "k_lk_track") else "streaming stencil"}
+    dev_total = sum(v[0] for v in kern.values())
+    shares = {k: round(v[0] / dev_total, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])} if dev_total else {}
+
+    # ---- CPU baseline on this box (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        # in a clean subprocess (no CUDA / OpenMP state inherited), bounded by its own timeout
+        log("cpu baseline subprocess ...")
+        path = save_clip(L, R)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-clip", path, "--cpu-frames", str(args.cpu_frames)],
+                               capture_output=True, text=True, timeout=240)
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:      # the GPU line is still valid without it
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "cpu baseline failed: %r" % (e,)}
+        finally:
+            os.remove(path)
+
+    h2d = 2 * (cor.W * ((cor.H + 1) // 2)) * B      # only the even rows the half-resolution resize reads are copied
+    in_bytes = 2 * img_bytes * B
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_pass["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "streams_per_gpu": B, "context_groups": G, "frames_per_step": B * world, "num_features": 150,
+                   "num_active_keyframes": 10, "ba": "synchronous, analytic Jacobians", "clip_frames": nclip,
+                   "priming_steps": args.priming,
+                   "l2": "per-step input %.0f MB per GPU > 126 MB L2 (inputs larger than L2)" % (in_bytes / 1e6)
+                   if in_bytes > 126e6 else "per-step input %.0f MB per GPU (< L2; distinct frames every step)" % (in_bytes / 1e6)},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * (56 + 12),
+                "h2d": "zero-copy: the resize kernel reads the pinned host frames over PCIe" if args.h2d_mode == 2 else "staged strided DMA copies",
+                "ms_per_step": e2e_pass["ms"] / args.steps},
+        "gpu_launches": int(dev_pass["launches"]),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "detail": {"phase_seconds": {k: round(v, 4) for k, v in dev_pass["phases"].items()},
+                   "e2e_phase_seconds": {k: round(v, 4) for k, v in e2e_pass["phases"].items()},
+                   "counts": dev_pass["counts"], "kernel_ms": {k: [round(v[0], 3), v[1]] for k, v in kern.items()},
+                   "kernel_time_share": shares, "device_busy_frac": dev_total / dev_pass["ms"] if dev_pass["ms"] else None,
+                   "lost_streams": dev_pass["lost"], "host_threads": os.cpu_count(), "host_threads_per_group": host_threads,
+                   "ba_lm_iterations_per_sec": cnt["ba_iterations"] * world / (dev_pass["ms"] * 1e-3)},
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("SVS_BENCH_STREAMS", "256")))
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("SVS_BENCH_GROUPS", "4")),
+                    help="independent contexts (one CUDA stream + one host thread each) the streams are split over")
+    ap.add_argument("--h2d-mode", type=int, default=2, choices=[0, 2],
+                    help="e2e transfer of the pinned host frames: 2 zero-copy kernel reads over PCIe, 0 staged DMA copies")
+    ap.add_argument("--clip-frames", type=int, default=48)
+    ap.add_argument("--priming", type=int, default=70, help="untimed steps before warm-up so the BA window is full")
+    ap.add_argument("--cpu-frames", type=int, default=40, help="frames per stream per process for the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-clip", default=None, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.cpu_baseline_clip:
+        cores = os.cpu_count() or 1
+        fps, frames, wall, kfs = cpu_reference_run(args.cpu_baseline_clip, args.cpu_frames, cores)
+        fps1, _, _, _ = cpu_reference_run(args.cpu_baseline_clip, args.cpu_frames, 1)
+        print(json.dumps({"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "single_core_value": fps1,
+                          "sample": "%d processes x %d frames of the same workload (OpenCV stages through cv2 %s = the library "
+                                    "the reference calls, 1 thread each; g2o blocks through oracle/geom.c); one core alone: %.1f frames/s"
+                                    % (cores, args.cpu_frames, __import__("cv2").__version__, fps1)}))
+        return
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,13 @@ SVS_API int svs_sync(svs_ctx *ctx);                       /* cudaStreamSynchroni
 SVS_API void *svs_stream(svs_ctx *ctx);                   /* the cudaStream_t, for event timing */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 SVS_API long long svs_launch_count(svs_ctx *ctx);
+/* Optional per-kernel device timing: when enabled every kernel launch of this context is bracketed by CUDA events
+ * on the context stream; svs_kernel_timing_get returns accumulated milliseconds and launch counts per kernel class
+ * (names via svs_kernel_name) and the number of classes. */
+SVS_API int svs_kernel_timing_enable(svs_ctx *ctx, int on);
+SVS_API int svs_kernel_timing_reset(svs_ctx *ctx);
+SVS_API int svs_kernel_timing_get(svs_ctx *ctx, double *ms, long long *count, int n);
+SVS_API const char *svs_kernel_name(int kid);
 /* pinned host memory helpers (for callers without their own pinned allocator) */
 SVS_API void *svs_host_alloc(size_t bytes);
 SVS_API void svs_host_free(void *p);
@@ -70,8 +77,11 @@ SVS_API int svs_frameset_size(const svs_frameset *fs, int *w, int *h, int *n_lev
  * on_device != 0: the pointers are device pointers (inputs already resident in HBM). */
 SVS_API int svs_frameset_push(svs_ctx *ctx, svs_frameset *fs, const uint8_t *left, const uint8_t *right,
                               size_t row_stride, size_t img_stride_bytes, int on_device);
-/* Same, with one pointer per stream (left[b], right[b]): dense rows `row_stride` apart.  Host pointers should be
- * pinned (svs_host_alloc) for full PCIe bandwidth. */
+/* Same, with one pointer per stream (left[b], right[b]): dense rows `row_stride` apart.
+ *   on_device = 0  host memory (pinned for full PCIe bandwidth): staged with strided DMA copies of the rows the resize reads
+ *   on_device = 1  device memory
+ *   on_device = 2  pinned, device-addressable host memory (cudaHostAlloc / svs_host_alloc): zero-copy — the resize kernel
+ *                  reads the frames directly over PCIe, each needed row exactly once */
 SVS_API int svs_frameset_push_ptrs(svs_ctx *ctx, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right,
                                    size_t row_stride, int on_device);
 /* Copy a pyramid level back (tests).  which: 0 = current left, 1 = previous left, 2 = current right */
@@ -215,6 +225,9 @@ SVS_API int svs_slam_get_landmarks(svs_slam *s, int stream, int active_only, int
  * device time).  counters[6]: frames, keyframes, BA problems, BA iterations, BA trials, BA edges. */
 SVS_API int svs_slam_get_counters(svs_slam *s, double *phase_seconds, long long *counters);
 SVS_API svs_frameset *svs_slam_frameset(svs_slam *s);
+/* Host threads (OpenMP) this pipeline uses for its per-stream bookkeeping; several pipelines on distinct contexts may be
+ * stepped concurrently from different host threads (their kernels and copies overlap on the device). */
+SVS_API int svs_slam_set_threads(svs_slam *s, int n);
 
 #ifdef __cplusplus
 }

@@ -10,12 +10,71 @@ int svs_i_gftt_overflow(svs_ctx *c, int n_img, int *flag_host);
 
 static std::string g_create_err;
 
+void svs_i_prof_begin(svs_ctx *c, int kid)
+{
+    if (!c->prof) return;
+    SvsPendingEv p;
+    p.kid = kid;
+    cudaEvent_t *ev[2] = {&p.a, &p.b};
+    for (int i = 0; i < 2; i++) {
+        if (!c->prof_free.empty()) { *ev[i] = c->prof_free.back(); c->prof_free.pop_back(); }
+        else cudaEventCreate(ev[i]);
+    }
+    cudaEventRecord(p.a, c->stream);
+    c->prof_pending.push_back(p);
+}
+void svs_i_prof_end(svs_ctx *c)
+{
+    if (!c->prof || c->prof_pending.empty()) return;
+    cudaEventRecord(c->prof_pending.back().b, c->stream);
+}
+static void prof_harvest(svs_ctx *c)
+{
+    if (c->prof_pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (SvsPendingEv &p : c->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { c->prof_ms[p.kid] += ms; c->prof_n[p.kid]++; }
+        c->prof_free.push_back(p.a); c->prof_free.push_back(p.b);
+    }
+    c->prof_pending.clear();
+}
+
 extern "C" {
 
 static int frameset_finish_push(svs_ctx *c, svs_frameset *fs, const uint8_t *dl, const uint8_t *dr, size_t rs, size_t is,
-                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4);
+                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated = 0);
 
 int svs_version(void) { return 100; }
+
+int svs_kernel_timing_enable(svs_ctx *c, int on)
+{
+    if (!c) return SVS_ERR_ARG;
+    prof_harvest(c);
+    c->prof = on != 0;
+    return SVS_OK;
+}
+int svs_kernel_timing_reset(svs_ctx *c)
+{
+    if (!c) return SVS_ERR_ARG;
+    prof_harvest(c);
+    for (int i = 0; i < KID_COUNT; i++) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return SVS_OK;
+}
+int svs_kernel_timing_get(svs_ctx *c, double *ms /* n */, long long *count /* n */, int n)
+{
+    if (!c) return SVS_ERR_ARG;
+    prof_harvest(c);
+    for (int i = 0; i < n && i < KID_COUNT; i++) { if (ms) ms[i] = c->prof_ms[i]; if (count) count[i] = c->prof_n[i]; }
+    return KID_COUNT;
+}
+const char *svs_kernel_name(int kid)
+{
+    static const char *names[KID_COUNT] = {"k_half_nearest", "k_copy2d", "k_pyr_down", "k_mask_boxes", "k_corner_response",
+                                           "k_corner_select", "k_corner_greedy", "k_lk_track", "k_triangulate", "k_pose_only_lm",
+                                           "k_ba_window", "k_bm_prefilter", "k_bm_sad", "k_backproject", "k_bgr2gray", "misc"};
+    return (kid >= 0 && kid < KID_COUNT) ? names[kid] : "";
+}
 const char *svs_create_error(void) { return g_create_err.c_str(); }
 
 svs_ctx *svs_create(int device)
@@ -52,6 +111,8 @@ void svs_destroy(svs_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    prof_harvest(c);
+    for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
     DevBuf *d[] = {&c->d_in, &c->d_in2, &c->d_out, &c->d_out2, &c->d_tmp, &c->d_tmp2, &c->d_tmp3, &c->d_tmp4, &c->d_tmp5, &c->d_tmp6};
     for (DevBuf *b : d) b->release();
     c->h_in.release(); c->h_out.release();
@@ -60,7 +121,7 @@ void svs_destroy(svs_ctx *c)
 }
 
 const char *svs_last_error(svs_ctx *c) { return c ? c->err.c_str() : "null context"; }
-int svs_sync(svs_ctx *c) { SVS_CUDA(c, cudaStreamSynchronize(c->stream)); return SVS_OK; }
+int svs_sync(svs_ctx *c) { SVS_CUDA(c, cudaStreamSynchronize(c->stream)); if (c->prof_pending.size() > 4096) prof_harvest(c); return SVS_OK; }
 void *svs_stream(svs_ctx *c) { return (void *)c->stream; }
 long long svs_launch_count(svs_ctx *c) { return c->launches; }
 void *svs_host_alloc(size_t bytes) { void *p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }
@@ -123,33 +184,32 @@ int svs_frameset_push(svs_ctx *c, svs_frameset *fs, const uint8_t *left, const u
     SVS_CUDA(c, cudaSetDevice(c->device));
     const uint8_t *dl = left, *dr = right;
     size_t rs = row_stride, is = img_stride;
+    int decim = 0;
     if (!on_device) {
-        size_t dense = (size_t)fs->in_w * fs->in_h;
+        // the half-resolution resize reads only the even rows (dst[y][x] = src[2y][2x]): only those cross PCIe
+        const int rows = fs->half ? fs->H : fs->in_h;
+        const size_t src_pitch = fs->half ? 2 * row_stride : row_stride;
+        size_t dense = (size_t)fs->in_w * rows;
         SVS_CUDA(c, fs->staging.reserve(2 * dense * fs->B));
         uint8_t *sl = fs->staging.as<uint8_t>(), *sr = sl + dense * fs->B;
-        if (row_stride == (size_t)fs->in_w && img_stride == dense) {
-            SVS_CUDA(c, cudaMemcpyAsync(sl, left, dense * fs->B, cudaMemcpyHostToDevice, c->stream));
-            SVS_CUDA(c, cudaMemcpyAsync(sr, right, dense * fs->B, cudaMemcpyHostToDevice, c->stream));
-        } else {
-            for (int b = 0; b < fs->B; b++) {
-                SVS_CUDA(c, cudaMemcpy2DAsync(sl + dense * b, fs->in_w, left + img_stride * b, row_stride, fs->in_w, fs->in_h, cudaMemcpyHostToDevice, c->stream));
-                SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right + img_stride * b, row_stride, fs->in_w, fs->in_h, cudaMemcpyHostToDevice, c->stream));
-            }
+        for (int b = 0; b < fs->B; b++) {
+            SVS_CUDA(c, cudaMemcpy2DAsync(sl + dense * b, fs->in_w, left + img_stride * b, src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
+            SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right + img_stride * b, src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
         }
-        dl = sl; dr = sr; rs = fs->in_w; is = dense;
+        dl = sl; dr = sr; rs = fs->in_w; is = dense; decim = fs->half ? 1 : 0;
     }
-    return frameset_finish_push(c, fs, dl, dr, rs, is, nullptr, nullptr, 0);
+    return frameset_finish_push(c, fs, dl, dr, rs, is, nullptr, nullptr, 0, decim);
 }
 
 static int frameset_finish_push(svs_ctx *c, svs_frameset *fs, const uint8_t *dl, const uint8_t *dr, size_t rs, size_t is,
-                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4)
+                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated)
 {
     fs->cur ^= 1;
     fs->pushes++;
     PyrDesc &Lc = fs->L[fs->cur];
     if (fs->half) {
-        SVS_TRY(svs_i_half_nearest(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc.base + Lc.off[0], fs->W, fs->H, Lc.stride[0], Lc.img_pitch, pl, aligned4));
-        SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R.base + fs->R.off[0], fs->W, fs->H, fs->R.stride[0], fs->R.img_pitch, pr, aligned4));
+        SVS_TRY(svs_i_half_nearest(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc.base + Lc.off[0], fs->W, fs->H, Lc.stride[0], Lc.img_pitch, pl, aligned4, rows_decimated));
+        SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R.base + fs->R.off[0], fs->W, fs->H, fs->R.stride[0], fs->R.img_pitch, pr, aligned4, rows_decimated));
     } else {
         SVS_TRY(svs_i_copy_level0(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc, pl));
         SVS_TRY(svs_i_copy_level0(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R, pr));
@@ -166,6 +226,8 @@ int svs_frameset_push_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *l
     if (row_stride < (size_t)fs->in_w) SVS_FAIL(c, SVS_ERR_ARG, "frameset_push_ptrs: bad row stride");
     SVS_CUDA(c, cudaSetDevice(c->device));
     const int B = fs->B;
+    // on_device == 2: the pointers are PINNED HOST memory that the device can address (cudaHostAlloc / UVA): the resize
+    // kernel reads the frames straight over PCIe (each needed row exactly once), no staging copy.
     if (on_device) {
         SVS_CUDA(c, fs->ptr_table.reserve((size_t)2 * B * sizeof(void *)));
         SVS_CUDA(c, fs->ptr_table_h.reserve((size_t)2 * B * sizeof(void *)));
@@ -181,19 +243,19 @@ int svs_frameset_push_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *l
         const uint8_t *const *dp = fs->ptr_table.as<const uint8_t *>();
         return frameset_finish_push(c, fs, nullptr, nullptr, row_stride, 0, dp, dp + B, aligned4);
     }
-    size_t dense = (size_t)fs->in_w * fs->in_h;
+    // Staged path: only the even rows the half-resolution resize reads cross PCIe (strided 2-D DMA copies); the kernel
+    // then reads the staged rows with a unit row step.  (Whole-frame linear copies were measured slower in the
+    // multi-context setting, zero-copy — on_device == 2 — faster: DESIGN.md §7.)
+    const int rows = fs->half ? fs->H : fs->in_h;
+    const size_t src_pitch = fs->half ? 2 * row_stride : row_stride;
+    size_t dense = (size_t)fs->in_w * rows;
     SVS_CUDA(c, fs->staging.reserve(2 * dense * B));
     uint8_t *sl = fs->staging.as<uint8_t>(), *sr = sl + dense * B;
     for (int b = 0; b < B; b++) {
-        if (row_stride == (size_t)fs->in_w) {
-            SVS_CUDA(c, cudaMemcpyAsync(sl + dense * b, left[b], dense, cudaMemcpyHostToDevice, c->stream));
-            SVS_CUDA(c, cudaMemcpyAsync(sr + dense * b, right[b], dense, cudaMemcpyHostToDevice, c->stream));
-        } else {
-            SVS_CUDA(c, cudaMemcpy2DAsync(sl + dense * b, fs->in_w, left[b], row_stride, fs->in_w, fs->in_h, cudaMemcpyHostToDevice, c->stream));
-            SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right[b], row_stride, fs->in_w, fs->in_h, cudaMemcpyHostToDevice, c->stream));
-        }
+        SVS_CUDA(c, cudaMemcpy2DAsync(sl + dense * b, fs->in_w, left[b], src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
+        SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right[b], src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
     }
-    return frameset_finish_push(c, fs, sl, sr, fs->in_w, dense, nullptr, nullptr, 0);
+    return frameset_finish_push(c, fs, sl, sr, fs->in_w, dense, nullptr, nullptr, 0, fs->half ? 1 : 0);
 }
 
 int svs_frameset_download(svs_ctx *c, svs_frameset *fs, int stream, int which, int level, uint8_t *out, int out_stride)

@@ -614,8 +614,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
         SVS_CUDA(c, cudaFuncSetAttribute(k_ba_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         attr_set = max_smem;
     }
-    k_ba_window<<<n_prob, BA_T, max_smem, c->stream>>>(A);
-    SVS_LAUNCH_CHECK(c);
+    SVS_KERNEL(c, KID_BA_WINDOW, k_ba_window<<<n_prob, BA_T, max_smem, c->stream>>>(A));
     uint8_t *ho = c->h_out.as<uint8_t>();
     SVS_CUDA(c, cudaMemcpyAsync(ho, c->d_out.p, out_b, cudaMemcpyDeviceToHost, c->stream));
     size_t ho_pose = align_up(out_b, 16), ho_lm = ho_pose + (size_t)sumN * 56;

@@ -282,10 +282,9 @@ int svs_triangulate(svs_ctx *c, const float *left_xy, const float *right_xy, int
     memcpy(hb + xy_b, right_xy, xy_b);
     SVS_CUDA(c, cudaMemcpyAsync(db, hb, 2 * xy_b, cudaMemcpyHostToDevice, c->stream));
     uint8_t *dob = c->d_out.as<uint8_t>();
-    k_triangulate<<<(n + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<float *>(db), reinterpret_cast<float *>(db + xy_b), n,
+    SVS_KERNEL(c, KID_TRIANGULATE, k_triangulate<<<(n + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<float *>(db), reinterpret_cast<float *>(db + xy_b), n,
                                                           Kl[0], Kl[1], Kl[2], Kl[3], Kr[0], Kr[1], Kr[2], Kr[3], baseline,
-                                                          reinterpret_cast<double *>(dob), dob + o_b);
-    SVS_LAUNCH_CHECK(c);
+                                                          reinterpret_cast<double *>(dob), dob + o_b));
     SVS_CUDA(c, cudaMemcpyAsync(c->h_out.p, dob, o_b + n, cudaMemcpyDeviceToHost, c->stream));
     SVS_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(out_xyz, c->h_out.p, o_b);
@@ -318,12 +317,11 @@ int svs_pose_only_lm(svs_ctx *c, int n_prob, const int32_t *off, const double *p
     memcpy(hb + off_b + p_b + u_b + k_b, T0, t_b);
     SVS_CUDA(c, cudaMemcpyAsync(db, hb, in_b, cudaMemcpyHostToDevice, c->stream));
     uint8_t *dob = c->d_out.as<uint8_t>();
-    k_pose_only_lm<<<(n_prob + PO_WARPS - 1) / PO_WARPS, PO_WARPS * 32, 0, c->stream>>>(
+    SVS_KERNEL(c, KID_POSE_LM, k_pose_only_lm<<<(n_prob + PO_WARPS - 1) / PO_WARPS, PO_WARPS * 32, 0, c->stream>>>(
         n_prob, reinterpret_cast<int32_t *>(db), reinterpret_cast<double *>(db + off_b), reinterpret_cast<double *>(db + off_b + p_b),
         reinterpret_cast<double *>(db + off_b + p_b + u_b), reinterpret_cast<double *>(db + off_b + p_b + u_b + k_b), chi2_th, rounds,
         iters, reinterpret_cast<double *>(dob), dob + t_b + st_b + ni_b, reinterpret_cast<int32_t *>(dob + t_b + st_b),
-        reinterpret_cast<svs_lm_stats *>(dob + t_b));
-    SVS_LAUNCH_CHECK(c);
+        reinterpret_cast<svs_lm_stats *>(dob + t_b)));
     SVS_CUDA(c, cudaMemcpyAsync(c->h_out.p, dob, out_b, cudaMemcpyDeviceToHost, c->stream));
     SVS_CUDA(c, cudaStreamSynchronize(c->stream));
     uint8_t *ho = c->h_out.as<uint8_t>();

@@ -292,17 +292,15 @@ int svs_i_gftt(svs_ctx *c, const uint8_t *img, int w, int h, int stride, size_t 
         SVS_CUDA(c, c->d_tmp3.reserve(P * n_img));
         mask_dev = c->d_tmp3.as<uint8_t>();
         SVS_CUDA(c, cudaMemsetAsync(mask_dev, 255, P * n_img, c->stream));
-        k_mask_boxes<<<n_occ_total, 128, 0, c->stream>>>(mask_dev, w, h, occ_off, n_img, occ_xy);
-        SVS_LAUNCH_CHECK(c);
+        SVS_KERNEL(c, KID_MASK, k_mask_boxes<<<n_occ_total, 128, 0, c->stream>>>(mask_dev, w, h, occ_off, n_img, occ_xy));
     }
     const double s = 1.0 / (4.0 * 3.0 * 255.0);
     float ks = (float)s, k2 = (float)(2.0 * s);
     int body = granule > 0 ? (w / granule) * granule : 0;
     int n_strips = (w + CR_OUT - 1) / CR_OUT;
     dim3 grd((n_strips + 3) / 4, n_img);
-    k_corner_response<<<grd, 128, 0, c->stream>>>(img, img_pitch, img_ids, w, h, stride, mask_dev, eig, maxbits, ks,
-                                                  k2, body);
-    SVS_LAUNCH_CHECK(c);
+    SVS_KERNEL(c, KID_CORNER_RESPONSE, k_corner_response<<<grd, 128, 0, c->stream>>>(img, img_pitch, img_ids, w, h, stride, mask_dev, eig, maxbits, ks,
+                                                  k2, body));
     if (max_corners <= 0) return SVS_OK;
     size_t cap = next_pow2(P / 4 + 1);
     SVS_CUDA(c, c->d_tmp4.reserve(cap * n_img * sizeof(unsigned long long)));
@@ -310,8 +308,7 @@ int svs_i_gftt(svs_ctx *c, const uint8_t *img, int w, int h, int stride, size_t 
     {
         dim3 blk(64, 4);
         dim3 g2((w - 2 + 63) / 64, (h - 2 + 3) / 4, n_img);
-        k_corner_select<<<g2, blk, 0, c->stream>>>(eig, mask_dev, w, h, maxbits, quality, cand, cap, count);
-        SVS_LAUNCH_CHECK(c);
+        SVS_KERNEL(c, KID_CORNER_SELECT, k_corner_select<<<g2, blk, 0, c->stream>>>(eig, mask_dev, w, h, maxbits, quality, cand, cap, count));
     }
     {
         size_t smem = GR_SMEM_KEYS * sizeof(unsigned long long) + ((P + 31) / 32) * 4;
@@ -321,9 +318,8 @@ int svs_i_gftt(svs_ctx *c, const uint8_t *img, int w, int h, int stride, size_t 
             SVS_CUDA(c, cudaFuncSetAttribute(k_corner_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = smem;
         }
-        k_corner_greedy<<<n_img, GR_T, smem, c->stream>>>(cand, cap, count, w, h, max_corners, min_distance, out_xy,
-                                                          out_resp, out_n, overflow);
-        SVS_LAUNCH_CHECK(c);
+        SVS_KERNEL(c, KID_CORNER_GREEDY, k_corner_greedy<<<n_img, GR_T, smem, c->stream>>>(cand, cap, count, w, h, max_corners, min_distance, out_xy,
+                                                          out_resp, out_n, overflow));
     }
     // overflow is checked by the caller after it synchronises (svs_i_gftt_overflow)
     return SVS_OK;

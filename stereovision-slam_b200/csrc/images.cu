@@ -35,14 +35,14 @@ int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t
 // dst[y][x] = src[min(2y,h-1)][min(2x,w-1)]; each thread produces 4 output pixels.
 __global__ void k_half_nearest(const uint8_t *__restrict__ src, const uint8_t *const *__restrict__ src_ptrs, int w, int h,
                                size_t row_stride, size_t img_stride, uint8_t *__restrict__ dst, int dw, int dh, int dst_stride,
-                               size_t dst_img_pitch, int vec_ok)
+                               size_t dst_img_pitch, int vec_ok, int rows_decimated)
 {
     int img = blockIdx.z;
     if (src_ptrs) { src = src_ptrs[img]; img_stride = 0; }
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (y >= dh || x4 >= dw) return;
-    int sy = min(2 * y, h - 1);
+    int sy = rows_decimated ? y : min(2 * y, h - 1);   // decimated staging already holds rows 0,2,4,...
     const uint8_t *srow = src + (size_t)img * img_stride + (size_t)sy * row_stride;
     uint8_t *drow = dst + (size_t)blockIdx.z * dst_img_pitch + (size_t)y * dst_stride;
     if (vec_ok && x4 + 4 <= dw && 2 * x4 + 8 <= w) {
@@ -57,18 +57,17 @@ __global__ void k_half_nearest(const uint8_t *__restrict__ src, const uint8_t *c
 
 int svs_i_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_stride, size_t img_stride,
                        int n, uint8_t *dst, int dw, int dh, int dst_stride, size_t dst_img_pitch,
-                       const uint8_t *const *src_ptrs_dev, int ptrs_aligned4)
+                       const uint8_t *const *src_ptrs_dev, int ptrs_aligned4, int rows_decimated)
 {
     if (n <= 0) return SVS_OK;
-    int vec_ok = ((reinterpret_cast<uintptr_t>(src) | (2 * row_stride) | img_stride) & 3) == 0 &&
+    int vec_ok = ((reinterpret_cast<uintptr_t>(src) | ((rows_decimated ? 1 : 2) * row_stride) | img_stride) & 3) == 0 &&
                  ((reinterpret_cast<uintptr_t>(dst) | (size_t)dst_stride | dst_img_pitch) & 3) == 0;
     if (src_ptrs_dev) vec_ok = ptrs_aligned4 && ((2 * row_stride) & 3) == 0 &&
                                ((reinterpret_cast<uintptr_t>(dst) | (size_t)dst_stride | dst_img_pitch) & 3) == 0;
     dim3 blk(32, 8);
     dim3 grd((dw + 4 * 32 - 1) / (4 * 32), (dh + 7) / 8, n);
-    k_half_nearest<<<grd, blk, 0, c->stream>>>(src, src_ptrs_dev, w, h, row_stride, img_stride, dst, dw, dh, dst_stride,
-                                               dst_img_pitch, vec_ok);
-    SVS_LAUNCH_CHECK(c);
+    SVS_KERNEL(c, KID_HALF, k_half_nearest<<<grd, blk, 0, c->stream>>>(src, src_ptrs_dev, w, h, row_stride, img_stride, dst, dw, dh, dst_stride,
+                                               dst_img_pitch, vec_ok, rows_decimated));
     return SVS_OK;
 }
 
@@ -90,9 +89,8 @@ int svs_i_copy_level0(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_s
     if (n <= 0) return SVS_OK;
     dim3 blk(64, 4);
     dim3 grd((w + 63) / 64, (h + 3) / 4, n);
-    k_copy2d<<<grd, blk, 0, c->stream>>>(src, src_ptrs_dev, w, h, row_stride, img_stride, d.base + d.off[0], d.stride[0],
-                                         d.img_pitch);
-    SVS_LAUNCH_CHECK(c);
+    SVS_KERNEL(c, KID_COPY0, k_copy2d<<<grd, blk, 0, c->stream>>>(src, src_ptrs_dev, w, h, row_stride, img_stride, d.base + d.off[0], d.stride[0],
+                                         d.img_pitch));
     return SVS_OK;
 }
 
@@ -145,9 +143,8 @@ int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images)
     for (int l = 1; l < d.nlev; l++) {
         dim3 blk(PD_TX, PD_TY);
         dim3 grd((d.w[l] + PD_TX - 1) / PD_TX, (d.h[l] + PD_TY - 1) / PD_TY, n_images);
-        k_pyr_down<<<grd, blk, 0, c->stream>>>(d.base + d.off[l - 1], d.w[l - 1], d.h[l - 1], d.stride[l - 1],
-                                               d.base + d.off[l], d.w[l], d.h[l], d.stride[l], d.img_pitch);
-        SVS_LAUNCH_CHECK(c);
+        SVS_KERNEL(c, KID_PYRDOWN, k_pyr_down<<<grd, blk, 0, c->stream>>>(d.base + d.off[l - 1], d.w[l - 1], d.h[l - 1], d.stride[l - 1],
+                                               d.base + d.off[l], d.w[l], d.h[l], d.stride[l], d.img_pitch));
     }
     return SVS_OK;
 }

@@ -192,12 +192,15 @@ int svs_i_lk(svs_ctx *c, const PyrDesc &prev, const PyrDesc &next, const int32_t
         k_lk_track<WN><<<blocks, LK_WARPS * 32, 0, c->stream>>>(prev, next, pt_img, prev_xy, next_xy, n_pts, \
                                                                 max_iter, eps2, status);                     \
         break;
+    svs_i_prof_begin(c, KID_LK);
     switch (win) {
         LK_CASE(5) LK_CASE(7) LK_CASE(9) LK_CASE(11) LK_CASE(13) LK_CASE(15) LK_CASE(21)
     default:
+        svs_i_prof_end(c);
         SVS_FAIL(c, SVS_ERR_ARG, "lk: window size must be one of 5,7,9,11,13,15,21");
     }
 #undef LK_CASE
+    svs_i_prof_end(c);
     SVS_LAUNCH_CHECK(c);
     return SVS_OK;
 }

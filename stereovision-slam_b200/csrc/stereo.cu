@@ -208,8 +208,7 @@ int svs_bgr2gray(svs_ctx *c, const uint8_t *bgr, int w, int h, int n, uint8_t *g
     SVS_CUDA(c, c->d_in.reserve(px * 3));
     SVS_CUDA(c, c->d_out.reserve(px));
     SVS_CUDA(c, cudaMemcpyAsync(c->d_in.p, bgr, px * 3, cudaMemcpyHostToDevice, c->stream));
-    k_bgr2gray<<<(unsigned)((px + 255) / 256), 256, 0, c->stream>>>(c->d_in.as<uint8_t>(), c->d_out.as<uint8_t>(), px);
-    SVS_LAUNCH_CHECK(c);
+    SVS_KERNEL(c, KID_BGR2GRAY, k_bgr2gray<<<(unsigned)((px + 255) / 256), 256, 0, c->stream>>>(c->d_in.as<uint8_t>(), c->d_out.as<uint8_t>(), px));
     SVS_CUDA(c, cudaMemcpyAsync(gray, c->d_out.p, px, cudaMemcpyDeviceToHost, c->stream));
     SVS_CUDA(c, cudaStreamSynchronize(c->stream));
     return SVS_OK;
@@ -227,12 +226,9 @@ int svs_i_stereo_bm(svs_ctx *c, const uint8_t *l_dev, const uint8_t *r_dev, int 
     SVS_CUDA(c, c->d_tmp.reserve(2 * px * n));
     uint8_t *Lp = c->d_tmp.as<uint8_t>(), *Rp = Lp + px * n;
     dim3 pb(64, 4), pg((w + 63) / 64, (h + 3) / 4, n);
-    k_bm_prefilter<<<pg, pb, 0, c->stream>>>(l_dev, w, h, stride, img_stride, Lp, cap);
-    SVS_LAUNCH_CHECK(c);
-    k_bm_prefilter<<<pg, pb, 0, c->stream>>>(r_dev, w, h, stride, img_stride, Rp, cap);
-    SVS_LAUNCH_CHECK(c);
-    k_fill_i16<<<(unsigned)((px * n + 255) / 256), 256, 0, c->stream>>>(disp_dev, px * n, (int16_t)-16);
-    SVS_LAUNCH_CHECK(c);
+    SVS_KERNEL(c, KID_BM_PREFILTER, k_bm_prefilter<<<pg, pb, 0, c->stream>>>(l_dev, w, h, stride, img_stride, Lp, cap));
+    SVS_KERNEL(c, KID_BM_PREFILTER, k_bm_prefilter<<<pg, pb, 0, c->stream>>>(r_dev, w, h, stride, img_stride, Rp, cap));
+    SVS_KERNEL(c, KID_MISC, k_fill_i16<<<(unsigned)((px * n + 255) / 256), 256, 0, c->stream>>>(disp_dev, px * n, (int16_t)-16));
     int nx = w - r - (ndisp - 1 + r), ny = h - 2 * r;
     if (nx <= 0 || ny <= 0) return SVS_OK;
     int cpitch = CW | 1;
@@ -244,8 +240,7 @@ int svs_i_stereo_bm(svs_ctx *c, const uint8_t *l_dev, const uint8_t *r_dev, int 
         attr_set = smem;
     }
     dim3 g((nx + BM_TW - 1) / BM_TW, (ny + BM_RS - 1) / BM_RS, n);
-    k_bm_sad<<<g, BM_T, smem, c->stream>>>(Lp, Rp, w, h, ndisp, r, cap, 10, 15, disp_dev);
-    SVS_LAUNCH_CHECK(c);
+    SVS_KERNEL(c, KID_BM_SAD, k_bm_sad<<<g, BM_T, smem, c->stream>>>(Lp, Rp, w, h, ndisp, r, cap, 10, 15, disp_dev));
     return SVS_OK;
 }
 
@@ -296,13 +291,10 @@ int svs_backproject(svs_ctx *c, const int16_t *disp, const uint8_t *bgr, int w, 
     SVS_CUDA(c, cudaMemcpyAsync(c->d_in.p, disp, px * 2, cudaMemcpyHostToDevice, c->stream));
     SVS_CUDA(c, cudaMemcpyAsync(c->d_in2.p, bgr, px * 3, cudaMemcpyHostToDevice, c->stream));
     float fb = (float)K[0] * (float)baseline;   // (focal_length * baseline) in f32, src/dense_reconstruction.cpp:120-136
-    k_bp_count<<<(w + 127) / 128, 128, 0, c->stream>>>(c->d_in.as<int16_t>(), w, h, fb, colc);
-    SVS_LAUNCH_CHECK(c);
-    k_bp_scan<<<1, 32, 0, c->stream>>>(colc, w, total);
-    SVS_LAUNCH_CHECK(c);
-    k_bp_emit<<<(w + 127) / 128, 128, 0, c->stream>>>(c->d_in.as<int16_t>(), c->d_in2.as<uint8_t>(), w, h, fb, K[0], K[1], K[2], K[3],
-                                                      dT, dT + 7, colc, c->d_out.as<float>(), c->d_out2.as<uint8_t>());
-    SVS_LAUNCH_CHECK(c);
+    SVS_KERNEL(c, KID_BACKPROJECT, k_bp_count<<<(w + 127) / 128, 128, 0, c->stream>>>(c->d_in.as<int16_t>(), w, h, fb, colc));
+    SVS_KERNEL(c, KID_BACKPROJECT, k_bp_scan<<<1, 32, 0, c->stream>>>(colc, w, total));
+    SVS_KERNEL(c, KID_BACKPROJECT, k_bp_emit<<<(w + 127) / 128, 128, 0, c->stream>>>(c->d_in.as<int16_t>(), c->d_in2.as<uint8_t>(), w, h, fb, K[0], K[1], K[2], K[3],
+                                                      dT, dT + 7, colc, c->d_out.as<float>(), c->d_out2.as<uint8_t>()));
     int tot = 0;
     SVS_CUDA(c, cudaMemcpyAsync(&tot, total, 4, cudaMemcpyDeviceToHost, c->stream));
     SVS_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -26,7 +26,7 @@ struct DevBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
+        size_t want = 2 * bytes + 4096;   // geometric growth: regrowing is a device-wide sync
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -41,7 +41,7 @@ struct PinBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
+        size_t want = 2 * bytes + 4096;
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -50,7 +50,18 @@ struct PinBuf {
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+// Kernel classes for the optional per-kernel CUDA-event timing (svs_kernel_timing_*; bench.py's roofline).
+enum SvsKernelId { KID_HALF = 0, KID_COPY0, KID_PYRDOWN, KID_MASK, KID_CORNER_RESPONSE, KID_CORNER_SELECT, KID_CORNER_GREEDY,
+                   KID_LK, KID_TRIANGULATE, KID_POSE_LM, KID_BA_WINDOW, KID_BM_PREFILTER, KID_BM_SAD, KID_BACKPROJECT,
+                   KID_BGR2GRAY, KID_MISC, KID_COUNT };
+struct SvsPendingEv { int kid; cudaEvent_t a, b; };
+
 struct svs_ctx {
+    bool prof = false;
+    std::vector<SvsPendingEv> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[KID_COUNT] = {0};
+    long long prof_n[KID_COUNT] = {0};
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -86,6 +97,11 @@ struct svs_frameset {
     do { int r__ = (call); if (r__ != SVS_OK) return r__; } while (0)
 #define SVS_LAUNCH_CHECK(ctx)                                                            \
     do { (ctx)->launches++; SVS_CUDA(ctx, cudaGetLastError()); } while (0)
+// Bracket one kernel launch with CUDA events on the context stream when timing is enabled.
+void svs_i_prof_begin(svs_ctx *c, int kid);
+void svs_i_prof_end(svs_ctx *c);
+#define SVS_KERNEL(ctx, kid, ...)                                                        \
+    do { svs_i_prof_begin(ctx, kid); __VA_ARGS__; svs_i_prof_end(ctx); SVS_LAUNCH_CHECK(ctx); } while (0)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -94,7 +110,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t *bytes_per_image);
 int svs_i_half_nearest(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
                        int n, uint8_t *dst_dev, int dw, int dh, int dst_stride, size_t dst_img_pitch,
-                       const uint8_t *const *src_ptrs_dev = nullptr, int ptrs_aligned4 = 0);
+                       const uint8_t *const *src_ptrs_dev = nullptr, int ptrs_aligned4 = 0, int rows_decimated = 0);
 int svs_i_copy_level0(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
                       int n, const PyrDesc &d, const uint8_t *const *src_ptrs_dev = nullptr);
 int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images);

@@ -2,6 +2,7 @@
 // classes (slam.h) do the per-stream bookkeeping (OpenMP over streams), and every third-party seam of
 // Frontend::AddFrame / Backend::Optimize becomes ONE batched call into the C ABI (include/svslam.h) per step.
 // Exposed through the svs_slam_* entry points (C ABI) for tests, bench.py and a C++ caller.
+#include <omp.h>
 #include <chrono>
 #include <cstring>
 #include <new>
@@ -58,6 +59,7 @@ public:
 
     int step(const uint8_t *const *left, const uint8_t *const *right, size_t row_stride, int on_device);
 
+    void set_threads(int n) { threads_ = n > 0 ? n : 1; }
     double t_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // push, track-lk, pose, detect, right-lk, triangulate, ba, host
     long long frames = 0, keyframes = 0, ba_problems = 0, ba_iterations = 0, ba_trials = 0, ba_edges = 0;
 
@@ -66,6 +68,7 @@ private:
     svs_frameset *fs_ = nullptr;
     Config cfg_;
     int W_ = 0, H_ = 0;
+    int threads_ = omp_get_max_threads();
     double baseline_ = 0;
     Camera::Ptr cam_left_, cam_right_;
     std::vector<Stream> streams_;
@@ -91,7 +94,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
     if (rc) return rc;
     t1 = now_s(); t_phase[0] += t1 - t0; t0 = t1;
 
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         s.ran_track = s.ran_detect = s.ran_backend = s.is_kf = false;
@@ -130,7 +133,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
     t1 = now_s(); t_phase[1] += t1 - t0; t0 = t1;
 
     // ---------------- EstimateCurrentPose: pose-only LM (src/frontend.cpp:408-527)
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (!s.ran_track) continue;
@@ -169,7 +172,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         }
         t1 = now_s(); t_phase[2] += t1 - t0; t0 = t1;
     }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (s.ran_track) s.frontend->finish_EstimateCurrentPose(s.pose);
@@ -203,7 +206,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         t1 = now_s(); t_phase[3] += t1 - t0; t0 = t1;
     }
     // ---------------- FindFeaturesInRight: LK current-left -> current-right (src/frontend.cpp:105-109)
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (!s.ran_detect) continue;
@@ -214,7 +217,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
     if ((rc = run_lk(1, [](const Stream &s) { return s.ran_detect; }))) return rc;
     t1 = now_s(); t_phase[4] += t1 - t0; t0 = t1;
     // ---------------- triangulation of new landmarks (src/frontend.cpp:174, :286)
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (!s.ran_detect) continue;
@@ -248,7 +251,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         t1 = now_s(); t_phase[5] += t1 - t0; t0 = t1;
     }
     // ---------------- Backend::UpdateMap -> Optimize, synchronous schedule (src/backend.cpp:9-248)
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (!s.ran_detect) continue;
@@ -299,7 +302,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         t1 = now_s(); t_phase[6] += t1 - t0; t0 = t1;
     }
     long long nkf = 0;
-#pragma omp parallel for schedule(static) reduction(+ : nkf)
+#pragma omp parallel for schedule(static) reduction(+ : nkf) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (s.ran_backend) s.backend->finish_Optimize(s.ba);
@@ -441,5 +444,12 @@ int svs_slam_get_counters(svs_slam *s, double *phase_seconds /* 8 */, long long 
 }
 
 svs_frameset *svs_slam_frameset(svs_slam *s) { return s ? s->batch->frameset() : nullptr; }
+
+int svs_slam_set_threads(svs_slam *s, int n)
+{
+    if (!s) return SVS_ERR_ARG;
+    s->batch->set_threads(n);
+    return SVS_OK;
+}
 
 }  // extern "C"

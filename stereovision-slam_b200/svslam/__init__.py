@@ -401,6 +401,9 @@ class Slam:
         cnames = ("frames", "keyframes", "ba_problems", "ba_iterations", "ba_trials", "ba_edges")
         return dict(zip(names, ph.tolist())), dict(zip(cnames, cn.tolist()))
 
+    def set_threads(self, n):
+        self.ctx._chk(self.ctx.lib.svs_slam_set_threads(C.c_void_p(self.h), int(n)))
+
     def close(self):
         if self.h:
             self.ctx.lib.svs_slam_destroy(C.c_void_p(self.h))
