@@ -208,7 +208,8 @@ def run_gpu(args, rank, world, local_rank):
     # inputs: the clip lives once in HBM (value) and once in pinned host memory (e2e)
     Ld = torch.from_numpy(L).cuda(dev); Rd = torch.from_numpy(R).cuda(dev)
     Lh = torch.from_numpy(L).pin_memory(); Rh = torch.from_numpy(R).pin_memory()
-    starts = [((7 * b) % 24 + 5 * rank) % max(1, nclip - 1) for b in range(B)]
+    from svslam import dist as sdist
+    starts = sdist.clip_starts(B, rank, nclip)
 
     def ptrs(base_l, base_r, step, g):
         idx = [pingpong(starts[b] + step, nclip) for b in range(goff[g], goff[g + 1])]
