@@ -26,6 +26,10 @@ import time
 
 import numpy as np
 
+# OpenMP teams of several pipelines / ranks share the host cores: never spin-wait (must be set before libgomp loads)
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "stereovision-slam_b200"))
@@ -197,7 +201,12 @@ def run_gpu(args, rank, world, local_rank):
     B = args.streams
     gsz = [B // G + (1 if g < B % G else 0) for g in range(G)]
     goff = np.concatenate([[0], np.cumsum(gsz)]).astype(int)
-    host_threads = max(1, (os.cpu_count() or 1) // G)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    host_threads = max(1, cores // (max(1, local_world) * G))
     log("rendering clip ...")
     cor, L, R, T = make_clip(args.clip_frames)
     log("clip ready")
@@ -390,7 +399,7 @@ def run_gpu(args, rank, world, local_rank):
                    "e2e_phase_seconds": {k: round(v, 4) for k, v in e2e_pass["phases"].items()},
                    "counts": dev_pass["counts"], "kernel_ms": {k: [round(v[0], 3), v[1]] for k, v in kern.items()},
                    "kernel_time_share": shares, "device_busy_frac": dev_total / dev_pass["ms"] if dev_pass["ms"] else None,
-                   "lost_streams": dev_pass["lost"], "host_threads": os.cpu_count(), "host_threads_per_group": host_threads,
+                   "lost_streams": dev_pass["lost"], "host_cores": cores, "host_threads_per_group": host_threads,
                    "ba_lm_iterations_per_sec": cnt["ba_iterations"] * world / (dev_pass["ms"] * 1e-3)},
     }
     print(json.dumps(out))
