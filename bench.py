@@ -234,14 +234,19 @@ def run_gpu(args, rank, world, local_rank):
         for s in slams:
             s.set_threads(host_threads)
         bl, br = (Ld.data_ptr(), Rd.data_ptr()) if on_device else (Lh.data_ptr(), Rh.data_ptr())
-        mode = 1 if on_device else args.h2d_mode      # e2e: 2 = zero-copy reads of pinned host frames, 0 = staged DMA copies
+        # e2e ingest: 2 = zero-copy kernel reads of the pinned host frames, 0 = staged strided DMA copies,
+        # 3 = mixed (even groups zero-copy, odd groups DMA) so SM-initiated reads and the copy engines share PCIe
+        def mode_of(g):
+            if on_device:
+                return 1
+            return args.h2d_mode if args.h2d_mode != 3 else (2 if g % 2 == 0 else 0)
         errors = []
 
         def loop(g, lo, hi, phase_off):
             try:
                 for s in range(lo, hi):
                     lp, rp = ptrs(bl, br, s + phase_off, g)
-                    slams[g].add_frames_ptrs(lp, rp, on_device=mode)
+                    slams[g].add_frames_ptrs(lp, rp, on_device=mode_of(g))
             except Exception as e:      # surface worker failures in the main thread
                 errors.append(e)
 
@@ -390,7 +395,7 @@ def run_gpu(args, rank, world, local_rank):
                    if in_bytes > 126e6 else "per-step input %.0f MB per GPU (< L2; distinct frames every step)" % (in_bytes / 1e6)},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * (56 + 12),
-                "h2d": "zero-copy: the resize kernel reads the pinned host frames over PCIe" if args.h2d_mode == 2 else "staged strided DMA copies",
+                "h2d": {2: "zero-copy: the resize kernel reads the pinned host frames over PCIe", 0: "staged strided DMA copies of the even rows", 3: "mixed: even context groups zero-copy, odd groups strided DMA"}[args.h2d_mode],
                 "ms_per_step": e2e_pass["ms"] / args.steps},
         "gpu_launches": int(dev_pass["launches"]),
         "roofline": roof,
@@ -416,7 +421,7 @@ def main():
     ap.add_argument("--streams", type=int, default=int(os.environ.get("SVS_BENCH_STREAMS", "256")))
     ap.add_argument("--groups", type=int, default=int(os.environ.get("SVS_BENCH_GROUPS", "4")),
                     help="independent contexts (one CUDA stream + one host thread each) the streams are split over")
-    ap.add_argument("--h2d-mode", type=int, default=2, choices=[0, 2],
+    ap.add_argument("--h2d-mode", type=int, default=2, choices=[0, 2, 3],
                     help="e2e transfer of the pinned host frames: 2 zero-copy kernel reads over PCIe, 0 staged DMA copies")
     ap.add_argument("--clip-frames", type=int, default=48)
     ap.add_argument("--priming", type=int, default=70, help="untimed steps before warm-up so the BA window is full")

@@ -12,8 +12,9 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-fopenmp", "--fmad=false"]
-# --fmad=false everywhere: the image kernels must round exactly where OpenCV rounds; the FP64
-# geometry kernels spell their fused operations explicitly (fma()).
+# --fmad=false for the image kernels: they must round exactly where OpenCV rounds.  The FP64 solver files may
+# contract to FMA (fewer instructions, better accuracy; parity there is a 1e-9 tolerance, not bit-exactness).
+FMA_OK = {"ba.cu", "geom.cu"}
 
 
 def sources():
@@ -45,7 +46,10 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, os.path.basename(s) + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_t):
-            cmd = [NVCC] + ARCH + COMMON + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", s, "-o", o]
+            flags = list(COMMON)
+            if os.path.basename(s) in FMA_OK:
+                flags.remove("--fmad=false")
+            cmd = [NVCC] + ARCH + flags + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):

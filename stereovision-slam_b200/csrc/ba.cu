@@ -29,7 +29,8 @@ struct BaProb {
     int poff0;      // p_off[poff0 + a ..] (NA+1 entries), values relative to e0
     int blk0;       // blk_i/blk_j/blk_off[blk0 + b] ; blk_off has nblk+1 entries at blk0 + prob index shift (see host)
     int boff0;
-    int pair0;      // pair_e1/pair_e2[pair0 + ...], values are edge indices relative to e0
+    int pair0;      // first contribution record of this problem (records are sorted by block)
+    int epoff0;     // ep_off[epoff0 + e .. ] (E+1 entries): per-edge list of record positions (relative to pair0)
     long long S_off;  // offset (doubles) into the global reduced-system scratch, or -1 when it fits shared memory
 };
 
@@ -41,7 +42,8 @@ struct BaArgs {
     const uint8_t *edge_cam;
     const double *edge_uv;
     const int32_t *l_off, *l_edges, *p_off, *p_edges;
-    const int32_t *blk_i, *blk_j, *blk_off, *pair_e1, *pair_e2;
+    const int32_t *blk_i, *blk_j, *blk_off, *ep_off, *ep_pos;
+    double *contrib;                // 36 doubles per (edge, edge) pair record
     double *Hpl, *WD;               // 18 / edge
     double *Hll, *Dinv;             // 9 / landmark
     double *bl, *xl, *lmT;          // 3 / landmark
@@ -163,7 +165,7 @@ __device__ bool block_ldlt_solve(double *S, int pitch, int n, const double *g, d
     return ok;
 }
 
-__global__ void __launch_bounds__(BA_T)
+__global__ void __launch_bounds__(BA_T, 2)
 k_ba_window(BaArgs A)
 {
     extern __shared__ double smd[];
@@ -323,7 +325,7 @@ k_ba_window(BaArgs A)
                 int a = i / 36, r = (i % 36) / 6, c2 = i % 6;
                 S[(6 * a + r) * pitch + 6 * a + c2] = Hpp[i] + (r == c2 ? lambda : 0.0);
             }
-            // ---- V^-1 and W V^-1
+            // ---- V^-1 per landmark
             for (int l = tid; l < L; l += BA_T) {
                 int s0 = l_off[l], s1 = l_off[l + 1];
                 if (s0 == s1) continue;
@@ -334,28 +336,44 @@ k_ba_window(BaArgs A)
                 if (!gd::inv3(D, Di)) s_flag = 0;
 #pragma unroll
                 for (int x = 0; x < 9; x++) Dinv[9 * (size_t)l + x] = Di[x];
-                for (int s = s0; s < s1; s++) {
-                    int e = l_edges[s];
-                    const double *W = Hpl + 18 * (size_t)e;
-                    double *O = WD + 18 * (size_t)e;
+            }
+            __syncthreads();
+            // ---- per EDGE: W V^-1, and the 6x6 contributions (W V^-1)_e1 W_e2^T for every edge e2 of the same landmark
+            //      with pose(e1) <= pose(e2), written once into block-sorted contiguous records
+            const int32_t *ep_off = A.ep_off + P.epoff0, *ep_pos = A.ep_pos + P.pair0;
+            double *contrib = A.contrib + 36 * (size_t)P.pair0;
+            for (int e = tid; e < E; e += BA_T) {
+                int l = edge_l[e], p1 = edge_p[e];
+                const double *Di = Dinv + 9 * (size_t)l, *W = Hpl + 18 * (size_t)e;
+                double X[18];
 #pragma unroll
-                    for (int x = 0; x < 6; x++)
+                for (int x = 0; x < 6; x++)
 #pragma unroll
-                        for (int y = 0; y < 3; y++) O[x * 3 + y] = W[x * 3] * Di[y] + W[x * 3 + 1] * Di[3 + y] + W[x * 3 + 2] * Di[6 + y];
+                    for (int y = 0; y < 3; y++) X[x * 3 + y] = W[x * 3] * Di[y] + W[x * 3 + 1] * Di[3 + y] + W[x * 3 + 2] * Di[6 + y];
+                double *O = WD + 18 * (size_t)e;
+#pragma unroll
+                for (int x = 0; x < 18; x++) O[x] = X[x];
+                int q = ep_off[e];
+                for (int s = l_off[l]; s < l_off[l + 1]; s++) {
+                    int e2 = l_edges[s];
+                    if (p1 > edge_p[e2]) continue;
+                    const double *Y = Hpl + 18 * (size_t)e2;
+                    double *C = contrib + 36 * (size_t)ep_pos[q++];
+#pragma unroll
+                    for (int r = 0; r < 6; r++)
+#pragma unroll
+                        for (int c2 = 0; c2 < 6; c2++)
+                            C[r * 6 + c2] = X[r * 3] * Y[c2 * 3] + X[r * 3 + 1] * Y[c2 * 3 + 1] + X[r * 3 + 2] * Y[c2 * 3 + 2];
                 }
             }
             __syncthreads();
-            // ---- S_ij -= sum over the block's (e1,e2) pairs of (W V^-1)_e1 W_e2^T   (36 threads own a block)
+            // ---- S_ij -= sum of the block's records (36 threads own a block; coalesced, fixed order => deterministic)
             const int32_t *blk_i = A.blk_i + P.blk0, *blk_j = A.blk_j + P.blk0, *blk_off = A.blk_off + P.boff0;
-            const int32_t *pe1 = A.pair_e1 + P.pair0, *pe2 = A.pair_e2 + P.pair0;
             for (int t = tid; t < P.nblk * 36; t += BA_T) {
                 int bk = t / 36, ent = t - 36 * bk, r = ent / 6, c2 = ent - 6 * r;
                 double sum = 0;
-                for (int s = blk_off[bk]; s < blk_off[bk + 1]; s++) {
-                    const double *X = WD + 18 * (size_t)pe1[s] + 3 * r;
-                    const double *Y = Hpl + 18 * (size_t)pe2[s] + 3 * c2;
-                    sum += X[0] * Y[0] + X[1] * Y[1] + X[2] * Y[2];
-                }
+                const double *C = contrib + ent;
+                for (int s = blk_off[bk]; s < blk_off[bk + 1]; s++) sum += C[36 * (size_t)s];
                 int i = blk_i[bk], j = blk_j[bk];
                 double v = S[(6 * i + r) * pitch + 6 * j + c2] - sum;
                 S[(6 * i + r) * pitch + 6 * j + c2] = v;
@@ -482,7 +500,8 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
 
     // ---- host-side structure: active poses, CSR by landmark / pose, per-block pair lists
     std::vector<BaProb> probs(n_prob);
-    std::vector<int32_t> act_pose, edge_p(sumE), l_off, l_edges(sumE), p_off, p_edges(sumE), blk_i, blk_j, blk_off, pe1, pe2;
+    std::vector<int32_t> act_pose, edge_p(sumE), l_off, l_edges(sumE), p_off, p_edges(sumE), blk_i, blk_j, blk_off, ep_off, ep_pos;
+    long long pairs_total = 0;
     const size_t smem_cap = 200 * 1024;
     size_t max_smem = 0;
     long long S_tot = 0;
@@ -517,7 +536,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
         { std::vector<int> fill(pc.begin(), pc.end() - 1);
           for (int e = 0; e < E; e++) p_edges[e0 + fill[edge_p[e0 + e]]++] = e; }
         // pair lists per upper block (i <= j): counting sort on block id i*NA + j
-        P.blk0 = (int)blk_i.size(); P.boff0 = (int)blk_off.size(); P.pair0 = (int)pe1.size();
+        P.blk0 = (int)blk_i.size(); P.boff0 = (int)blk_off.size(); P.pair0 = (int)ep_pos.size(); P.epoff0 = (int)ep_off.size();
         std::vector<int> bcount((size_t)NA * NA + 1, 0);
         const int32_t *lo = l_off.data() + P.loff0;
         for (int l = 0; l < L; l++)
@@ -526,29 +545,34 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
                     int i = edge_p[e0 + l_edges[e0 + s1]], j = edge_p[e0 + l_edges[e0 + s2]];
                     if (i <= j) bcount[(size_t)i * NA + j + 1]++;
                 }
-        std::vector<int> bmap((size_t)NA * NA, -1);
         int nblk = 0, run = 0;
         blk_off.push_back(0);
         std::vector<int> bstart((size_t)NA * NA, 0);
         for (size_t k = 0; k < (size_t)NA * NA; k++) {
             int cn = bcount[k + 1];
             if (cn > 0) {
-                bmap[k] = nblk++; bstart[k] = run; run += cn;
+                nblk++; bstart[k] = run; run += cn;
                 blk_i.push_back((int)(k / NA)); blk_j.push_back((int)(k % NA));
                 blk_off.push_back(run);
             }
         }
         P.nblk = nblk;
-        size_t pbase = pe1.size();
-        pe1.resize(pbase + run); pe2.resize(pbase + run);
+        // per-edge record positions: edge e1 (in edge order) enumerates the edges e2 of its landmark in list order and
+        // keeps those with pose(e1) <= pose(e2); each such pair gets the next free slot of its block
+        size_t pbase = ep_pos.size();
+        ep_pos.resize(pbase + run);
         std::vector<int> bfill(bstart);
-        for (int l = 0; l < L; l++)
-            for (int s1 = lo[l]; s1 < lo[l + 1]; s1++)
-                for (int s2 = lo[l]; s2 < lo[l + 1]; s2++) {
-                    int ea = l_edges[e0 + s1], eb = l_edges[e0 + s2];
-                    int i = edge_p[e0 + ea], j = edge_p[e0 + eb];
-                    if (i <= j) { int pos = bfill[(size_t)i * NA + j]++; pe1[pbase + pos] = ea; pe2[pbase + pos] = eb; }
-                }
+        int q = 0;
+        for (int e = 0; e < E; e++) {
+            ep_off.push_back(q);
+            int l = edge_lm[e0 + e], i = edge_p[e0 + e];
+            for (int s2 = lo[l]; s2 < lo[l + 1]; s2++) {
+                int j = edge_p[e0 + l_edges[e0 + s2]];
+                if (i <= j) ep_pos[pbase + q++] = bfill[(size_t)i * NA + j]++;
+            }
+        }
+        ep_off.push_back(q);
+        pairs_total += run;
         size_t with = ba_smem_bytes(NA, true);
         if (with <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, with); }
         else { P.S_off = S_tot; size_t np = 6 * (size_t)NA; S_tot += (long long)(np * (np | 1)); max_smem = std::max(max_smem, ba_smem_bytes(NA, false)); }
@@ -573,8 +597,8 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     size_t o_bi = add(blk_i.data(), blk_i.size() * 4);
     size_t o_bj = add(blk_j.data(), blk_j.size() * 4);
     size_t o_bo = add(blk_off.data(), blk_off.size() * 4);
-    size_t o_p1 = add(pe1.data(), pe1.size() * 4);
-    size_t o_p2 = add(pe2.data(), pe2.size() * 4);
+    size_t o_p1 = add(ep_off.data(), ep_off.size() * 4);
+    size_t o_p2 = add(ep_pos.data(), ep_pos.size() * 4);
     size_t o_pose = add(poses, (size_t)sumN * 56);
     size_t o_lm = add(lms, (size_t)sumL * 24);
     SVS_CUDA(c, c->h_in.reserve(tot + 16));
@@ -583,7 +607,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     for (const Seg &s : segs) if (s.bytes) memcpy(hb + s.off, s.src, s.bytes);
     SVS_CUDA(c, cudaMemcpyAsync(db, hb, tot, cudaMemcpyHostToDevice, c->stream));
     // scratch
-    size_t sc_b = ((size_t)sumE * 36 + (size_t)sumL * 27 + (size_t)S_tot) * 8 + 64;
+    size_t sc_b = ((size_t)sumE * 36 + (size_t)sumL * 27 + (size_t)S_tot + (size_t)pairs_total * 36) * 8 + 64;
     SVS_CUDA(c, c->d_tmp.reserve(sc_b));
     size_t out_b = (size_t)sumE * 8 + (size_t)n_prob * sizeof(svs_ba_stats);
     SVS_CUDA(c, c->d_out.reserve(out_b + 16));
@@ -599,11 +623,12 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     A.p_off = reinterpret_cast<int32_t *>(db + o_po); A.p_edges = reinterpret_cast<int32_t *>(db + o_pe);
     A.blk_i = reinterpret_cast<int32_t *>(db + o_bi); A.blk_j = reinterpret_cast<int32_t *>(db + o_bj);
     A.blk_off = reinterpret_cast<int32_t *>(db + o_bo);
-    A.pair_e1 = reinterpret_cast<int32_t *>(db + o_p1); A.pair_e2 = reinterpret_cast<int32_t *>(db + o_p2);
+    A.ep_off = reinterpret_cast<int32_t *>(db + o_p1); A.ep_pos = reinterpret_cast<int32_t *>(db + o_p2);
     A.Hpl = scr; A.WD = A.Hpl + (size_t)sumE * 18;
     A.Hll = A.WD + (size_t)sumE * 18; A.Dinv = A.Hll + (size_t)sumL * 9;
     A.bl = A.Dinv + (size_t)sumL * 9; A.xl = A.bl + (size_t)sumL * 3; A.lmT = A.xl + (size_t)sumL * 3;
     A.S_glob = A.lmT + (size_t)sumL * 3;
+    A.contrib = A.S_glob + (size_t)S_tot;
     A.edge_chi2 = c->d_out.as<double>();
     A.stats = reinterpret_cast<svs_ba_stats *>(c->d_out.as<uint8_t>() + (size_t)sumE * 8);
     for (int i = 0; i < 4; i++) { A.K[0][i] = K_left[i]; A.K[1][i] = K_right[i]; }

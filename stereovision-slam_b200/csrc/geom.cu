@@ -116,6 +116,87 @@ __device__ bool ldlt6_solve(double *A /* 36, lower used, destroyed */, const dou
     return true;
 }
 
+// 6x6 LDL^T without pivoting, fully unrolled (register resident).  H is packed upper (21), lambda added to the
+// diagonal.  For the symmetric positive definite H + lambda I of the pose problem this gives the same solution as
+// Eigen's pivoted LDLT up to rounding; "isPositive" = no negative pivot.
+__device__ __forceinline__ bool ldlt6_reg(const double *Hp, double lambda, const double *b, double *x)
+{
+    double A[6][6];
+    {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = a; c < 6; c++) { A[c][a] = Hp[k]; k++; }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) A[a][a] += lambda;
+    double d[6];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double dj = A[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) dj -= A[j][k] * A[j][k] * d[k];
+        d[j] = dj;
+        if (dj < 0.0) ok = false;
+        double inv = (fabs(dj) > DBL_MIN) ? 1.0 / dj : 0.0;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            double v = A[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) v -= A[i][k] * A[j][k] * d[k];
+            A[i][j] = v * inv;
+        }
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double v = b[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) v -= A[i][k] * y[k];
+        y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] = (fabs(d[i]) > DBL_MIN) ? y[i] / d[i] : 0.0;
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        double v = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) v -= A[k][i] * x[k];
+        x[i] = v;
+    }
+    return ok;
+}
+
+// Sum 32 per-lane values across the warp so that EVERY lane ends with all 32 totals (bitwise identical on all lanes):
+// recursive-halving reduce-scatter (31 shuffle steps) + an all-gather through shared memory.
+__device__ __forceinline__ void warp_allreduce32(double *v /* 32 per lane, in/out */, double *sm /* 32 doubles per warp */, int lane)
+{
+#pragma unroll
+    for (int o = 16, n = 32; o > 0; o >>= 1, n >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (i < n / 2) {
+                double send = up ? v[i] : v[i + n / 2];
+                double keep = up ? v[i + n / 2] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+    }
+    // lane now owns the total of value index: bits chosen by the halving order
+    int idx = 0;
+#pragma unroll
+    for (int o = 16, n = 32; o > 0; o >>= 1, n >>= 1) if (lane & o) idx += n / 2;
+    __syncwarp();
+    sm[idx] = v[0];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = sm[i];
+    __syncwarp();
+}
+
 #define PO_WARPS 4
 // One warp per problem.  flags[e]: bit0 = outlier (inactive, level 1).  Stale-error semantics of g2o are kept
 // by remembering the pose at which the active edges' errors were last evaluated (Teval).
@@ -124,9 +205,11 @@ k_pose_only_lm(int n_prob, const int32_t *__restrict__ off, const double *__rest
                const double *__restrict__ Kall, const double *__restrict__ T0all, double chi2_th, int rounds, int iters,
                double *__restrict__ T_out, uint8_t *__restrict__ outl, int32_t *__restrict__ n_inlier, svs_lm_stats *__restrict__ stats)
 {
+    __shared__ double s_red[PO_WARPS][32];
     int prob = blockIdx.x * PO_WARPS + (threadIdx.x >> 5);
     if (prob >= n_prob) return;
     int lane = threadIdx.x & 31;
+    double *red = s_red[threadIdx.x >> 5];
     int e0 = off[prob], e1 = off[prob + 1];
     double K[4], T0[7], T[7], Teval[7];
 #pragma unroll
@@ -186,11 +269,22 @@ k_pose_only_lm(int n_prob, const int32_t *__restrict__ off, const double *__rest
                         for (int c2 = a; c2 < 6; c2++) H[k++] += r1 * (J[a] * J[c2] + J[6 + a] * J[6 + c2]);
                     }
                 }
-                cur = gd::warp_sum(cur);
+                {
+                    double v[32];
 #pragma unroll
-                for (int i = 0; i < 21; i++) H[i] = gd::warp_sum(H[i]);
+                    for (int i = 0; i < 21; i++) v[i] = H[i];
 #pragma unroll
-                for (int i = 0; i < 6; i++) b[i] = gd::warp_sum(b[i]);
+                    for (int i = 0; i < 6; i++) v[21 + i] = b[i];
+                    v[27] = cur;
+#pragma unroll
+                    for (int i = 28; i < 32; i++) v[i] = 0.0;
+                    warp_allreduce32(v, red, lane);
+#pragma unroll
+                    for (int i = 0; i < 21; i++) H[i] = v[i];
+#pragma unroll
+                    for (int i = 0; i < 6; i++) b[i] = v[21 + i];
+                    cur = v[27];
+                }
                 st_lin++;
                 if (it == 0) {
                     double md = 0;
@@ -202,15 +296,8 @@ k_pose_only_lm(int n_prob, const int32_t *__restrict__ off, const double *__rest
                 double rho = 0;
                 int q = 0;
                 do {
-                    double Hd[36], x[6];
-                    int k = 0;
-#pragma unroll
-                    for (int a = 0; a < 6; a++)
-#pragma unroll
-                        for (int c2 = a; c2 < 6; c2++) { Hd[a * 6 + c2] = H[k]; Hd[c2 * 6 + a] = H[k]; k++; }
-#pragma unroll
-                    for (int a = 0; a < 6; a++) Hd[a * 7] += lm.lambda;
-                    bool ok = ldlt6_solve(Hd, b, x);
+                    double x[6];
+                    bool ok = ldlt6_reg(H, lm.lambda, b, x);
                     st_sol++;
                     if (!ok) { for (int a = 0; a < 6; a++) x[a] = 0; }
                     double Tn[7];

