@@ -175,6 +175,32 @@ SVS_API int svs_ba_optimize(svs_ctx *ctx, int n_prob, const int32_t *kf_off, dou
                             double huber_delta, int max_iter, int jacobian_mode,
                             double *edge_chi2_out /* sumE */, svs_ba_stats *stats /* n_prob or NULL */);
 
+/* ---------------------------------------------------------------- a7, sharded : large / multi-GPU bundle adjustment
+ * Same problem and solver as svs_ba_optimize, for windows too large for one CTA (config 4: N = 50, L = 1e5) and for
+ * landmark sharding across GPUs: every shard holds ALL n_kf poses and a disjoint subset of the landmarks
+ * with their edges (edge_lm indexes the shard's own landmarks).  The caller runs g2o's LM control loop and SUMS three
+ * device buffers over the shards between the calls (NCCL all-reduce, nothing for one shard) — see
+ * stereovision-slam_b200/svslam/ba_shard.py:
+ *   svs_ba_shard_linearize -> lin_dev[42 n_kf + 2] = [Hpp | bp | robust chi2 | 0]   (sum), maxdiag_dev[1] (max)
+ *   svs_ba_shard_schur     -> red_dev[(6 n_kf)^2 + 6 n_kf]                          (sum), flag_dev[1] (min)
+ *   svs_ba_shard_try       -> tri_dev[4] = [trial chi2 | landmark scale | pose scale (replicated) | solve ok]  (sum of [0..1])
+ *   svs_ba_shard_accept    commits the trial state. */
+typedef struct svs_ba_shard svs_ba_shard;
+SVS_API svs_ba_shard *svs_ba_shard_create(svs_ctx *ctx, int n_kf, const double *poses, int n_lm, const double *lms, int n_edge,
+                                          const int32_t *edge_kf, const int32_t *edge_lm, const uint8_t *edge_cam,
+                                          const double *edge_uv, const double K_left[4], const double K_right[4],
+                                          const double ext_left[7], const double ext_right[7], double huber_delta,
+                                          int jacobian_mode);
+SVS_API void svs_ba_shard_destroy(svs_ctx *ctx, svs_ba_shard *sh);
+SVS_API int svs_ba_shard_lin_size(const svs_ba_shard *sh);
+SVS_API int svs_ba_shard_red_size(const svs_ba_shard *sh);
+SVS_API int svs_ba_shard_linearize(svs_ctx *ctx, svs_ba_shard *sh, double *lin_dev, double *maxdiag_dev);
+SVS_API int svs_ba_shard_schur(svs_ctx *ctx, svs_ba_shard *sh, double lambda, double *red_dev, int *flag_dev);
+SVS_API int svs_ba_shard_try(svs_ctx *ctx, svs_ba_shard *sh, const double *lin_dev, const double *red_dev, double lambda,
+                             int flag_ok, double *tri_dev);
+SVS_API int svs_ba_shard_accept(svs_ctx *ctx, svs_ba_shard *sh);
+SVS_API int svs_ba_shard_get(svs_ctx *ctx, svs_ba_shard *sh, double *poses_out, double *lms_out, double *edge_chi2_out);
+
 /* ---------------------------------------------------------------- a10 : dense stereo
  * svs_stereo_bm replaces stereo_depth_est_->compute(l, r, disp) (src/dense_reconstruction.cpp:114) for
  * cv::StereoBM::create(ndisp, block) with OpenCV's defaults (XSOBEL prefilter cap 31, texture 10,

@@ -14,7 +14,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-fopenmp", "--fmad=false"]
 # --fmad=false for the image kernels: they must round exactly where OpenCV rounds.  The FP64 solver files may
 # contract to FMA (fewer instructions, better accuracy; parity there is a 1e-9 tolerance, not bit-exactness).
-FMA_OK = {"ba.cu", "geom.cu"}
+FMA_OK = {"ba.cu", "geom.cu", "ba_shard.cu"}
 
 
 def sources():
