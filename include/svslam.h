@@ -248,7 +248,8 @@ SVS_API int svs_slam_get_keyframes(svs_slam *s, int stream, int active_only, int
 SVS_API int svs_slam_get_landmarks(svs_slam *s, int stream, int active_only, int64_t *ids, double *xyz,
                                    int32_t *observed_times, int cap, int *n);
 /* phase_seconds[8]: push, track-LK, pose LM, detect, right-LK, triangulate, BA, host bookkeeping (wall clock, includes
- * device time).  counters[6]: frames, keyframes, BA problems, BA iterations, BA trials, BA edges. */
+ * device time).  counters[10]: frames, keyframes, BA problems, BA iterations, BA trials, BA edges, BA landmarks,
+ * BA keyframes, LK points, pose-LM edges. */
 SVS_API int svs_slam_get_counters(svs_slam *s, double *phase_seconds, long long *counters);
 SVS_API svs_frameset *svs_slam_frameset(svs_slam *s);
 /* Host threads (OpenMP) this pipeline uses for its per-stream bookkeeping; several pipelines on distinct contexts may be

@@ -37,11 +37,13 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
 {
     constexpr int PW = WIN + 3;                 // previous-image patch (window + bilinear + Scharr halo)
     constexpr int DW = WIN + 1;                 // derivative / next-image patch
-    constexpr int PP = (PW + 3) & ~3;           // smem row pitch (bytes)
+    constexpr int IWORDS = (PW + 3 + 3) / 4;    // aligned 32-bit words covering a patch row at any byte offset
+    constexpr int JWORDS = (DW + 3 + 3) / 4;
+    constexpr int IP = 4 * IWORDS, JP = 4 * JWORDS;   // smem row pitches (bytes)
     constexpr int NPL = (WIN * WIN + 31) / 32;  // window samples per lane
-    __shared__ uint8_t sI[LK_WARPS][PW * PP];
+    __shared__ __align__(16) uint8_t sI[LK_WARPS][PW * IP];
     __shared__ short2 sD[LK_WARPS][DW * DW];
-    __shared__ uint8_t sJ[LK_WARPS][DW * PP];
+    __shared__ __align__(16) uint8_t sJ[LK_WARPS][DW * JP];
     const int W_BITS = 14;
     const float FLT_SCALE = 1.f / (1 << 20);
     const float half = (WIN - 1) * 0.5f;
@@ -75,10 +77,21 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
         int w11 = (1 << W_BITS) - w00 - w01 - w10;
 
         __syncwarp();
-        // stage the previous-image patch: mI[j][i] = I(ix-1+i, iy-1+j), reflect-101 outside
-        for (int k = lane; k < PW * PW; k += 32) {
-            int j = k / PW, i = k - j * PW;
-            mI[j * PP + i] = __ldg(I + (size_t)lk_refl101(iy - 1 + j, Ih) * Is + lk_refl101(ix - 1 + i, Iw));
+        // stage the previous-image patch: mI[j][ioff + i] = I(ix-1+i, iy-1+j), reflect-101 outside.
+        // Interior patches (the common case) are staged with aligned 32-bit loads and no border arithmetic.
+        int ioff = 0;
+        if (ix - 1 >= 0 && iy - 1 >= 0 && ix - 1 + PW <= Iw && iy - 1 + PW <= Ih) {
+            ioff = (ix - 1) & 3;
+            const uint8_t *base = I + (size_t)(iy - 1) * Is + (ix - 1 - ioff);
+            for (int k = lane; k < PW * IWORDS; k += 32) {
+                int j = k / IWORDS, q = k - j * IWORDS;
+                reinterpret_cast<uint32_t *>(mI)[j * IWORDS + q] = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)j * Is) + q);
+            }
+        } else {
+            for (int k = lane; k < PW * PW; k += 32) {
+                int j = k / PW, i = k - j * PW;
+                mI[j * IP + i] = __ldg(I + (size_t)lk_refl101(iy - 1 + j, Ih) * Is + lk_refl101(ix - 1 + i, Iw));
+            }
         }
         __syncwarp();
         // Scharr derivative patch (zero outside the image: BORDER_CONSTANT on the derivative buffer)
@@ -87,10 +100,10 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
             int X = ix + i, Y = iy + j;
             short2 d = make_short2(0, 0);
             if (X >= 0 && X < Iw && Y >= 0 && Y < Ih) {
-                const uint8_t *p = mI + j * PP + i;   // top-left of the 3x3 neighbourhood
+                const uint8_t *p = mI + j * IP + i + ioff;   // top-left of the 3x3 neighbourhood
                 int v00 = p[0], v01 = p[1], v02 = p[2];
-                int v10 = p[PP], v11 = p[PP + 1], v12 = p[PP + 2];
-                int v20 = p[2 * PP], v21 = p[2 * PP + 1], v22 = p[2 * PP + 2];
+                int v10 = p[IP], v11 = p[IP + 1], v12 = p[IP + 2];
+                int v20 = p[2 * IP], v21 = p[2 * IP + 1], v22 = p[2 * IP + 2];
                 int s0l = (v00 + v20) * 3 + v10 * 10, s0r = (v02 + v22) * 3 + v12 * 10;
                 int s1l = v20 - v00, s1c = v21 - v01, s1r = v22 - v02;
                 d.x = (short)(s0r - s0l);
@@ -108,8 +121,8 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
             Iv[q] = 0; Ixv[q] = 0; Iyv[q] = 0;
             if (k < WIN * WIN) {
                 int y = k / WIN, x = k - y * WIN;
-                const uint8_t *p = mI + (y + 1) * PP + (x + 1);
-                int ival = descale(p[0] * w00 + p[1] * w01 + p[PP] * w10 + p[PP + 1] * w11, W_BITS - 5);
+                const uint8_t *p = mI + (y + 1) * IP + (x + 1) + ioff;
+                int ival = descale(p[0] * w00 + p[1] * w01 + p[IP] * w10 + p[IP + 1] * w11, W_BITS - 5);
                 short2 d00 = mD[y * DW + x], d01 = mD[y * DW + x + 1], d10 = mD[(y + 1) * DW + x], d11 = mD[(y + 1) * DW + x + 1];
                 int ixv = descale(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, W_BITS);
                 int iyv = descale(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, W_BITS);
@@ -137,9 +150,19 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
             w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), (float)(1 << W_BITS)));
             w11 = (1 << W_BITS) - w00 - w01 - w10;
             __syncwarp();
-            for (int k = lane; k < DW * DW; k += 32) {
-                int r = k / DW, i = k - r * DW;
-                mJ[r * PP + i] = __ldg(J + (size_t)lk_refl101(jy + r, Jh) * Js + lk_refl101(jx + i, Jw));
+            int joff = 0;
+            if (jx >= 0 && jy >= 0 && jx + DW <= Jw && jy + DW <= Jh) {
+                joff = jx & 3;
+                const uint8_t *base = J + (size_t)jy * Js + (jx - joff);
+                for (int k = lane; k < DW * JWORDS; k += 32) {
+                    int r = k / JWORDS, q = k - r * JWORDS;
+                    reinterpret_cast<uint32_t *>(mJ)[r * JWORDS + q] = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)r * Js) + q);
+                }
+            } else {
+                for (int k = lane; k < DW * DW; k += 32) {
+                    int r = k / DW, i = k - r * DW;
+                    mJ[r * JP + i] = __ldg(J + (size_t)lk_refl101(jy + r, Jh) * Js + lk_refl101(jx + i, Jw));
+                }
             }
             __syncwarp();
             int pb1 = 0, pb2 = 0;
@@ -148,8 +171,8 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
                 int k = lane + 32 * q;
                 if (k < WIN * WIN) {
                     int y = k / WIN, x = k - y * WIN;
-                    const uint8_t *p = mJ + y * PP + x;
-                    int diff = descale(p[0] * w00 + p[1] * w01 + p[PP] * w10 + p[PP + 1] * w11, W_BITS - 5) - Iv[q];
+                    const uint8_t *p = mJ + y * JP + x + joff;
+                    int diff = descale(p[0] * w00 + p[1] * w01 + p[JP] * w10 + p[JP + 1] * w11, W_BITS - 5) - Iv[q];
                     pb1 += diff * Ixv[q]; pb2 += diff * Iyv[q];
                 }
             }

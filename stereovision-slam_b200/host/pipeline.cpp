@@ -61,7 +61,7 @@ public:
 
     void set_threads(int n) { threads_ = n > 0 ? n : 1; }
     double t_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // push, track-lk, pose, detect, right-lk, triangulate, ba, host
-    long long frames = 0, keyframes = 0, ba_problems = 0, ba_iterations = 0, ba_trials = 0, ba_edges = 0;
+    long long frames = 0, keyframes = 0, ba_problems = 0, ba_iterations = 0, ba_trials = 0, ba_edges = 0, ba_lms = 0, ba_kfs = 0, lk_points = 0, pose_edges = 0;
 
 private:
     svs_ctx *ctx_;
@@ -109,6 +109,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         for (int b = 0; b < B; b++) off_[b + 1] = off_[b] + (sel(streams_[b]) ? (int)streams_[b].lk.status.size() : 0);
         int tot = off_[B];
         if (tot == 0) return 0;
+        lk_points += tot;
         f0_.resize((size_t)2 * tot); f1_.resize((size_t)2 * tot); u0_.resize(tot);
         for (int b = 0; b < B; b++) {
             if (!sel(streams_[b])) continue;
@@ -149,6 +150,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
             off_.assign(np + 1, 0);
             for (int k = 0; k < np; k++) off_[k + 1] = off_[k] + (int)streams_[ids_[k]].pose.feat_index.size();
             int M = off_[np];
+            pose_edges += M;
             d0_.resize((size_t)3 * M + 1); d1_.resize((size_t)2 * M + 1); d2_.resize((size_t)4 * np); d3_.resize((size_t)7 * np);
             d4_.resize((size_t)7 * np); u0_.resize(M + 1); i0_.resize(np);
             for (int k = 0; k < np; k++) {
@@ -296,6 +298,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
                 if (!q.lms.empty()) memcpy(q.lms.data(), &d1_[3 * (size_t)off2_[k]], q.lms.size() * 8);
                 memcpy(q.chi2.data(), &d3_[off3_[k]], q.chi2.size() * 8);
                 ba_iterations += bast_[k].iterations; ba_trials += bast_[k].trials; ba_edges += (long long)q.edge_kf.size();
+                ba_lms += (long long)q.lm_ids.size(); ba_kfs += (long long)q.kf_ids.size();
             }
             ba_problems += np;
         }
@@ -431,7 +434,7 @@ int svs_slam_get_landmarks(svs_slam *s, int stream, int active_only, int64_t *id
     return SVS_OK;
 }
 
-int svs_slam_get_counters(svs_slam *s, double *phase_seconds /* 8 */, long long *counters /* 6 */)
+int svs_slam_get_counters(svs_slam *s, double *phase_seconds /* 8 */, long long *counters /* 10 */)
 {
     if (!s) return SVS_ERR_ARG;
     slam::StreamBatch &b = *s->batch;
@@ -439,6 +442,7 @@ int svs_slam_get_counters(svs_slam *s, double *phase_seconds /* 8 */, long long 
     if (counters) {
         counters[0] = b.frames; counters[1] = b.keyframes; counters[2] = b.ba_problems;
         counters[3] = b.ba_iterations; counters[4] = b.ba_trials; counters[5] = b.ba_edges;
+        counters[6] = b.ba_lms; counters[7] = b.ba_kfs; counters[8] = b.lk_points; counters[9] = b.pose_edges;
     }
     return SVS_OK;
 }

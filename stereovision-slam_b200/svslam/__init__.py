@@ -395,10 +395,10 @@ class Slam:
         return ids[:n.value].copy(), xyz[:n.value].copy(), ot[:n.value].copy()
 
     def counters(self):
-        ph = np.zeros(8); cn = np.zeros(6, np.int64)
+        ph = np.zeros(8); cn = np.zeros(10, np.int64)
         self.ctx._chk(self.ctx.lib.svs_slam_get_counters(C.c_void_p(self.h), _p(ph), _p(cn)))
         names = ("push", "track_lk", "pose_lm", "detect", "right_lk", "triangulate", "ba", "host")
-        cnames = ("frames", "keyframes", "ba_problems", "ba_iterations", "ba_trials", "ba_edges")
+        cnames = ("frames", "keyframes", "ba_problems", "ba_iterations", "ba_trials", "ba_edges", "ba_lms", "ba_kfs", "lk_points", "pose_edges")
         return dict(zip(names, ph.tolist())), dict(zip(cnames, cn.tolist()))
 
     def set_threads(self, n):
