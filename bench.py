@@ -63,45 +63,83 @@ def make_clip(n_frames):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  Default: NVML in-process
+    (nvidia_ml_py) every 200 ms — the same counters `nvidia-smi --query-gpu=clocks.sm,...,clocks_event_reasons.*` prints,
+    without a second process hammering the driver; `--sampler smi` uses the nvidia-smi command line of the recipe."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+    def __init__(self, gpu, mode="nvml", period=0.2):
+        self.gpu, self.mode, self.period = gpu, mode, period
+        self.rows, self.proc, self.t, self.stop_flag = [], None, None, False
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
 
     def start(self):
+        if self.mode == "none":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.nv = pynvml
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+                self.t = threading.Thread(target=self._poll, daemon=True)
+                self.t.start()
+                return
+            except Exception:
+                self.mode = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for n, bit in names:
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
+            r = [x.strip() for x in line.split(",")]
             if len(r) < 9:
+                continue
+            try:
+                self.sm.append(float(r[1])); self.mx.append(float(r[2])); self.power.append(float(r[3]))
+            except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        if self.mode == "none" or self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler unavailable" if self.mode != "none" else "sampler off"]}
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        self.t.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "power_w": float(np.median(self.power)) if self.power else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "sampler": self.mode}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -261,10 +299,15 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def run_pass(on_device, timing):
-        slams = [ctxs[g].slam(gsz[g], cor.W, cor.H, Kh, cor.baseline, half=True, backend_on=1) for g in range(G)]
-        for s in slams:
-            s.set_threads(host_threads)
+    # ONE set of pipelines, primed once (untimed) until every stream's sliding BA window is full, then timed in several
+    # regions that only differ in where the frames live / whether launches are instrumented.  Every region does its own
+    # W warm-up steps first; the stream state simply continues from region to region (steady state).
+    slams = [ctxs[g].slam(gsz[g], cor.W, cor.H, Kh, cor.baseline, half=True, backend_on=1) for g in range(G)]
+    for s in slams:
+        s.set_threads(host_threads)
+    cursor = [0]
+
+    def run_steps(n, on_device):
         bl, br = (Ld.data_ptr(), Rd.data_ptr()) if on_device else (Lh.data_ptr(), Rh.data_ptr())
         # e2e ingest: 2 = zero-copy kernel reads of the pinned host frames, 0 = staged strided DMA copies,
         # 3 = mixed (even groups zero-copy, odd groups DMA) so SM-initiated reads and the copy engines share PCIe
@@ -273,29 +316,27 @@ def run_gpu(args, rank, world, local_rank):
                 return 1
             return args.h2d_mode if args.h2d_mode != 3 else (2 if g % 2 == 0 else 0)
         errors = []
+        lo = cursor[0]
 
-        def loop(g, lo, hi, phase_off):
+        def loop(g):
             try:
-                for s in range(lo, hi):
-                    lp, rp = ptrs(bl, br, s + phase_off, g)
+                for s in range(lo, lo + n):
+                    lp, rp = ptrs(bl, br, s, g)
                     slams[g].add_frames_ptrs(lp, rp, on_device=mode_of(g))
             except Exception as e:      # surface worker failures in the main thread
                 errors.append(e)
 
-        def run_all(lo, hi, phase_off=0):
-            th = [threading.Thread(target=loop, args=(g, lo, hi, phase_off)) for g in range(G)]
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
-            if errors:
-                raise errors[0]
+        th = [threading.Thread(target=loop, args=(g,)) for g in range(G)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        cursor[0] += n
+        if errors:
+            raise errors[0]
 
-        # priming (untimed, before the W warm-up steps): run until the sliding BA window is full so that the timed
-        # steps see steady-state problem sizes (10 keyframes, ~2.5k edges); timing a cold pipeline would overstate
-        run_all(-args.priming, 0, 100000 * (2 * nclip - 2))
-        log("primed %d steps" % args.priming)
-        run_all(0, args.warmup)
+    def timed_region(on_device, timing, profile_window=False):
+        run_steps(args.warmup, on_device)
         for c in ctxs:
             lib.svs_kernel_timing_reset(C.c_void_p(c.h))
             lib.svs_kernel_timing_enable(C.c_void_p(c.h), 1 if timing else 0)
@@ -303,16 +344,20 @@ def run_gpu(args, rank, world, local_rank):
         l0 = sum(c.launch_count() for c in ctxs)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        if profile_window:     # `ncu --profile-from-start off`: only the steady-state steps below are captured
+            torch.cuda.profiler.start()
         t0 = time.perf_counter()
         e0.record()
-        run_all(args.warmup, args.warmup + args.steps)
+        run_steps(args.steps, on_device)
         torch.cuda.synchronize(dev)
         e1.record()
+        if profile_window:
+            torch.cuda.profiler.stop()
         e1.synchronize()
         wall = time.perf_counter() - t0
         barrier()
-        log("timed region done (on_device=%s)" % on_device)
         ms = e0.elapsed_time(e1)
+        log("timed region done (on_device=%s, instrumented=%s): %.1f ms/step" % (on_device, timing, ms / args.steps))
         launches = sum(c.launch_count() for c in ctxs) - l0
         cn1 = [s.counters() for s in slams]
         lost = int(sum((s.status == 3).sum() for s in slams))
@@ -327,8 +372,6 @@ def run_gpu(args, rank, world, local_rank):
                     name = lib.svs_kernel_name(i).decode()
                     a = kern.get(name, (0.0, 0))
                     kern[name] = (a[0] + float(kms[i]), a[1] + int(kcnt[i]))
-        for s in slams:
-            s.close()
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -337,11 +380,32 @@ def run_gpu(args, rank, world, local_rank):
         counts = {k: sum(c1[1][k] - c0[1][k] for c0, c1 in zip(cn0, cn1)) for k in cn1[0][1]}
         return dict(ms=ms, wall=wall, launches=launches, phases=phases, counts=counts, kern=kern, lost=lost)
 
-    sampler = ClockSampler(dev)
+    # priming (untimed, before any warm-up): run until the sliding BA window of every stream is full so that the timed
+    # steps see steady-state problem sizes (10 keyframes); timing a cold pipeline would overstate.  The priming steps
+    # also grow every grow-only device / pinned buffer to its steady-state size (regrowing is a device-wide sync).
+    run_steps(args.priming, True)
+    log("primed %d steps" % args.priming)
+    if args.profile_window:   # profiling aid (never a bench number): one device-resident region inside a profiler window
+        timed_region(True, False, profile_window=True)
+        log("profile window done")
+        return
+    run_steps(args.warmup, False)     # the e2e path's own buffers (pointer tables, staging) exist before anything is timed
+    # three regions over the same workload: (1) frames resident in HBM -> value, (2) frames in pinned host memory -> e2e,
+    # both with the clock sampler running and no per-kernel instrumentation; (3) device-resident again with every launch
+    # bracketed by CUDA events on its stream -> per-kernel durations for the roofline block (not used for value / e2e)
+    sampler = ClockSampler(dev, args.sampler)
     sampler.start()
-    dev_pass = run_pass(True, True)
+    dev_pass = timed_region(True, False)
+    e2e_pass = timed_region(False, False)
     clocks = sampler.stop()
-    e2e_pass = run_pass(False, False)
+    kern_pass = timed_region(True, True) if not args.no_kernel_pass else dev_pass
+    diag = None
+    if args.diag:      # repeat the two headline regions without the sampler: sampler / ordering sensitivity
+        d2, e2 = timed_region(True, False), timed_region(False, False)
+        diag = {"dev_ms_per_step_again": d2["ms"] / args.steps, "e2e_ms_per_step_again": e2["ms"] / args.steps,
+                "e2e_phase_seconds_again": {k: round(v, 4) for k, v in e2["phases"].items()}}
+    for s in slams:
+        s.close()
 
     ba4 = None
     if not args.no_ba4:
@@ -361,9 +425,9 @@ def run_gpu(args, rank, world, local_rank):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    kern = dev_pass["kern"]
+    kern = kern_pass["kern"]
     dom = max(kern, key=lambda k: kern[k][0]) if kern else None
-    cnt = dev_pass["counts"]
+    cnt = kern_pass["counts"]
     P = 613 * 185
     frames = cnt["frames"]
     # ALGORITHMIC bytes moved by each kernel class over the whole timed region (DESIGN.md §4 / SURVEY.md §8d per-unit
@@ -429,10 +493,12 @@ def run_gpu(args, rank, world, local_rank):
         "detail": {"phase_seconds": {k: round(v, 4) for k, v in dev_pass["phases"].items()},
                    "e2e_phase_seconds": {k: round(v, 4) for k, v in e2e_pass["phases"].items()},
                    "counts": dev_pass["counts"], "kernel_ms": {k: [round(v[0], 3), v[1]] for k, v in kern.items()},
-                   "kernel_time_share": shares, "device_busy_frac": dev_total / dev_pass["ms"] if dev_pass["ms"] else None,
+                   "kernel_time_share": shares, "kernel_pass_ms_per_step": kern_pass["ms"] / args.steps,
+                   "summed_kernel_ms_over_wall_ms": dev_total / kern_pass["ms"] if kern_pass["ms"] else None,
                    "lost_streams": dev_pass["lost"], "host_cores": cores, "host_threads_per_group": host_threads,
-                   "ba_lm_iterations_per_sec": cnt["ba_iterations"] * world / (dev_pass["ms"] * 1e-3),
-                   "ba_config4": ba4},
+                   "ba_lm_iterations_per_sec": dev_pass["counts"]["ba_iterations"] * world / (dev_pass["ms"] * 1e-3),
+                   "kernel_pass_phase_seconds": {k: round(v, 4) for k, v in kern_pass["phases"].items()},
+                   "diag": diag, "ba_config4": ba4},
     }
     print(json.dumps(out))
     if dist is not None:
@@ -451,10 +517,15 @@ def main():
     ap.add_argument("--h2d-mode", type=int, default=2, choices=[0, 2, 3],
                     help="e2e transfer of the pinned host frames: 2 zero-copy kernel reads over PCIe, 0 staged DMA copies")
     ap.add_argument("--clip-frames", type=int, default=48)
-    ap.add_argument("--priming", type=int, default=70, help="untimed steps before warm-up so the BA window is full")
+    ap.add_argument("--priming", type=int, default=150, help="untimed steps before warm-up so the BA window is full")
+    ap.add_argument("--diag", action="store_true", help="repeat the value / e2e regions a second time (detail.diag)")
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames per stream per process for the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba4", action="store_true", help="skip the config-4 sharded-BA detail block")
+    ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "none"], help="clock / throttle-reason sampler")
+    ap.add_argument("--no-kernel-pass", action="store_true", help="skip the instrumented per-kernel timing pass")
+    ap.add_argument("--profile-window", action="store_true",
+                    help="profiling aid: run only a device-resident pass with cudaProfilerStart/Stop around the timed steps")
     ap.add_argument("--cpu-baseline-clip", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3:

@@ -3,6 +3,7 @@
 // staging through pinned buffers owned by the context; one CUDA stream per context.
 #include "svs_internal.h"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -43,7 +44,8 @@ static void prof_harvest(svs_ctx *c)
 extern "C" {
 
 static int frameset_finish_push(svs_ctx *c, svs_frameset *fs, const uint8_t *dl, const uint8_t *dr, size_t rs, size_t is,
-                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated = 0);
+                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated = 0,
+                                int zero_copy = 0);
 
 int svs_version(void) { return 100; }
 
@@ -98,6 +100,7 @@ svs_ctx *svs_create(int device)
     if (!c) { g_create_err = "out of memory"; return nullptr; }
     c->device = device;
     c->sm_count = p.multiProcessorCount;
+    if (const char *z = getenv("SVS_ZC_CTAS")) { int v = atoi(z); if (v > 0) c->zc_ctas = v; }
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
         delete c;
@@ -202,12 +205,16 @@ int svs_frameset_push(svs_ctx *c, svs_frameset *fs, const uint8_t *left, const u
 }
 
 static int frameset_finish_push(svs_ctx *c, svs_frameset *fs, const uint8_t *dl, const uint8_t *dr, size_t rs, size_t is,
-                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated)
+                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated, int zero_copy)
 {
     fs->cur ^= 1;
     fs->pushes++;
     PyrDesc &Lc = fs->L[fs->cur];
-    if (fs->half) {
+    if (fs->half && zero_copy && pl && pr == pl + fs->B && Lc.stride[0] == fs->R.stride[0] && Lc.img_pitch == fs->R.img_pitch) {
+        // frames live in pinned host memory: small persistent grid, both eyes in one launch (images.cu)
+        SVS_TRY(svs_i_half_nearest_zc(c, pl, fs->B, fs->in_w, fs->in_h, rs, Lc.base + Lc.off[0], fs->R.base + fs->R.off[0], fs->W, fs->H,
+                                      Lc.stride[0], Lc.img_pitch, aligned4));
+    } else if (fs->half) {
         SVS_TRY(svs_i_half_nearest(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc.base + Lc.off[0], fs->W, fs->H, Lc.stride[0], Lc.img_pitch, pl, aligned4, rows_decimated));
         SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R.base + fs->R.off[0], fs->W, fs->H, fs->R.stride[0], fs->R.img_pitch, pr, aligned4, rows_decimated));
     } else {
@@ -241,7 +248,7 @@ int svs_frameset_push_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *l
         }
         SVS_CUDA(c, cudaMemcpyAsync(fs->ptr_table.p, hp, (size_t)2 * B * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
         const uint8_t *const *dp = fs->ptr_table.as<const uint8_t *>();
-        return frameset_finish_push(c, fs, nullptr, nullptr, row_stride, 0, dp, dp + B, aligned4);
+        return frameset_finish_push(c, fs, nullptr, nullptr, row_stride, 0, dp, dp + B, aligned4, 0, on_device == 2);
     }
     // Staged path: only the even rows the half-resolution resize reads cross PCIe (strided 2-D DMA copies); the kernel
     // then reads the staged rows with a unit row step.  (Whole-frame linear copies were measured slower in the

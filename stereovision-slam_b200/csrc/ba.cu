@@ -7,9 +7,11 @@
 // k_ba_window: ONE persistent CTA per window problem runs the whole LM loop on-device (no host round trips):
 //   linearise   landmark-parallel: residuals, 2x6 / 2x3 Jacobian blocks, Huber weights -> Hll (3x3), bl, Hpl (6x3/edge)
 //               pose-parallel (warp per keyframe, butterfly reduction) -> Hpp (6x6), bp
-//   schur       landmark-parallel V^-1 = (Hll + lambda I)^-1, W V^-1 per edge; then every 6x6 block (i,j) of the
-//               reduced system is OWNED by 36 threads that sum their precomputed (edge,edge) pair list in a fixed
-//               order -> no atomics, bitwise deterministic
+//   schur       landmark-parallel V^-1 = (Hll + lambda I)^-1, W V^-1 per edge; the (edge, edge) pairs of every 6x6 block
+//               (i,j) of the reduced system are listed by the host, sorted by block and cut into chunks of <= BA_CH
+//               pairs; 4 threads own a chunk (one 3x3 quadrant each) and accumulate (W V^-1)_e1 W_e2^T in registers,
+//               then 36 threads per block add the chunk partials in a fixed order -> no atomics, bitwise
+//               deterministic, and the only traffic is L1/L2 reads of the 144-byte edge blocks
 //   solve       pivoted LDLT (Eigen::LDLT order of operations) in shared memory, 4 lanes per row
 //   back-subst  landmark-parallel; trial chi2; g2o's rho test / lambda schedule on thread 0
 // The reduced system lives in shared memory (<= ~200 KB, i.e. N <= 26 keyframes); larger windows fall back
@@ -27,10 +29,12 @@ struct BaProb {
     int lm0, e0;    // first landmark / edge (global)
     int loff0;      // l_off[loff0 + l .. ] (L+1 entries), values relative to e0
     int poff0;      // p_off[poff0 + a ..] (NA+1 entries), values relative to e0
-    int blk0;       // blk_i/blk_j/blk_off[blk0 + b] ; blk_off has nblk+1 entries at blk0 + prob index shift (see host)
-    int boff0;
-    int pair0;      // first contribution record of this problem (records are sorted by block)
-    int epoff0;     // ep_off[epoff0 + e .. ] (E+1 entries): per-edge list of record positions (relative to pair0)
+    int blk0;       // blk_i/blk_j[blk0 + b]
+    int pair0;      // pr_e1/pr_e2[pair0 + p]: the (edge, edge) pairs of this problem, sorted by block
+    int nch, ch0;   // chunks: ch_blk[ch0 + c] = block of chunk c, pairs [ch_off[choff0 + c], ch_off[choff0 + c + 1])
+    int choff0;
+    int bch0;       // blk_ch[bch0 + b .. ] (nblk+1 entries): chunk range of block b
+    long long part0;  // first partial-sum record (36 doubles per chunk) in the global scratch
     long long S_off;  // offset (doubles) into the global reduced-system scratch, or -1 when it fits shared memory
 };
 
@@ -42,8 +46,8 @@ struct BaArgs {
     const uint8_t *edge_cam;
     const double *edge_uv;
     const int32_t *l_off, *l_edges, *p_off, *p_edges;
-    const int32_t *blk_i, *blk_j, *blk_off, *ep_off, *ep_pos;
-    double *contrib;                // 36 doubles per (edge, edge) pair record
+    const int32_t *blk_i, *blk_j, *blk_ch, *pr_e1, *pr_e2, *ch_blk, *ch_off;
+    double *part;                   // 36 doubles per chunk
     double *Hpl, *WD;               // 18 / edge
     double *Hll, *Dinv;             // 9 / landmark
     double *bl, *xl, *lmT;          // 3 / landmark
@@ -56,6 +60,7 @@ struct BaArgs {
 };
 
 #define BA_T 256
+#define BA_CH 16    // (edge, edge) pairs per Schur chunk
 #include "ba_ldlt.cuh"
 
 __device__ __forceinline__ double block_sum(double v, double *red)
@@ -258,46 +263,56 @@ k_ba_window(BaArgs A)
                 for (int x = 0; x < 9; x++) Dinv[9 * (size_t)l + x] = Di[x];
             }
             __syncthreads();
-            // ---- per EDGE: W V^-1, and the 6x6 contributions (W V^-1)_e1 W_e2^T for every edge e2 of the same landmark
-            //      with pose(e1) <= pose(e2), written once into block-sorted contiguous records
-            const int32_t *ep_off = A.ep_off + P.epoff0, *ep_pos = A.ep_pos + P.pair0;
-            double *contrib = A.contrib + 36 * (size_t)P.pair0;
+            // ---- per EDGE: W V^-1
             for (int e = tid; e < E; e += BA_T) {
-                int l = edge_l[e], p1 = edge_p[e];
-                const double *Di = Dinv + 9 * (size_t)l, *W = Hpl + 18 * (size_t)e;
+                const double *Di = Dinv + 9 * (size_t)edge_l[e], *W = Hpl + 18 * (size_t)e;
                 double X[18];
 #pragma unroll
                 for (int x = 0; x < 6; x++)
 #pragma unroll
                     for (int y = 0; y < 3; y++) X[x * 3 + y] = W[x * 3] * Di[y] + W[x * 3 + 1] * Di[3 + y] + W[x * 3 + 2] * Di[6 + y];
-                double *O = WD + 18 * (size_t)e;
+                double2 *O = reinterpret_cast<double2 *>(WD + 18 * (size_t)e);
 #pragma unroll
-                for (int x = 0; x < 18; x++) O[x] = X[x];
-                int q = ep_off[e];
-                for (int s = l_off[l]; s < l_off[l + 1]; s++) {
-                    int e2 = l_edges[s];
-                    if (p1 > edge_p[e2]) continue;
-                    const double *Y = Hpl + 18 * (size_t)e2;
-                    double *C = contrib + 36 * (size_t)ep_pos[q++];
-#pragma unroll
-                    for (int r = 0; r < 6; r++)
-#pragma unroll
-                        for (int c2 = 0; c2 < 6; c2++)
-                            C[r * 6 + c2] = X[r * 3] * Y[c2 * 3] + X[r * 3 + 1] * Y[c2 * 3 + 1] + X[r * 3 + 2] * Y[c2 * 3 + 2];
+                for (int x = 0; x < 9; x++) O[x] = make_double2(X[2 * x], X[2 * x + 1]);
+            }
+            __syncthreads();
+            // ---- chunk partials: 4 threads per chunk, thread (qr, qc) accumulates the 3x3 quadrant
+            //      sum_pairs (W V^-1)_e1[3qr.., :] (W_e2[3qc.., :])^T in registers
+            {
+                const int32_t *pr_e1 = A.pr_e1 + P.pair0, *pr_e2 = A.pr_e2 + P.pair0;
+                const int32_t *ch_off = A.ch_off + P.choff0;
+                double *part = A.part + 36 * (size_t)P.part0;
+                for (int t = tid; t < 4 * P.nch; t += BA_T) {
+                    int ch = t >> 2, qr = (t >> 1) & 1, qc = t & 1;
+                    double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
+                    int p1 = ch_off[ch + 1];
+                    for (int p = ch_off[ch]; p < p1; p++) {
+                        const double *X = WD + 18 * (size_t)pr_e1[p] + 9 * qr, *Y = Hpl + 18 * (size_t)pr_e2[p] + 9 * qc;
+                        double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3], x4 = X[4], x5 = X[5], x6 = X[6], x7 = X[7], x8 = X[8];
+                        double y0 = Y[0], y1 = Y[1], y2 = Y[2], y3 = Y[3], y4 = Y[4], y5 = Y[5], y6 = Y[6], y7 = Y[7], y8 = Y[8];
+                        a00 += x0 * y0 + x1 * y1 + x2 * y2; a01 += x0 * y3 + x1 * y4 + x2 * y5; a02 += x0 * y6 + x1 * y7 + x2 * y8;
+                        a10 += x3 * y0 + x4 * y1 + x5 * y2; a11 += x3 * y3 + x4 * y4 + x5 * y5; a12 += x3 * y6 + x4 * y7 + x5 * y8;
+                        a20 += x6 * y0 + x7 * y1 + x8 * y2; a21 += x6 * y3 + x7 * y4 + x8 * y5; a22 += x6 * y6 + x7 * y7 + x8 * y8;
+                    }
+                    double *O = part + 36 * (size_t)ch + 18 * qr + 3 * qc;     // row-major 6x6 record
+                    O[0] = a00; O[1] = a01; O[2] = a02; O[6] = a10; O[7] = a11; O[8] = a12; O[12] = a20; O[13] = a21; O[14] = a22;
                 }
             }
             __syncthreads();
-            // ---- S_ij -= sum of the block's records (36 threads own a block; coalesced, fixed order => deterministic)
-            const int32_t *blk_i = A.blk_i + P.blk0, *blk_j = A.blk_j + P.blk0, *blk_off = A.blk_off + P.boff0;
-            for (int t = tid; t < P.nblk * 36; t += BA_T) {
-                int bk = t / 36, ent = t - 36 * bk, r = ent / 6, c2 = ent - 6 * r;
-                double sum = 0;
-                const double *C = contrib + ent;
-                for (int s = blk_off[bk]; s < blk_off[bk + 1]; s++) sum += C[36 * (size_t)s];
-                int i = blk_i[bk], j = blk_j[bk];
-                double v = S[(6 * i + r) * pitch + 6 * j + c2] - sum;
-                S[(6 * i + r) * pitch + 6 * j + c2] = v;
-                if (i != j) S[(6 * j + c2) * pitch + 6 * i + r] = v;
+            // ---- S_ij -= sum of the block's chunk partials (36 threads own a block; coalesced, fixed order => deterministic)
+            {
+                const int32_t *blk_i = A.blk_i + P.blk0, *blk_j = A.blk_j + P.blk0, *blk_ch = A.blk_ch + P.bch0;
+                const double *part = A.part + 36 * (size_t)P.part0;
+                for (int t = tid; t < P.nblk * 36; t += BA_T) {
+                    int bk = t / 36, ent = t - 36 * bk, r = ent / 6, c2 = ent - 6 * r;
+                    double sum = 0;
+                    const double *C = part + ent;
+                    for (int s = blk_ch[bk]; s < blk_ch[bk + 1]; s++) sum += C[36 * (size_t)s];
+                    int i = blk_i[bk], j = blk_j[bk];
+                    double v = S[(6 * i + r) * pitch + 6 * j + c2] - sum;
+                    S[(6 * i + r) * pitch + 6 * j + c2] = v;
+                    if (i != j) S[(6 * j + c2) * pitch + 6 * i + r] = v;
+                }
             }
             // ---- g_i = bp_i - sum_e (W V^-1)_e bl
             for (int a = warp; a < NA; a += BA_T / 32) {
@@ -420,7 +435,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
 
     // ---- host-side structure: active poses, CSR by landmark / pose, per-block pair lists
     std::vector<BaProb> probs(n_prob);
-    std::vector<int32_t> act_pose, edge_p(sumE), l_off, l_edges(sumE), p_off, p_edges(sumE), blk_i, blk_j, blk_off, ep_off, ep_pos;
+    std::vector<int32_t> act_pose, edge_p(sumE), l_off, l_edges(sumE), p_off, p_edges(sumE), blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off;
     long long pairs_total = 0;
     const size_t smem_cap = 200 * 1024;
     size_t max_smem = 0;
@@ -455,8 +470,10 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
         for (int a = 0; a <= NA; a++) p_off.push_back(pc[a]);
         { std::vector<int> fill(pc.begin(), pc.end() - 1);
           for (int e = 0; e < E; e++) p_edges[e0 + fill[edge_p[e0 + e]]++] = e; }
-        // pair lists per upper block (i <= j): counting sort on block id i*NA + j
-        P.blk0 = (int)blk_i.size(); P.boff0 = (int)blk_off.size(); P.pair0 = (int)ep_pos.size(); P.epoff0 = (int)ep_off.size();
+        // (edge, edge) pairs per upper block (i <= j), sorted by block id i*NA + j (counting sort; inside a block in
+        // landmark / list order), then cut into chunks of <= BA_CH pairs that never span two blocks
+        P.blk0 = (int)blk_i.size(); P.bch0 = (int)blk_ch.size(); P.pair0 = (int)pr_e1.size();
+        P.ch0 = (int)ch_blk.size(); P.choff0 = (int)ch_off.size(); P.part0 = (long long)ch_blk.size();
         std::vector<int> bcount((size_t)NA * NA + 1, 0);
         const int32_t *lo = l_off.data() + P.loff0;
         for (int l = 0; l < L; l++)
@@ -465,33 +482,30 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
                     int i = edge_p[e0 + l_edges[e0 + s1]], j = edge_p[e0 + l_edges[e0 + s2]];
                     if (i <= j) bcount[(size_t)i * NA + j + 1]++;
                 }
-        int nblk = 0, run = 0;
-        blk_off.push_back(0);
+        int nblk = 0, run = 0, nch = 0;
         std::vector<int> bstart((size_t)NA * NA, 0);
         for (size_t k = 0; k < (size_t)NA * NA; k++) {
             int cn = bcount[k + 1];
             if (cn > 0) {
-                nblk++; bstart[k] = run; run += cn;
+                nblk++; bstart[k] = run;
                 blk_i.push_back((int)(k / NA)); blk_j.push_back((int)(k % NA));
-                blk_off.push_back(run);
+                blk_ch.push_back(nch);
+                for (int c0 = 0; c0 < cn; c0 += BA_CH) { ch_blk.push_back(nblk - 1); ch_off.push_back(run + c0); nch++; }
+                run += cn;
             }
         }
-        P.nblk = nblk;
-        // per-edge record positions: edge e1 (in edge order) enumerates the edges e2 of its landmark in list order and
-        // keeps those with pose(e1) <= pose(e2); each such pair gets the next free slot of its block
-        size_t pbase = ep_pos.size();
-        ep_pos.resize(pbase + run);
-        std::vector<int> bfill(bstart);
-        int q = 0;
-        for (int e = 0; e < E; e++) {
-            ep_off.push_back(q);
-            int l = edge_lm[e0 + e], i = edge_p[e0 + e];
-            for (int s2 = lo[l]; s2 < lo[l + 1]; s2++) {
-                int j = edge_p[e0 + l_edges[e0 + s2]];
-                if (i <= j) ep_pos[pbase + q++] = bfill[(size_t)i * NA + j]++;
-            }
-        }
-        ep_off.push_back(q);
+        blk_ch.push_back(nch);
+        ch_off.push_back(run);
+        P.nblk = nblk; P.nch = nch;
+        size_t pbase = pr_e1.size();
+        pr_e1.resize(pbase + run); pr_e2.resize(pbase + run);
+        for (int l = 0; l < L; l++)
+            for (int s1 = lo[l]; s1 < lo[l + 1]; s1++)
+                for (int s2 = lo[l]; s2 < lo[l + 1]; s2++) {
+                    int e1 = l_edges[e0 + s1], e2 = l_edges[e0 + s2];
+                    int i = edge_p[e0 + e1], j = edge_p[e0 + e2];
+                    if (i <= j) { int q = bstart[(size_t)i * NA + j]++; pr_e1[pbase + q] = e1; pr_e2[pbase + q] = e2; }
+                }
         pairs_total += run;
         size_t with = ba_smem_bytes(NA, true);
         if (with <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, with); }
@@ -516,9 +530,11 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     size_t o_pe = add(p_edges.data(), (size_t)sumE * 4);
     size_t o_bi = add(blk_i.data(), blk_i.size() * 4);
     size_t o_bj = add(blk_j.data(), blk_j.size() * 4);
-    size_t o_bo = add(blk_off.data(), blk_off.size() * 4);
-    size_t o_p1 = add(ep_off.data(), ep_off.size() * 4);
-    size_t o_p2 = add(ep_pos.data(), ep_pos.size() * 4);
+    size_t o_bc = add(blk_ch.data(), blk_ch.size() * 4);
+    size_t o_p1 = add(pr_e1.data(), pr_e1.size() * 4);
+    size_t o_p2 = add(pr_e2.data(), pr_e2.size() * 4);
+    size_t o_cb = add(ch_blk.data(), ch_blk.size() * 4);
+    size_t o_co = add(ch_off.data(), ch_off.size() * 4);
     size_t o_pose = add(poses, (size_t)sumN * 56);
     size_t o_lm = add(lms, (size_t)sumL * 24);
     SVS_CUDA(c, c->h_in.reserve(tot + 16));
@@ -527,7 +543,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     for (const Seg &s : segs) if (s.bytes) memcpy(hb + s.off, s.src, s.bytes);
     SVS_CUDA(c, cudaMemcpyAsync(db, hb, tot, cudaMemcpyHostToDevice, c->stream));
     // scratch
-    size_t sc_b = ((size_t)sumE * 36 + (size_t)sumL * 27 + (size_t)S_tot + (size_t)pairs_total * 36) * 8 + 64;
+    size_t sc_b = ((size_t)sumE * 36 + (size_t)sumL * 27 + (size_t)S_tot + ch_blk.size() * 36) * 8 + 64;
     SVS_CUDA(c, c->d_tmp.reserve(sc_b));
     size_t out_b = (size_t)sumE * 8 + (size_t)n_prob * sizeof(svs_ba_stats);
     SVS_CUDA(c, c->d_out.reserve(out_b + 16));
@@ -542,13 +558,14 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     A.l_off = reinterpret_cast<int32_t *>(db + o_lo); A.l_edges = reinterpret_cast<int32_t *>(db + o_le);
     A.p_off = reinterpret_cast<int32_t *>(db + o_po); A.p_edges = reinterpret_cast<int32_t *>(db + o_pe);
     A.blk_i = reinterpret_cast<int32_t *>(db + o_bi); A.blk_j = reinterpret_cast<int32_t *>(db + o_bj);
-    A.blk_off = reinterpret_cast<int32_t *>(db + o_bo);
-    A.ep_off = reinterpret_cast<int32_t *>(db + o_p1); A.ep_pos = reinterpret_cast<int32_t *>(db + o_p2);
+    A.blk_ch = reinterpret_cast<int32_t *>(db + o_bc);
+    A.pr_e1 = reinterpret_cast<int32_t *>(db + o_p1); A.pr_e2 = reinterpret_cast<int32_t *>(db + o_p2);
+    A.ch_blk = reinterpret_cast<int32_t *>(db + o_cb); A.ch_off = reinterpret_cast<int32_t *>(db + o_co);
     A.Hpl = scr; A.WD = A.Hpl + (size_t)sumE * 18;
     A.Hll = A.WD + (size_t)sumE * 18; A.Dinv = A.Hll + (size_t)sumL * 9;
     A.bl = A.Dinv + (size_t)sumL * 9; A.xl = A.bl + (size_t)sumL * 3; A.lmT = A.xl + (size_t)sumL * 3;
     A.S_glob = A.lmT + (size_t)sumL * 3;
-    A.contrib = A.S_glob + (size_t)S_tot;
+    A.part = A.S_glob + (size_t)S_tot;
     A.edge_chi2 = c->d_out.as<double>();
     A.stats = reinterpret_cast<svs_ba_stats *>(c->d_out.as<uint8_t>() + (size_t)sumE * 8);
     for (int i = 0; i < 4; i++) { A.K[0][i] = K_left[i]; A.K[1][i] = K_right[i]; }

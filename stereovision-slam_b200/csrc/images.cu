@@ -6,6 +6,7 @@
 //
 // Both are HBM-streaming stencils over a batch of images (blockIdx.z = image).
 #include "svs_internal.h"
+#include <algorithm>
 
 int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t *bytes_per_image)
 {
@@ -71,6 +72,73 @@ int svs_i_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_
     return SVS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Zero-copy ingest (frames in pinned, device-addressable HOST memory): the same resize, reading the even source rows
+// straight over PCIe.  A PCIe read has ~2 us latency, so what this kernel needs is bytes in flight (~100 KB at the
+// link's ~45 GB/s), NOT SM residency: a normal one-thread-per-output grid fills every CTA slot of the device with warps
+// parked on PCIe loads and keeps the other contexts' kernels (LK, pose-LM, BA of other stream groups) off the SMs for
+// the whole transfer.  So: a SMALL persistent grid, each thread keeps ZC_U x 2 independent 4-byte loads in flight and
+// walks (image, row, 4-pixel chunk) items with a grid stride; both eyes in one launch (src_ptrs = [left.. | right..]).
+#define ZC_U 4
+__global__ void __launch_bounds__(256)
+k_half_nearest_zc(const uint8_t *const *__restrict__ src_ptrs, int n_img_per_eye, int w, int h, size_t row_stride,
+                  uint8_t *__restrict__ dstL, uint8_t *__restrict__ dstR, int dw, int dh, int dst_stride, size_t dst_img_pitch, int vec_ok)
+{
+    const int chunks = (dw + 3) >> 2;                    // 4 output pixels per item
+    const long long per_img = (long long)chunks * dh;
+    const long long total = per_img * 2 * n_img_per_eye;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += nthr * ZC_U) {
+        uint32_t a[ZC_U], b[ZC_U];
+        uint8_t *drow[ZC_U];
+        const uint8_t *srow[ZC_U];
+        int x4[ZC_U];
+        bool fast[ZC_U];
+#pragma unroll
+        for (int u = 0; u < ZC_U; u++) {
+            long long it = base + (long long)u * nthr;
+            fast[u] = false; drow[u] = nullptr; srow[u] = nullptr; x4[u] = 0; a[u] = b[u] = 0;
+            if (it >= total) continue;
+            int img = (int)(it / per_img);
+            int r = (int)(it - (long long)img * per_img);
+            int y = r / chunks;
+            x4[u] = (r - y * chunks) * 4;
+            srow[u] = src_ptrs[img] + (size_t)min(2 * y, h - 1) * row_stride;
+            uint8_t *dst = img < n_img_per_eye ? dstL + (size_t)img * dst_img_pitch : dstR + (size_t)(img - n_img_per_eye) * dst_img_pitch;
+            drow[u] = dst + (size_t)y * dst_stride;
+            fast[u] = vec_ok && x4[u] + 4 <= dw && 2 * x4[u] + 8 <= w;
+            if (fast[u]) {
+                const uint32_t *s32 = reinterpret_cast<const uint32_t *>(srow[u] + 2 * x4[u]);
+                a[u] = __ldg(s32); b[u] = __ldg(s32 + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ZC_U; u++) {
+            if (!drow[u]) continue;
+            if (fast[u]) {
+                uint32_t o = (a[u] & 0xFF) | ((a[u] >> 8) & 0xFF00) | ((b[u] & 0xFF) << 16) | ((b[u] << 8) & 0xFF000000u);
+                *reinterpret_cast<uint32_t *>(drow[u] + x4[u]) = o;
+            } else {
+                for (int k = 0; k < 4 && x4[u] + k < dw; k++) drow[u][x4[u] + k] = __ldg(srow[u] + min(2 * (x4[u] + k), w - 1));
+            }
+        }
+    }
+}
+
+int svs_i_half_nearest_zc(svs_ctx *c, const uint8_t *const *src_ptrs_dev, int n_per_eye, int w, int h, size_t row_stride,
+                          uint8_t *dstL, uint8_t *dstR, int dw, int dh, int dst_stride, size_t dst_img_pitch, int ptrs_aligned4)
+{
+    if (n_per_eye <= 0) return SVS_OK;
+    int vec_ok = ptrs_aligned4 && ((2 * row_stride) & 3) == 0 &&
+                 ((reinterpret_cast<uintptr_t>(dstL) | reinterpret_cast<uintptr_t>(dstR) | (size_t)dst_stride | dst_img_pitch) & 3) == 0;
+    long long items = (long long)((dw + 3) / 4) * dh * 2 * n_per_eye;
+    long long want = (items + 256 * ZC_U - 1) / (256 * ZC_U);
+    int grid = (int)std::min<long long>(want, c->zc_ctas > 0 ? c->zc_ctas : 64);
+    SVS_KERNEL(c, KID_HALF, k_half_nearest_zc<<<grid, 256, 0, c->stream>>>(src_ptrs_dev, n_per_eye, w, h, row_stride, dstL, dstR, dw, dh,
+                                                                         dst_stride, dst_img_pitch, vec_ok));
+    return SVS_OK;
+}
+
 __global__ void k_copy2d(const uint8_t *__restrict__ src, const uint8_t *const *__restrict__ src_ptrs, int w, int h,
                          size_t row_stride, size_t img_stride, uint8_t *__restrict__ dst, int dst_stride, size_t dst_img_pitch)
 {
@@ -96,8 +164,11 @@ int svs_i_copy_level0(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_s
 
 // ---------------------------------------------------------------------------------------------
 // pyrDown: separable [1 4 6 4 1], BORDER_REFLECT_101, even rows/cols, (sum + 128) >> 8.
-// One CTA = 32x8 output pixels; the 67x19 input tile is staged in shared memory (each input byte is
-// read from HBM/L2 once per CTA), then a horizontal pass into shared memory and a vertical pass.
+// One CTA = 64x16 output pixels.  The 136-byte x 35-row input tile is staged in shared memory with aligned 32-bit loads
+// (per-byte reflection only for words that straddle the image border), the horizontal pass produces two outputs per item
+// packed as 16-bit halves of one word (a row sum is <= 16*255 = 4080), and the vertical pass runs on the packed halves
+// (<= 16*4080 = 65280 < 2^16, so neither the weighted sum nor the +128 rounding carries across halves) and stores four
+// output pixels per thread with one 32-bit store.
 __device__ __forceinline__ int refl101(int i, int n)
 {
     if (n == 1) return 0;
@@ -105,35 +176,59 @@ __device__ __forceinline__ int refl101(int i, int n)
     return i;
 }
 
-#define PD_TX 32
-#define PD_TY 8
-__global__ void __launch_bounds__(PD_TX *PD_TY)
+#define PD_TX 64
+#define PD_TY 16
+#define PD_ROWS (2 * PD_TY + 3)
+#define PD_WORDS (PD_TX / 2 + 2)
+__global__ void __launch_bounds__(256)
 k_pyr_down(const uint8_t *__restrict__ src_base, int sw, int sh, int sstride, uint8_t *__restrict__ dst_base,
            int dw, int dh, int dstride, size_t img_pitch)
 {
-    __shared__ uint8_t tile[2 * PD_TY + 3][2 * PD_TX + 3 + 1];
-    __shared__ int hrow[2 * PD_TY + 3][PD_TX];
+    __shared__ uint32_t tile[PD_ROWS][PD_WORDS];
+    __shared__ __align__(8) uint32_t hrow[PD_ROWS][PD_TX / 2];
     const uint8_t *src = src_base + (size_t)blockIdx.z * img_pitch;
     uint8_t *dst = dst_base + (size_t)blockIdx.z * img_pitch;
-    int ox0 = blockIdx.x * PD_TX, oy0 = blockIdx.y * PD_TY;
-    int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
-    int tid = threadIdx.y * PD_TX + threadIdx.x;
-    for (int i = tid; i < (2 * PD_TY + 3) * (2 * PD_TX + 3); i += PD_TX * PD_TY) {
-        int ty = i / (2 * PD_TX + 3), tx = i % (2 * PD_TX + 3);
-        tile[ty][tx] = __ldg(src + (size_t)refl101(iy0 + ty, sh) * sstride + refl101(ix0 + tx, sw));
+    const int ox0 = blockIdx.x * PD_TX, oy0 = blockIdx.y * PD_TY;
+    const int bx0 = 2 * ox0 - 4, iy0 = 2 * oy0 - 2;      // image x of tile byte 0 (4-byte aligned), image y of tile row 0
+    const int tid = threadIdx.x;
+    for (int i = tid; i < PD_ROWS * PD_WORDS; i += 256) {
+        int r = i / PD_WORDS, q = i - r * PD_WORDS;
+        const uint8_t *row = src + (size_t)refl101(iy0 + r, sh) * sstride;
+        int x = bx0 + 4 * q;
+        uint32_t v;
+        if (x >= 0 && x + 4 <= sw) v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
+        else v = (uint32_t)__ldg(row + refl101(x, sw)) | ((uint32_t)__ldg(row + refl101(x + 1, sw)) << 8) |
+                 ((uint32_t)__ldg(row + refl101(x + 2, sw)) << 16) | ((uint32_t)__ldg(row + refl101(x + 3, sw)) << 24);
+        tile[r][q] = v;
     }
     __syncthreads();
-    for (int i = tid; i < (2 * PD_TY + 3) * PD_TX; i += PD_TX * PD_TY) {
-        int ty = i / PD_TX, tx = i % PD_TX;
-        const uint8_t *t = &tile[ty][2 * tx];
-        hrow[ty][tx] = t[0] + 4 * t[1] + 6 * t[2] + 4 * t[3] + t[4];
+    // horizontal: outputs ox0+2j (tile bytes 4j+2..4j+6) and ox0+2j+1 (tile bytes 4j+4..4j+8)
+    for (int i = tid; i < PD_ROWS * (PD_TX / 2); i += 256) {
+        int r = i / (PD_TX / 2), j = i - r * (PD_TX / 2);
+        uint32_t w0 = tile[r][j], w1 = tile[r][j + 1], w2 = tile[r][j + 2];
+        uint32_t b2 = (w0 >> 16) & 0xFF, b3 = w0 >> 24, b4 = w1 & 0xFF, b5 = (w1 >> 8) & 0xFF, b6 = (w1 >> 16) & 0xFF, b7 = w1 >> 24,
+                 b8 = w2 & 0xFF;
+        uint32_t A = b2 + 4 * b3 + 6 * b4 + 4 * b5 + b6;
+        uint32_t B = b4 + 4 * b5 + 6 * b6 + 4 * b7 + b8;
+        hrow[r][j] = A | (B << 16);
     }
     __syncthreads();
-    int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
-    if (ox < dw && oy < dh) {
-        int ty = 2 * threadIdx.y, tx = threadIdx.x;
-        int s = hrow[ty][tx] + 4 * hrow[ty + 1][tx] + 6 * hrow[ty + 2][tx] + 4 * hrow[ty + 3][tx] + hrow[ty + 4][tx];
-        dst[(size_t)oy * dstride + ox] = (uint8_t)((s + 128) >> 8);
+    // vertical on packed halves: thread = (output row, 4 adjacent output columns)
+    {
+        int ty = tid >> 4, jq = tid & 15;
+        int oy = oy0 + ty, ox = ox0 + 4 * jq;
+        if (oy < dh && ox < dw) {
+            const uint2 *h = reinterpret_cast<const uint2 *>(&hrow[2 * ty][2 * jq]);
+            const int rp = (PD_TX / 2) / 2;     // row pitch in uint2
+            uint2 h0 = h[0], h1 = h[rp], h2 = h[2 * rp], h3 = h[3 * rp], h4 = h[4 * rp];
+            uint32_t s0 = h0.x + 4 * h1.x + 6 * h2.x + 4 * h3.x + h4.x;
+            uint32_t s1 = h0.y + 4 * h1.y + 6 * h2.y + 4 * h3.y + h4.y;
+            uint32_t r0 = ((s0 + 0x00800080u) >> 8) & 0x00FF00FFu, r1 = ((s1 + 0x00800080u) >> 8) & 0x00FF00FFu;
+            uint32_t out = (r0 & 0xFF) | ((r0 >> 16) << 8) | ((r1 & 0xFF) << 16) | ((r1 >> 16) << 24);
+            uint8_t *d = dst + (size_t)oy * dstride + ox;
+            if (ox + 4 <= dw) *reinterpret_cast<uint32_t *>(d) = out;
+            else for (int k = 0; k < 4 && ox + k < dw; k++) d[k] = (uint8_t)(out >> (8 * k));
+        }
     }
 }
 
@@ -141,7 +236,7 @@ int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images)
 {
     if (n_images <= 0) return SVS_OK;
     for (int l = 1; l < d.nlev; l++) {
-        dim3 blk(PD_TX, PD_TY);
+        dim3 blk(256);
         dim3 grd((d.w[l] + PD_TX - 1) / PD_TX, (d.h[l] + PD_TY - 1) / PD_TY, n_images);
         SVS_KERNEL(c, KID_PYRDOWN, k_pyr_down<<<grd, blk, 0, c->stream>>>(d.base + d.off[l - 1], d.w[l - 1], d.h[l - 1], d.stride[l - 1],
                                                d.base + d.off[l], d.w[l], d.h[l], d.stride[l], d.img_pitch));

@@ -64,6 +64,7 @@ struct svs_ctx {
     long long prof_n[KID_COUNT] = {0};
     int device = 0;
     int sm_count = 0;
+    int zc_ctas = 64;   // persistent grid of the zero-copy (PCIe) ingest kernel; env SVS_ZC_CTAS overrides
     cudaStream_t stream = nullptr;
     std::string err;
     long long launches = 0;
@@ -111,6 +112,8 @@ int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t
 int svs_i_half_nearest(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
                        int n, uint8_t *dst_dev, int dw, int dh, int dst_stride, size_t dst_img_pitch,
                        const uint8_t *const *src_ptrs_dev = nullptr, int ptrs_aligned4 = 0, int rows_decimated = 0);
+int svs_i_half_nearest_zc(svs_ctx *c, const uint8_t *const *src_ptrs_dev, int n_per_eye, int w, int h, size_t row_stride,
+                          uint8_t *dstL, uint8_t *dstR, int dw, int dh, int dst_stride, size_t dst_img_pitch, int ptrs_aligned4);
 int svs_i_copy_level0(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
                       int n, const PyrDesc &d, const uint8_t *const *src_ptrs_dev = nullptr);
 int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images);

@@ -103,6 +103,14 @@ class FrameSet:
             C.c_void_p(self.ctx.h), C.c_void_p(self.h), C.c_void_p(left_ptr), C.c_void_p(right_ptr),
             C.c_size_t(self.in_w), C.c_size_t(self.in_w * self.in_h), int(on_device)))
 
+    def push_ptrs(self, left_ptrs, right_ptrs, on_device, row_stride=None):
+        """One pointer per stream.  on_device: 0 host (staged DMA), 1 device, 2 pinned host read zero-copy over PCIe."""
+        n = self.n_streams
+        lp = (C.c_void_p * n)(*[int(x) for x in left_ptrs])
+        rp = (C.c_void_p * n)(*[int(x) for x in right_ptrs])
+        self.ctx._chk(self.ctx.lib.svs_frameset_push_ptrs(
+            C.c_void_p(self.ctx.h), C.c_void_p(self.h), lp, rp, C.c_size_t(row_stride or self.in_w), int(on_device)))
+
     def download(self, stream, which, level):
         w, h = self.w, self.hgt
         for _ in range(level):

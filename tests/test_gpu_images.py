@@ -98,6 +98,37 @@ def test_frameset_pyramids_and_batched_gftt(ctx, granule):
         fs.close()
 
 
+@pytest.mark.parametrize("H,W,pad", [(370, 1226, 0), (376, 1241, 3), (47, 101, 1)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_frameset_ingest_modes(ctx, H, W, pad, mode):
+    """svs_frameset_push_ptrs: staged DMA (0), device-resident (1) and zero-copy pinned-host (2, the persistent small-grid
+    PCIe reader) ingest give the same half-resolution image and pyramid as the oracle, for aligned and unaligned rows."""
+    import torch
+    B = 6
+    stride = W + pad
+    buf = np.zeros((2, B, H, stride), np.uint8)
+    for e in range(2):
+        for b in range(B):
+            buf[e, b, :, :W] = texture(H, W, 100 * e + b + H)
+    t = torch.from_numpy(buf)
+    t = t.cuda() if mode == 1 else (t.pin_memory() if mode == 2 else t)
+    base = t.data_ptr()
+    lp = [base + (0 * B + b) * H * stride for b in range(B)]
+    rp = [base + (1 * B + b) * H * stride for b in range(B)]
+    fs = ctx.frameset(B, W, H, half=True)
+    try:
+        for rep in range(2):     # twice: current/previous double buffering
+            fs.push_ptrs(lp, rp, mode, row_stride=stride)
+        for b in (0, 3, B - 1):
+            for which, e in ((0, 0), (1, 0), (2, 1)):
+                pyr = o.build_pyramid(o.half_nearest(buf[e, b, :, :W]))
+                for lvl in range(fs.n_levels):
+                    assert np.array_equal(fs.download(b, which, lvl), pyr[lvl]), (b, which, lvl)
+    finally:
+        fs.close()
+    del t
+
+
 @pytest.mark.parametrize("h,w,seed", [(188, 620, 1), (185, 613, 2), (376, 1241, 3), (30, 40, 4)])
 def test_lk_bit_identical_to_oracle(ctx, h, w, seed):
     a, b = moved_pair(h, w, seed)
