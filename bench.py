@@ -29,6 +29,10 @@ import numpy as np
 # OpenMP teams of several pipelines / ranks share the host cores: never spin-wait (must be set before libgomp loads)
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 os.environ.setdefault("GOMP_SPINCOUNT", "0")
+# One hardware work queue per CUDA stream (16 context groups x (main + ingest stream)): with the default of 8 connections
+# several streams share a queue and a group's kernels wait behind ANOTHER group's long PCIe-bound ingest kernel
+# (head-of-line blocking).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -320,9 +324,14 @@ def run_gpu(args, rank, world, local_rank):
 
         def loop(g):
             try:
+                nxt = ptrs(bl, br, lo, g)
                 for s in range(lo, lo + n):
-                    lp, rp = ptrs(bl, br, s, g)
-                    slams[g].add_frames_ptrs(lp, rp, on_device=mode_of(g))
+                    lp, rp = nxt
+                    nxt = ptrs(bl, br, s + 1, g)
+                    if args.no_prefetch:
+                        slams[g].add_frames_ptrs(lp, rp, on_device=mode_of(g))
+                    else:   # double-buffered ingest: frame s+1 crosses PCIe / is resized while frame s is tracked
+                        slams[g].add_frames_ptrs(lp, rp, on_device=mode_of(g), next_left_ptrs=nxt[0], next_right_ptrs=nxt[1])
             except Exception as e:      # surface worker failures in the main thread
                 errors.append(e)
 
@@ -479,7 +488,8 @@ def run_gpu(args, rank, world, local_rank):
         "ms_per_step": dev_pass["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "streams_per_gpu": B, "context_groups": G, "frames_per_step": B * world, "num_features": 150,
-                   "num_active_keyframes": 10, "ba": "synchronous, analytic Jacobians", "clip_frames": nclip,
+                   "num_active_keyframes": 10, "ba": "synchronous, analytic Jacobians",
+                   "ingest": "per-step push" if args.no_prefetch else "double-buffered: frame t+1 is ingested on a second stream during step t", "clip_frames": nclip,
                    "priming_steps": args.priming,
                    "l2": "per-step input %.0f MB per GPU > 126 MB L2 (inputs larger than L2)" % (in_bytes / 1e6)
                    if in_bytes > 126e6 else "per-step input %.0f MB per GPU (< L2; distinct frames every step)" % (in_bytes / 1e6)},
@@ -518,6 +528,7 @@ def main():
                     help="e2e transfer of the pinned host frames: 2 zero-copy kernel reads over PCIe, 0 staged DMA copies")
     ap.add_argument("--clip-frames", type=int, default=48)
     ap.add_argument("--priming", type=int, default=150, help="untimed steps before warm-up so the BA window is full")
+    ap.add_argument("--no-prefetch", action="store_true", help="disable the double-buffered ingest (svs_slam_hint_next)")
     ap.add_argument("--diag", action="store_true", help="repeat the value / e2e regions a second time (detail.diag)")
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames per stream per process for the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -84,6 +84,13 @@ SVS_API int svs_frameset_push(svs_ctx *ctx, svs_frameset *fs, const uint8_t *lef
  *                  reads the frames directly over PCIe, each needed row exactly once */
 SVS_API int svs_frameset_push_ptrs(svs_ctx *ctx, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right,
                                    size_t row_stride, int on_device);
+/* Asynchronous ingest of the NEXT stereo pair (double buffering): starts the resize + pyramids of the pair the caller will
+ * push next into spare buffers on the context's second (ingest) stream and returns immediately, so that the PCIe
+ * transfer of frame t+1 overlaps the tracking / optimisation kernels of frame t.  The following
+ * svs_frameset_push_ptrs with the SAME pointers, row stride and mode only rotates buffers; a push with anything else
+ * discards the prefetch and ingests normally.  The frames must stay valid and unchanged until that push. */
+SVS_API int svs_frameset_prefetch_ptrs(svs_ctx *ctx, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right,
+                                       size_t row_stride, int on_device);
 /* Copy a pyramid level back (tests).  which: 0 = current left, 1 = previous left, 2 = current right */
 SVS_API int svs_frameset_download(svs_ctx *ctx, svs_frameset *fs, int stream, int which, int level,
                                   uint8_t *out, int out_stride);
@@ -241,6 +248,10 @@ SVS_API void svs_slam_destroy(svs_slam *s);
 SVS_API int svs_slam_add_frames(svs_slam *s, const uint8_t *const *left, const uint8_t *const *right, size_t row_stride,
                                 int on_device, double *poses_out /* 7*n */, int32_t *status_out, int32_t *keyframe_out,
                                 int32_t *inliers_out);
+/* Optional hint: the frames of the NEXT svs_slam_add_frames call after the coming one (n pointers each, same row stride
+ * and on_device as the coming call).  The coming call starts their ingest (svs_frameset_prefetch_ptrs) right after its
+ * own push, overlapping it with this step's kernels.  Consumed by one call. */
+SVS_API int svs_slam_hint_next(svs_slam *s, const uint8_t *const *next_left, const uint8_t *const *next_right);
 SVS_API int svs_slam_get_features(svs_slam *s, int stream, int right, float *xy, int64_t *map_point_ids, uint8_t *valid,
                                   int cap, int *n);
 SVS_API int svs_slam_get_keyframes(svs_slam *s, int stream, int active_only, int64_t *kf_ids, int64_t *frame_ids,
@@ -251,6 +262,10 @@ SVS_API int svs_slam_get_landmarks(svs_slam *s, int stream, int active_only, int
  * device time).  counters[10]: frames, keyframes, BA problems, BA iterations, BA trials, BA edges, BA landmarks,
  * BA keyframes, LK points, pose-LM edges. */
 SVS_API int svs_slam_get_counters(svs_slam *s, double *phase_seconds, long long *counters);
+/* host_seconds[8]: the "host bookkeeping" phase split by section (begin + prepare track, finish track + prepare pose,
+ * finish pose + prepare detect, finish detect + prepare right, finish right + prepare triangulate, finish triangulate +
+ * prepare BA, finish BA + end, unused). */
+SVS_API int svs_slam_get_host_seconds(svs_slam *s, double *host_seconds);
 SVS_API svs_frameset *svs_slam_frameset(svs_slam *s);
 /* Host threads (OpenMP) this pipeline uses for its per-stream bookkeeping; several pipelines on distinct contexts may be
  * stepped concurrently from different host threads (their kernels and copies overlap on the device). */

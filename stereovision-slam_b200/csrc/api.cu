@@ -2,6 +2,8 @@
 // (a0 half-resolution resize, a1 GFTT, a2/a3 pyramidal LK).  Host pointers in, host pointers out;
 // staging through pinned buffers owned by the context; one CUDA stream per context.
 #include "svs_internal.h"
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -10,6 +12,14 @@
 int svs_i_gftt_overflow(svs_ctx *c, int n_img, int *flag_host);
 
 static std::string g_create_err;
+static std::atomic<int> g_live_ctx{0};
+
+int svs_i_zc_grid(const svs_ctx *c)
+{
+    if (c->zc_ctas > 0) return c->zc_ctas;
+    int live = std::max(1, g_live_ctx.load());
+    return std::max(2, 32 / live);
+}
 
 void svs_i_prof_begin(svs_ctx *c, int kid)
 {
@@ -43,9 +53,10 @@ static void prof_harvest(svs_ctx *c)
 
 extern "C" {
 
-static int frameset_finish_push(svs_ctx *c, svs_frameset *fs, const uint8_t *dl, const uint8_t *dr, size_t rs, size_t is,
-                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated = 0,
-                                int zero_copy = 0);
+static int frameset_fill(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const PyrDesc &Rc, const uint8_t *dl, const uint8_t *dr,
+                         size_t rs, size_t is, const uint8_t *const *pl, const uint8_t *const *pr, int aligned4,
+                         int rows_decimated = 0, int zero_copy = 0);
+static int frameset_begin_push(svs_ctx *c, svs_frameset *fs);
 
 int svs_version(void) { return 100; }
 
@@ -81,6 +92,9 @@ const char *svs_create_error(void) { return g_create_err.c_str(); }
 
 svs_ctx *svs_create(int device)
 {
+    // one hardware work queue per stream (a context owns two): with the default of 8, streams of different contexts share
+    // a queue and wait behind each other's long ingest kernels.  Only effective if the CUDA context does not exist yet.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -106,6 +120,7 @@ svs_ctx *svs_create(int device)
         delete c;
         return nullptr;
     }
+    g_live_ctx++;
     return c;
 }
 
@@ -120,6 +135,8 @@ void svs_destroy(svs_ctx *c)
     for (DevBuf *b : d) b->release();
     c->h_in.release(); c->h_out.release();
     cudaStreamDestroy(c->stream);
+    if (c->stream_in) cudaStreamDestroy(c->stream_in);
+    g_live_ctx--;
     delete c;
 }
 
@@ -145,7 +162,7 @@ svs_frameset *svs_frameset_create(svs_ctx *c, int n_streams, int in_w, int in_h,
     PyrDesc d;
     svs_i_make_pyr_desc(&d, fs->W, fs->H, lk_win, lk_max_level, &per);
     fs->nlev = d.nlev;
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 5; i++) {
         if (fs->pyr[i].reserve(per * n_streams) != cudaSuccess) {
             c->err = "frameset: cudaMalloc failed";
             svs_frameset_destroy(c, fs);
@@ -153,20 +170,30 @@ svs_frameset *svs_frameset_create(svs_ctx *c, int n_streams, int in_w, int in_h,
         }
         cudaMemsetAsync(fs->pyr[i].p, 0, per * n_streams, c->stream);
     }
-    fs->L[0] = d; fs->L[0].base = fs->pyr[0].as<uint8_t>();
-    fs->L[1] = d; fs->L[1].base = fs->pyr[1].as<uint8_t>();
-    fs->R = d; fs->R.base = fs->pyr[2].as<uint8_t>();
+    for (int i = 0; i < 3; i++) { fs->L[i] = d; fs->L[i].base = fs->pyr[i].as<uint8_t>(); }
+    for (int i = 0; i < 2; i++) { fs->R[i] = d; fs->R[i].base = fs->pyr[3 + i].as<uint8_t>(); }
+    if (cudaEventCreateWithFlags(&fs->pf_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fs->pf_order, cudaEventDisableTiming) != cudaSuccess) {
+        c->err = "frameset: cudaEventCreate failed";
+        svs_frameset_destroy(c, fs);
+        return nullptr;
+    }
     return fs;
 }
 
 void svs_frameset_destroy(svs_ctx *c, svs_frameset *fs)
 {
     if (!fs) return;
-    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
-    for (int i = 0; i < 3; i++) fs->pyr[i].release();
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); if (c->stream_in) cudaStreamSynchronize(c->stream_in); }
+    for (int i = 0; i < 5; i++) fs->pyr[i].release();
     fs->staging.release();
     fs->ptr_table.release();
     fs->ptr_table_h.release();
+    fs->pf_staging.release();
+    fs->pf_ptr_table.release();
+    fs->pf_ptr_table_h.release();
+    if (fs->pf_done) cudaEventDestroy(fs->pf_done);
+    if (fs->pf_order) cudaEventDestroy(fs->pf_order);
     delete fs;
 }
 
@@ -201,29 +228,81 @@ int svs_frameset_push(svs_ctx *c, svs_frameset *fs, const uint8_t *left, const u
         }
         dl = sl; dr = sr; rs = fs->in_w; is = dense; decim = fs->half ? 1 : 0;
     }
-    return frameset_finish_push(c, fs, dl, dr, rs, is, nullptr, nullptr, 0, decim);
+    SVS_TRY(frameset_begin_push(c, fs));
+    return frameset_fill(c, fs, fs->L[fs->il_cur], fs->R[fs->ir_cur], dl, dr, rs, is, nullptr, nullptr, 0, decim);
 }
 
-static int frameset_finish_push(svs_ctx *c, svs_frameset *fs, const uint8_t *dl, const uint8_t *dr, size_t rs, size_t is,
-                                const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated, int zero_copy)
+// resize (or copy) + pyramids of one stereo pair per stream into the given target buffers, on c->stream
+static int frameset_fill(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const PyrDesc &Rc, const uint8_t *dl, const uint8_t *dr,
+                         size_t rs, size_t is, const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated,
+                         int zero_copy)
 {
-    fs->cur ^= 1;
-    fs->pushes++;
-    PyrDesc &Lc = fs->L[fs->cur];
-    if (fs->half && zero_copy && pl && pr == pl + fs->B && Lc.stride[0] == fs->R.stride[0] && Lc.img_pitch == fs->R.img_pitch) {
+    if (fs->half && zero_copy && pl && pr == pl + fs->B) {
         // frames live in pinned host memory: small persistent grid, both eyes in one launch (images.cu)
-        SVS_TRY(svs_i_half_nearest_zc(c, pl, fs->B, fs->in_w, fs->in_h, rs, Lc.base + Lc.off[0], fs->R.base + fs->R.off[0], fs->W, fs->H,
+        SVS_TRY(svs_i_half_nearest_zc(c, pl, fs->B, fs->in_w, fs->in_h, rs, Lc.base + Lc.off[0], Rc.base + Rc.off[0], fs->W, fs->H,
                                       Lc.stride[0], Lc.img_pitch, aligned4));
     } else if (fs->half) {
         SVS_TRY(svs_i_half_nearest(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc.base + Lc.off[0], fs->W, fs->H, Lc.stride[0], Lc.img_pitch, pl, aligned4, rows_decimated));
-        SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R.base + fs->R.off[0], fs->W, fs->H, fs->R.stride[0], fs->R.img_pitch, pr, aligned4, rows_decimated));
+        SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, Rc.base + Rc.off[0], fs->W, fs->H, Rc.stride[0], Rc.img_pitch, pr, aligned4, rows_decimated));
     } else {
         SVS_TRY(svs_i_copy_level0(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc, pl));
-        SVS_TRY(svs_i_copy_level0(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, fs->R, pr));
+        SVS_TRY(svs_i_copy_level0(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, Rc, pr));
     }
     SVS_TRY(svs_i_build_pyramid(c, Lc, fs->B));
-    SVS_TRY(svs_i_build_pyramid(c, fs->R, fs->B));
+    SVS_TRY(svs_i_build_pyramid(c, Rc, fs->B));
     return SVS_OK;
+}
+
+// A push without a usable prefetch: order after any pending prefetch (it wrote the buffers that become "current"),
+// drop it, rotate the buffer roles.
+static int frameset_begin_push(svs_ctx *c, svs_frameset *fs)
+{
+    if (fs->pf_pending) {
+        SVS_CUDA(c, cudaStreamWaitEvent(c->stream, fs->pf_done, 0));
+        fs->pf_pending = false;
+        fs->prefetch_misses++;
+    }
+    fs->rotate();
+    fs->pushes++;
+    return SVS_OK;
+}
+
+// Host pointers (pinned or pageable) -> staged copies of the rows the resize reads; device / zero-copy pointers ->
+// pointer table.  Everything is enqueued on c->stream (the caller may have swapped in the ingest stream).
+static int frameset_ingest_ptrs(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const PyrDesc &Rc, const uint8_t *const *left,
+                                const uint8_t *const *right, size_t row_stride, int on_device, DevBuf &ptr_table, PinBuf &ptr_table_h,
+                                DevBuf &staging, bool table_may_be_in_flight)
+{
+    const int B = fs->B;
+    // on_device == 2: the pointers are PINNED HOST memory that the device can address (cudaHostAlloc / UVA): the resize
+    // kernel reads the frames straight over PCIe (each needed row exactly once), no staging copy.
+    if (on_device) {
+        SVS_CUDA(c, ptr_table.reserve((size_t)2 * B * sizeof(void *)));
+        SVS_CUDA(c, ptr_table_h.reserve((size_t)2 * B * sizeof(void *)));
+        const uint8_t **hp = ptr_table_h.as<const uint8_t *>();
+        int aligned4 = 1;
+        // the previous table copy must have been consumed before the pinned table is overwritten
+        if (table_may_be_in_flight) SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int b = 0; b < B; b++) {
+            hp[b] = left[b]; hp[B + b] = right[b];
+            if ((reinterpret_cast<uintptr_t>(left[b]) | reinterpret_cast<uintptr_t>(right[b])) & 3) aligned4 = 0;
+        }
+        SVS_CUDA(c, cudaMemcpyAsync(ptr_table.p, hp, (size_t)2 * B * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+        const uint8_t *const *dp = ptr_table.as<const uint8_t *>();
+        return frameset_fill(c, fs, Lc, Rc, nullptr, nullptr, row_stride, 0, dp, dp + B, aligned4, 0, on_device == 2);
+    }
+    // Staged path: only the even rows the half-resolution resize reads cross PCIe (strided 2-D DMA copies); the kernel
+    // then reads the staged rows with a unit row step.
+    const int rows = fs->half ? fs->H : fs->in_h;
+    const size_t src_pitch = fs->half ? 2 * row_stride : row_stride;
+    size_t dense = (size_t)fs->in_w * rows;
+    SVS_CUDA(c, staging.reserve(2 * dense * B));
+    uint8_t *sl = staging.as<uint8_t>(), *sr = sl + dense * B;
+    for (int b = 0; b < B; b++) {
+        SVS_CUDA(c, cudaMemcpy2DAsync(sl + dense * b, fs->in_w, left[b], src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
+        SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right[b], src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
+    }
+    return frameset_fill(c, fs, Lc, Rc, sl, sr, fs->in_w, dense, nullptr, nullptr, 0, fs->half ? 1 : 0);
 }
 
 int svs_frameset_push_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right, size_t row_stride,
@@ -233,43 +312,58 @@ int svs_frameset_push_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *l
     if (row_stride < (size_t)fs->in_w) SVS_FAIL(c, SVS_ERR_ARG, "frameset_push_ptrs: bad row stride");
     SVS_CUDA(c, cudaSetDevice(c->device));
     const int B = fs->B;
-    // on_device == 2: the pointers are PINNED HOST memory that the device can address (cudaHostAlloc / UVA): the resize
-    // kernel reads the frames straight over PCIe (each needed row exactly once), no staging copy.
-    if (on_device) {
-        SVS_CUDA(c, fs->ptr_table.reserve((size_t)2 * B * sizeof(void *)));
-        SVS_CUDA(c, fs->ptr_table_h.reserve((size_t)2 * B * sizeof(void *)));
-        const uint8_t **hp = fs->ptr_table_h.as<const uint8_t *>();
-        int aligned4 = 1;
-        // the previous push's table copy must have been consumed before the pinned table is overwritten
-        SVS_CUDA(c, cudaStreamSynchronize(c->stream));
-        for (int b = 0; b < B; b++) {
-            hp[b] = left[b]; hp[B + b] = right[b];
-            if ((reinterpret_cast<uintptr_t>(left[b]) | reinterpret_cast<uintptr_t>(right[b])) & 3) aligned4 = 0;
-        }
-        SVS_CUDA(c, cudaMemcpyAsync(fs->ptr_table.p, hp, (size_t)2 * B * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
-        const uint8_t *const *dp = fs->ptr_table.as<const uint8_t *>();
-        return frameset_finish_push(c, fs, nullptr, nullptr, row_stride, 0, dp, dp + B, aligned4, 0, on_device == 2);
+    if (fs->pf_pending && fs->pf_mode == on_device && fs->pf_row_stride == row_stride &&
+        memcmp(fs->pf_ptrs.data(), left, (size_t)B * sizeof(void *)) == 0 &&
+        memcmp(fs->pf_ptrs.data() + B, right, (size_t)B * sizeof(void *)) == 0) {
+        // this pair was prefetched into the "next" buffers on the ingest stream: rotate and order the main stream after it
+        fs->pf_pending = false;
+        fs->prefetch_hits++;
+        fs->rotate();
+        fs->pushes++;
+        SVS_CUDA(c, cudaStreamWaitEvent(c->stream, fs->pf_done, 0));
+        return SVS_OK;
     }
-    // Staged path: only the even rows the half-resolution resize reads cross PCIe (strided 2-D DMA copies); the kernel
-    // then reads the staged rows with a unit row step.  (Whole-frame linear copies were measured slower in the
-    // multi-context setting, zero-copy — on_device == 2 — faster: DESIGN.md §7.)
-    const int rows = fs->half ? fs->H : fs->in_h;
-    const size_t src_pitch = fs->half ? 2 * row_stride : row_stride;
-    size_t dense = (size_t)fs->in_w * rows;
-    SVS_CUDA(c, fs->staging.reserve(2 * dense * B));
-    uint8_t *sl = fs->staging.as<uint8_t>(), *sr = sl + dense * B;
-    for (int b = 0; b < B; b++) {
-        SVS_CUDA(c, cudaMemcpy2DAsync(sl + dense * b, fs->in_w, left[b], src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
-        SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right[b], src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
-    }
-    return frameset_finish_push(c, fs, sl, sr, fs->in_w, dense, nullptr, nullptr, 0, fs->half ? 1 : 0);
+    SVS_TRY(frameset_begin_push(c, fs));
+    return frameset_ingest_ptrs(c, fs, fs->L[fs->il_cur], fs->R[fs->ir_cur], left, right, row_stride, on_device, fs->ptr_table,
+                                fs->ptr_table_h, fs->staging, true);
+}
+
+int svs_frameset_prefetch_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right,
+                               size_t row_stride, int on_device)
+{
+    if (!c || !fs || !left || !right) return SVS_ERR_ARG;
+    if (row_stride < (size_t)fs->in_w) SVS_FAIL(c, SVS_ERR_ARG, "frameset_prefetch_ptrs: bad row stride");
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    if (!c->stream_in) SVS_CUDA(c, cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking));
+    const int B = fs->B;
+    // a previous prefetch that was never consumed: its kernels (and its pointer-table copy) must be done before its
+    // buffers / tables are reused
+    if (fs->pf_pending) { SVS_CUDA(c, cudaEventSynchronize(fs->pf_done)); fs->pf_pending = false; fs->prefetch_misses++; }
+    else if (fs->pushes > 0 || fs->prefetch_hits > 0) SVS_CUDA(c, cudaEventSynchronize(fs->pf_done));
+    // the "next" buffers may still be read by work already queued on the main stream
+    SVS_CUDA(c, cudaEventRecord(fs->pf_order, c->stream));
+    SVS_CUDA(c, cudaStreamWaitEvent(c->stream_in, fs->pf_order, 0));
+    fs->pf_ptrs.resize((size_t)2 * B);
+    memcpy(fs->pf_ptrs.data(), left, (size_t)B * sizeof(void *));
+    memcpy(fs->pf_ptrs.data() + B, right, (size_t)B * sizeof(void *));
+    fs->pf_mode = on_device; fs->pf_row_stride = row_stride;
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->stream_in;           // every svs_i_* launch below goes to the ingest stream
+    int rc = frameset_ingest_ptrs(c, fs, fs->L[fs->il_next], fs->R[fs->ir_next], left, right, row_stride, on_device, fs->pf_ptr_table,
+                                  fs->pf_ptr_table_h, fs->pf_staging, false);
+    cudaError_t e = cudaEventRecord(fs->pf_done, c->stream_in);
+    c->stream = main_stream;
+    if (rc != SVS_OK) return rc;
+    SVS_CUDA(c, e);
+    fs->pf_pending = true;
+    return SVS_OK;
 }
 
 int svs_frameset_download(svs_ctx *c, svs_frameset *fs, int stream, int which, int level, uint8_t *out, int out_stride)
 {
     if (!c || !fs || stream < 0 || stream >= fs->B || level < 0 || level >= fs->nlev || which < 0 || which > 2) return SVS_ERR_ARG;
     SVS_CUDA(c, cudaSetDevice(c->device));
-    const PyrDesc &d = which == 0 ? fs->L[fs->cur] : which == 1 ? fs->L[fs->cur ^ 1] : fs->R;
+    const PyrDesc &d = which == 0 ? fs->Lcur() : which == 1 ? fs->Lprev() : fs->Rcur();
     SVS_CUDA(c, cudaMemcpy2DAsync(out, out_stride, d.base + (size_t)stream * d.img_pitch + d.off[level], d.stride[level],
                                   d.w[level], d.h[level], cudaMemcpyDeviceToHost, c->stream));
     SVS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -381,7 +475,7 @@ int svs_gftt_detect_batch(svs_ctx *c, svs_frameset *fs, const int32_t *stream_id
     if (n_sel == 0) return SVS_OK;
     for (int i = 0; i < n_sel; i++) if (stream_ids[i] < 0 || stream_ids[i] >= fs->B) SVS_FAIL(c, SVS_ERR_ARG, "gftt_batch: stream id out of range");
     SVS_CUDA(c, cudaSetDevice(c->device));
-    const PyrDesc &L = fs->L[fs->cur];
+    const PyrDesc &L = fs->Lcur();
     return gftt_common(c, L.base + L.off[0], fs->W, fs->H, L.stride[0], L.img_pitch, n_sel, stream_ids, nullptr, 0, occ_off,
                        occupied_xy, max_corners, quality, min_distance, granule, out_xy, out_response, out_n);
 }
@@ -441,8 +535,8 @@ int svs_lk_track_batch(svs_ctx *c, svs_frameset *fs, int pair, const int32_t *of
 {
     if (!c || !fs || !off || (pair != 0 && pair != 1)) return SVS_ERR_ARG;
     SVS_CUDA(c, cudaSetDevice(c->device));
-    const PyrDesc &prev = pair == 0 ? fs->L[fs->cur ^ 1] : fs->L[fs->cur];
-    const PyrDesc &next = pair == 0 ? fs->L[fs->cur] : fs->R;
+    const PyrDesc &prev = pair == 0 ? fs->Lprev() : fs->Lcur();
+    const PyrDesc &next = pair == 0 ? fs->Lcur() : fs->Rcur();
     return lk_common(c, prev, next, fs->B, off, prev_xy, next_xy, fs->win, max_iter, eps, status);
 }
 

@@ -59,7 +59,7 @@ struct BaArgs {
     int max_iter, jac_mode;
 };
 
-#define BA_T 256
+#define BA_T 512    // one CTA per SM: a window problem is latency-bound, so it gets as many threads as 128 registers each allow
 #define BA_CH 16    // (edge, edge) pairs per Schur chunk
 #include "ba_ldlt.cuh"
 
@@ -90,7 +90,7 @@ __device__ __forceinline__ double block_max(double v, double *red)
     return r;
 }
 
-__global__ void __launch_bounds__(BA_T, 2)
+__global__ void __launch_bounds__(BA_T, 1)
 k_ba_window(BaArgs A)
 {
     extern __shared__ double smd[];

@@ -261,12 +261,27 @@ k_pose_only_lm(int n_prob, const int32_t *__restrict__ off, const double *__rest
                     double e2 = er[0] * er[0] + er[1] * er[1], r0 = e2, r1 = 1.0;
                     if (robust) gd::huber(e2, huber_delta, r0, r1);
                     cur += r0;
-                    int k = 0;
+                    // J = [a0 0 a2 a3 a4 a5; 0 b1 b2 b3 b4 b5] (g2o_types.h:159-162): the structural zeros are skipped,
+                    // which leaves every sum unchanged (they would add +-0)
+                    const double w0 = r1 * er[0], w1 = r1 * er[1];
+                    b[0] -= J[0] * w0; b[1] -= J[7] * w1;
 #pragma unroll
-                    for (int a = 0; a < 6; a++) {
-                        b[a] -= r1 * (J[a] * er[0] + J[6 + a] * er[1]);
+                    for (int a = 2; a < 6; a++) b[a] -= J[a] * w0 + J[6 + a] * w1;
+                    const double ra0 = r1 * J[0], rb1 = r1 * J[7];
+                    H[0] += ra0 * J[0];                                   // (0,0)
 #pragma unroll
-                        for (int c2 = a; c2 < 6; c2++) H[k++] += r1 * (J[a] * J[c2] + J[6 + a] * J[6 + c2]);
+                    for (int c2 = 2; c2 < 6; c2++) H[c2] += ra0 * J[c2];   // (0,2..5); (0,1) stays 0
+                    H[6] += rb1 * J[7];                                   // (1,1)
+#pragma unroll
+                    for (int c2 = 2; c2 < 6; c2++) H[5 + c2] += rb1 * J[6 + c2];   // (1,2..5)
+                    {
+                        int k = 11;
+#pragma unroll
+                        for (int a = 2; a < 6; a++) {
+                            const double ra = r1 * J[a], rb = r1 * J[6 + a];
+#pragma unroll
+                            for (int c2 = a; c2 < 6; c2++) H[k++] += ra * J[c2] + rb * J[6 + c2];
+                        }
                     }
                 }
                 {

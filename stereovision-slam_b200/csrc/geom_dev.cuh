@@ -77,16 +77,16 @@ __device__ __forceinline__ void huber(double e2, double delta, double &rho0, dou
 {
     double d2 = delta * delta;
     if (e2 <= d2) { rho0 = e2; rho1 = 1.0; }
-    else { double s = sqrt(e2); rho0 = 2 * s * delta - d2; rho1 = delta / s; }
+    else { double rs = rsqrt(e2), s = e2 * rs; rho0 = 2 * s * delta - d2; rho1 = delta * rs; }   // one rsqrt instead of sqrt + divide
 }
 
 // EdgeProjectionPoseOnly::computeError (g2o_types.h:117-130)
 __device__ __forceinline__ void po_error(const double *T, const double *K, const double *pw, const double *uv, double *e, double *pc)
 {
     se3_act(T, pw, pc);
-    double px = K[0] * pc[0] + K[2] * pc[2], py = K[1] * pc[1] + K[3] * pc[2], pz = pc[2];
-    e[0] = uv[0] - px / pz;
-    e[1] = uv[1] - py / pz;
+    double px = K[0] * pc[0] + K[2] * pc[2], py = K[1] * pc[1] + K[3] * pc[2], iz = 1.0 / pc[2];   // one reciprocal, two products
+    e[0] = uv[0] - px * iz;
+    e[1] = uv[1] - py * iz;
 }
 // EdgeProjectionPoseOnly::linearizeOplus (g2o_types.h:132-163), J 2x6 row-major
 __device__ __forceinline__ void po_jac(const double *K, const double *pc, double *J)
@@ -103,9 +103,9 @@ __device__ __forceinline__ void ba_error(const double *T, const double *ext, con
 {
     se3_act(T, p, a);
     se3_act(ext, a, c);
-    double px = K[0] * c[0] + K[2] * c[2], py = K[1] * c[1] + K[3] * c[2], pz = c[2];
-    e[0] = uv[0] - px / pz;
-    e[1] = uv[1] - py / pz;
+    double px = K[0] * c[0] + K[2] * c[2], py = K[1] * c[1] + K[3] * c[2], iz = 1.0 / c[2];
+    e[0] = uv[0] - px * iz;
+    e[1] = uv[1] - py * iz;
 }
 // analytic Jacobians of EdgeProjection w.r.t. the left-multiplicative pose update (2x6) and the landmark (2x3)
 __device__ __forceinline__ void ba_jac_analytic(const double *T, const double *ext, const double *K, const double *a, const double *c,

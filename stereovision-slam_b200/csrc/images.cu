@@ -79,7 +79,9 @@ int svs_i_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_
 // parked on PCIe loads and keeps the other contexts' kernels (LK, pose-LM, BA of other stream groups) off the SMs for
 // the whole transfer.  So: a SMALL persistent grid, each thread keeps ZC_U x 2 independent 4-byte loads in flight and
 // walks (image, row, 4-pixel chunk) items with a grid stride; both eyes in one launch (src_ptrs = [left.. | right..]).
-#define ZC_U 4
+// The grid is sized so that ALL live contexts together keep ~0.5 MB in flight (svs_i_zc_grid): with double-buffered
+// ingest every context has such a kernel resident most of the time.
+#define ZC_U 8
 __global__ void __launch_bounds__(256)
 k_half_nearest_zc(const uint8_t *const *__restrict__ src_ptrs, int n_img_per_eye, int w, int h, size_t row_stride,
                   uint8_t *__restrict__ dstL, uint8_t *__restrict__ dstR, int dw, int dh, int dst_stride, size_t dst_img_pitch, int vec_ok)
@@ -133,7 +135,7 @@ int svs_i_half_nearest_zc(svs_ctx *c, const uint8_t *const *src_ptrs_dev, int n_
                  ((reinterpret_cast<uintptr_t>(dstL) | reinterpret_cast<uintptr_t>(dstR) | (size_t)dst_stride | dst_img_pitch) & 3) == 0;
     long long items = (long long)((dw + 3) / 4) * dh * 2 * n_per_eye;
     long long want = (items + 256 * ZC_U - 1) / (256 * ZC_U);
-    int grid = (int)std::min<long long>(want, c->zc_ctas > 0 ? c->zc_ctas : 64);
+    int grid = (int)std::min<long long>(want, svs_i_zc_grid(c));
     SVS_KERNEL(c, KID_HALF, k_half_nearest_zc<<<grid, 256, 0, c->stream>>>(src_ptrs_dev, n_per_eye, w, h, row_stride, dstL, dstR, dw, dh,
                                                                          dst_stride, dst_img_pitch, vec_ok));
     return SVS_OK;

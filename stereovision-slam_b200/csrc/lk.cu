@@ -5,8 +5,9 @@
 // One warp per keypoint; the warp walks the pyramid levels coarse -> fine inside the kernel.
 // Per level the (win+3)^2 patch of the previous image is staged in shared memory, the Scharr
 // derivative patch is derived from it, each lane keeps its <=ceil(win^2/32) window samples
-// (I, Ix, Iy as int16 values) in registers, and every iteration stages the (win+1)^2 patch of the
-// next image and reduces the two mismatch sums with redux.sync.  All window sums are exact
+// (I, Ix, Iy as int16 values) in registers; a (win+1+12)^2 region of the next image is staged once
+// per level (restaged only if the window leaves it), every iteration samples its window from that
+// region and reduces the two mismatch sums with redux.sync.  All window sums are exact
 // integers (OpenCV accumulates the same integers in f32 lanes), the 2x2 solve is f32 with the
 // exact operation order of OpenCV — compile with --fmad=false.
 #include "svs_internal.h"
@@ -29,6 +30,7 @@ __device__ __forceinline__ int cvfloor(float v) { return __float2int_rd(v); }
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
 #define LK_WARPS 4
+#define LK_MARGIN 6      // the next-image region staged per level extends this many pixels around the first window
 
 template <int WIN>
 __global__ void __launch_bounds__(LK_WARPS * 32)
@@ -38,12 +40,19 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
     constexpr int PW = WIN + 3;                 // previous-image patch (window + bilinear + Scharr halo)
     constexpr int DW = WIN + 1;                 // derivative / next-image patch
     constexpr int IWORDS = (PW + 3 + 3) / 4;    // aligned 32-bit words covering a patch row at any byte offset
-    constexpr int JWORDS = (DW + 3 + 3) / 4;
-    constexpr int IP = 4 * IWORDS, JP = 4 * JWORDS;   // smem row pitches (bytes)
+    constexpr int IP = 4 * IWORDS;              // smem row pitch of the previous-image patch (bytes)
+    // Next-image REGION: DW + 2*LK_MARGIN rows x RWORDS aligned words, staged once per level around the first window.
+    // The iterations of a level move the window by fractions of a pixel, so almost all of them sample straight from
+    // this region and touch no global memory (one L2 round trip per level instead of one per iteration).
+    constexpr int RH = DW + 2 * LK_MARGIN;
+    constexpr int RWORDS = (DW + 2 * LK_MARGIN + 3 + 3) / 4;
+    constexpr int RP = 4 * RWORDS;              // region row pitch (bytes); the border-case patch uses the same pitch
+    constexpr int RN = (RH * RWORDS + 31) / 32; // region words per lane
+    constexpr int IN = (PW * IWORDS + 31) / 32; // previous-patch words per lane
     constexpr int NPL = (WIN * WIN + 31) / 32;  // window samples per lane
     __shared__ __align__(16) uint8_t sI[LK_WARPS][PW * IP];
     __shared__ short2 sD[LK_WARPS][DW * DW];
-    __shared__ __align__(16) uint8_t sJ[LK_WARPS][DW * JP];
+    __shared__ __align__(16) uint8_t sJ[LK_WARPS][RH * RP];
     const int W_BITS = 14;
     const float FLT_SCALE = 1.f / (1 << 20);
     const float half = (WIN - 1) * 0.5f;
@@ -57,6 +66,15 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
     uint8_t *mI = sI[warp], *mJ = sJ[warp];
     short2 *mD = sD[warp];
     int nlev = min(prev.nlev, next.nlev);
+    // this lane's window samples: smem offsets in the previous-image patch and in the next-image region
+    int offI[NPL], offJ[NPL], offD[NPL];
+#pragma unroll
+    for (int q = 0; q < NPL; q++) {
+        int k = lane + 32 * q;
+        int y = k / WIN, x = k - y * WIN;
+        offI[q] = (y + 1) * IP + (x + 1); offJ[q] = y * RP + x; offD[q] = y * DW + x;
+    }
+    const float eps2f = (float)eps2, eps_lo = eps2f * 0.9999f, eps_hi = eps2f * 1.0001f;
 
     for (int level = nlev - 1; level >= 0; level--) {
         const uint8_t *I = prev.base + (size_t)img * prev.img_pitch + prev.off[level];
@@ -75,22 +93,57 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
         int w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
         int w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), (float)(1 << W_BITS)));
         int w11 = (1 << W_BITS) - w00 - w01 - w10;
+        float nx = __fsub_rn(nxt_x, half), ny = __fsub_rn(nxt_y, half);
 
         __syncwarp();
+        // ---- issue the next-image region loads first (they are independent of everything below), then stage the
+        //      previous-image patch; both global round trips overlap
+        bool reg_valid = false;
+        int rx0 = 0, ry0 = 0;
+        uint32_t jr[RN];
+        {
+            int jx = cvfloor(nx), jy = cvfloor(ny);
+            if (jx >= 0 && jy >= 0 && jx + DW <= Jw && jy + DW <= Jh) {
+                ry0 = jy - LK_MARGIN; rx0 = (jx - LK_MARGIN) & ~3;
+                reg_valid = true;
+#pragma unroll
+                for (int u = 0; u < RN; u++) {
+                    int k = lane + 32 * u;
+                    int r = k / RWORDS, q = k - r * RWORDS;
+                    int y = min(max(ry0 + r, 0), Jh - 1), x = min(max(rx0 + 4 * q, 0), Js - 4);
+                    jr[u] = (k < RH * RWORDS) ? __ldg(reinterpret_cast<const uint32_t *>(J + (size_t)y * Js + x)) : 0u;
+                }
+            }
+        }
         // stage the previous-image patch: mI[j][ioff + i] = I(ix-1+i, iy-1+j), reflect-101 outside.
         // Interior patches (the common case) are staged with aligned 32-bit loads and no border arithmetic.
         int ioff = 0;
         if (ix - 1 >= 0 && iy - 1 >= 0 && ix - 1 + PW <= Iw && iy - 1 + PW <= Ih) {
             ioff = (ix - 1) & 3;
             const uint8_t *base = I + (size_t)(iy - 1) * Is + (ix - 1 - ioff);
-            for (int k = lane; k < PW * IWORDS; k += 32) {
+            uint32_t ir[IN];
+#pragma unroll
+            for (int u = 0; u < IN; u++) {
+                int k = lane + 32 * u;
                 int j = k / IWORDS, q = k - j * IWORDS;
-                reinterpret_cast<uint32_t *>(mI)[j * IWORDS + q] = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)j * Is) + q);
+                ir[u] = (k < PW * IWORDS) ? __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)j * Is) + q) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < IN; u++) {
+                int k = lane + 32 * u;
+                if (k < PW * IWORDS) reinterpret_cast<uint32_t *>(mI)[k] = ir[u];
             }
         } else {
             for (int k = lane; k < PW * PW; k += 32) {
                 int j = k / PW, i = k - j * PW;
                 mI[j * IP + i] = __ldg(I + (size_t)lk_refl101(iy - 1 + j, Ih) * Is + lk_refl101(ix - 1 + i, Iw));
+            }
+        }
+        if (reg_valid) {
+#pragma unroll
+            for (int u = 0; u < RN; u++) {
+                int k = lane + 32 * u;
+                if (k < RH * RWORDS) reinterpret_cast<uint32_t *>(mJ)[k] = jr[u];
             }
         }
         __syncwarp();
@@ -102,13 +155,12 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
             if (X >= 0 && X < Iw && Y >= 0 && Y < Ih) {
                 const uint8_t *p = mI + j * IP + i + ioff;   // top-left of the 3x3 neighbourhood
                 int v00 = p[0], v01 = p[1], v02 = p[2];
-                int v10 = p[IP], v11 = p[IP + 1], v12 = p[IP + 2];
+                int v10 = p[IP], v12 = p[IP + 2];
                 int v20 = p[2 * IP], v21 = p[2 * IP + 1], v22 = p[2 * IP + 2];
                 int s0l = (v00 + v20) * 3 + v10 * 10, s0r = (v02 + v22) * 3 + v12 * 10;
                 int s1l = v20 - v00, s1c = v21 - v01, s1r = v22 - v02;
                 d.x = (short)(s0r - s0l);
                 d.y = (short)((s1l + s1r) * 3 + s1c * 10);
-                (void)v11;
             }
             mD[k] = d;
         }
@@ -120,10 +172,10 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
             int k = lane + 32 * q;
             Iv[q] = 0; Ixv[q] = 0; Iyv[q] = 0;
             if (k < WIN * WIN) {
-                int y = k / WIN, x = k - y * WIN;
-                const uint8_t *p = mI + (y + 1) * IP + (x + 1) + ioff;
+                const uint8_t *p = mI + offI[q] + ioff;
                 int ival = descale(p[0] * w00 + p[1] * w01 + p[IP] * w10 + p[IP + 1] * w11, W_BITS - 5);
-                short2 d00 = mD[y * DW + x], d01 = mD[y * DW + x + 1], d10 = mD[(y + 1) * DW + x], d11 = mD[(y + 1) * DW + x + 1];
+                const short2 *dp = mD + offD[q];
+                short2 d00 = dp[0], d01 = dp[1], d10 = dp[DW], d11 = dp[DW + 1];
                 int ixv = descale(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, W_BITS);
                 int iyv = descale(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, W_BITS);
                 Iv[q] = (short)ival; Ixv[q] = (short)ixv; Iyv[q] = (short)iyv;
@@ -139,7 +191,6 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
         float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * WIN * WIN));
         if ((double)minEig < 1e-4 || D < FLT_EPSILON) { if (level == 0) st = false; continue; }
         D = __fdiv_rn(1.f, D);
-        float nx = __fsub_rn(nxt_x, half), ny = __fsub_rn(nxt_y, half);
         float pdx = 0.f, pdy = 0.f;
         for (int j = 0; j < max_iter; j++) {
             int jx = cvfloor(nx), jy = cvfloor(ny);
@@ -149,30 +200,38 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
             w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
             w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), (float)(1 << W_BITS)));
             w11 = (1 << W_BITS) - w00 - w01 - w10;
-            __syncwarp();
-            int joff = 0;
+            const uint8_t *pJ;
             if (jx >= 0 && jy >= 0 && jx + DW <= Jw && jy + DW <= Jh) {
-                joff = jx & 3;
-                const uint8_t *base = J + (size_t)jy * Js + (jx - joff);
-                for (int k = lane; k < DW * JWORDS; k += 32) {
-                    int r = k / JWORDS, q = k - r * JWORDS;
-                    reinterpret_cast<uint32_t *>(mJ)[r * JWORDS + q] = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)r * Js) + q);
+                if (!(reg_valid && jx >= rx0 && jx + DW <= rx0 + RP && jy >= ry0 && jy + DW <= ry0 + RH)) {
+                    // the window left the staged region (or there is none yet): restage around the current window
+                    __syncwarp();
+                    ry0 = jy - LK_MARGIN; rx0 = (jx - LK_MARGIN) & ~3;
+                    for (int k = lane; k < RH * RWORDS; k += 32) {
+                        int r = k / RWORDS, q = k - r * RWORDS;
+                        int y = min(max(ry0 + r, 0), Jh - 1), x = min(max(rx0 + 4 * q, 0), Js - 4);
+                        reinterpret_cast<uint32_t *>(mJ)[k] = __ldg(reinterpret_cast<const uint32_t *>(J + (size_t)y * Js + x));
+                    }
+                    reg_valid = true;
+                    __syncwarp();
                 }
+                pJ = mJ + (jy - ry0) * RP + (jx - rx0);
             } else {
+                __syncwarp();
                 for (int k = lane; k < DW * DW; k += 32) {
                     int r = k / DW, i = k - r * DW;
-                    mJ[r * JP + i] = __ldg(J + (size_t)lk_refl101(jy + r, Jh) * Js + lk_refl101(jx + i, Jw));
+                    mJ[r * RP + i] = __ldg(J + (size_t)lk_refl101(jy + r, Jh) * Js + lk_refl101(jx + i, Jw));
                 }
+                reg_valid = false;
+                __syncwarp();
+                pJ = mJ;
             }
-            __syncwarp();
             int pb1 = 0, pb2 = 0;
 #pragma unroll
             for (int q = 0; q < NPL; q++) {
                 int k = lane + 32 * q;
                 if (k < WIN * WIN) {
-                    int y = k / WIN, x = k - y * WIN;
-                    const uint8_t *p = mJ + y * JP + x + joff;
-                    int diff = descale(p[0] * w00 + p[1] * w01 + p[JP] * w10 + p[JP + 1] * w11, W_BITS - 5) - Iv[q];
+                    const uint8_t *p = pJ + offJ[q];
+                    int diff = descale(p[0] * w00 + p[1] * w01 + p[RP] * w10 + p[RP + 1] * w11, W_BITS - 5) - Iv[q];
                     pb1 += diff * Ixv[q]; pb2 += diff * Iyv[q];
                 }
             }
@@ -182,8 +241,14 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
             float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
             nxt_x = __fadd_rn(nx, half); nxt_y = __fadd_rn(ny, half);
-            if ((double)dx * (double)dx + (double)dy * (double)dy <= eps2) break;
-            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+            // OpenCV: delta.ddot(delta) <= eps^2 in double.  A float estimate decides everything except a 1e-4-wide
+            // band around the threshold, where the exact double expression is evaluated (values are warp-uniform).
+            float d2f = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            bool conv = d2f < eps_lo;
+            if (!conv && d2f <= eps_hi) conv = (double)dx * (double)dx + (double)dy * (double)dy <= eps2;
+            if (conv) break;
+            // |(double)(dx + pdx)| < 0.01 for a float argument is exactly |.| <= 0.01f (0.01f < 0.01 < nextafter(0.01f))
+            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
                 nxt_x = __fsub_rn(nxt_x, __fmul_rn(dx, 0.5f)); nxt_y = __fsub_rn(nxt_y, __fmul_rn(dy, 0.5f));
                 break;
             }

@@ -64,8 +64,9 @@ struct svs_ctx {
     long long prof_n[KID_COUNT] = {0};
     int device = 0;
     int sm_count = 0;
-    int zc_ctas = 64;   // persistent grid of the zero-copy (PCIe) ingest kernel; env SVS_ZC_CTAS overrides
+    int zc_ctas = 0;    // persistent grid of the zero-copy (PCIe) ingest kernel: 0 = automatic (svs_i_zc_grid), env SVS_ZC_CTAS overrides
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_in = nullptr;   // ingest stream: prefetch of the NEXT frame pair overlaps this step's compute
     std::string err;
     long long launches = 0;
     // scratch (named by user)
@@ -75,13 +76,29 @@ struct svs_ctx {
 
 struct svs_frameset {
     int B = 0, in_w = 0, in_h = 0, half = 0, W = 0, H = 0, win = 11, nlev = 1;
-    PyrDesc L[2], R;   // L[cur], L[cur^1] = previous
-    int cur = 0;
+    // Triple-buffered left pyramids (previous / current / next) and double-buffered right pyramids (current / next):
+    // "next" is the target of svs_frameset_prefetch_ptrs, filled on the context's ingest stream while the current
+    // step's kernels run; a push rotates the roles.
+    PyrDesc L[3], R[2];
+    int il_prev = 1, il_cur = 0, il_next = 2, ir_cur = 0, ir_next = 1;
+    const PyrDesc &Lcur() const { return L[il_cur]; }
+    const PyrDesc &Lprev() const { return L[il_prev]; }
+    const PyrDesc &Rcur() const { return R[ir_cur]; }
+    void rotate() { int p = il_prev; il_prev = il_cur; il_cur = il_next; il_next = p; int r = ir_cur; ir_cur = ir_next; ir_next = r; }
     long long pushes = 0;
-    DevBuf pyr[3];     // storage of L[0], L[1], R
+    DevBuf pyr[5];     // storage of L[0..2], R[0..1]
     DevBuf staging;    // raw input images when pushed from the host
     DevBuf ptr_table;  // per-stream device pointers (push_ptrs with on_device)
     PinBuf ptr_table_h;
+    // pending prefetch (svs_frameset_prefetch_ptrs)
+    bool pf_pending = false;
+    int pf_mode = 0;
+    size_t pf_row_stride = 0;
+    std::vector<const uint8_t *> pf_ptrs;   // [left.. | right..] as given by the caller
+    cudaEvent_t pf_done = nullptr, pf_order = nullptr;
+    DevBuf pf_staging, pf_ptr_table;
+    PinBuf pf_ptr_table_h;
+    long long prefetch_hits = 0, prefetch_misses = 0;
 };
 
 #define SVS_CUDA(ctx, call)                                                              \
@@ -112,6 +129,7 @@ int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t
 int svs_i_half_nearest(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
                        int n, uint8_t *dst_dev, int dw, int dh, int dst_stride, size_t dst_img_pitch,
                        const uint8_t *const *src_ptrs_dev = nullptr, int ptrs_aligned4 = 0, int rows_decimated = 0);
+int svs_i_zc_grid(const svs_ctx *c);   // CTAs of the zero-copy ingest kernel: ~32 in total over all live contexts
 int svs_i_half_nearest_zc(svs_ctx *c, const uint8_t *const *src_ptrs_dev, int n_per_eye, int w, int h, size_t row_stride,
                           uint8_t *dstL, uint8_t *dstR, int dw, int dh, int dst_stride, size_t dst_img_pitch, int ptrs_aligned4);
 int svs_i_copy_level0(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,

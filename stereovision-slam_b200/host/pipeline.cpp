@@ -60,7 +60,15 @@ public:
     int step(const uint8_t *const *left, const uint8_t *const *right, size_t row_stride, int on_device);
 
     void set_threads(int n) { threads_ = n > 0 ? n : 1; }
+    void hint_next(const uint8_t *const *l, const uint8_t *const *r)
+    {
+        next_left_.assign(l, l + n()); next_right_.assign(r, r + n());
+        has_next_ = true;
+    }
     double t_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // push, track-lk, pose, detect, right-lk, triangulate, ba, host
+    // host bookkeeping by section: begin+prepare track | finish track+prepare pose | finish pose+prepare detect |
+    // finish detect+prepare right | finish right+prepare triangulate | finish triangulate+prepare BA | finish BA+end
+    double t_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long frames = 0, keyframes = 0, ba_problems = 0, ba_iterations = 0, ba_trials = 0, ba_edges = 0, ba_lms = 0, ba_kfs = 0, lk_points = 0, pose_edges = 0;
 
 private:
@@ -72,6 +80,8 @@ private:
     double baseline_ = 0;
     Camera::Ptr cam_left_, cam_right_;
     std::vector<Stream> streams_;
+    std::vector<const uint8_t *> next_left_, next_right_;
+    bool has_next_ = false;
     // gather buffers
     std::vector<int32_t> off_, off2_, off3_, ids_;
     std::vector<float> f0_, f1_, f2_;
@@ -92,6 +102,10 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
     double t0 = now_s(), t1;
     int rc = svs_frameset_push_ptrs(ctx_, fs_, left, right, row_stride, on_device);
     if (rc) return rc;
+    if (has_next_) {   // double buffering: the next pair's PCIe transfer / resize / pyramids overlap this step's kernels
+        has_next_ = false;
+        if ((rc = svs_frameset_prefetch_ptrs(ctx_, fs_, next_left_.data(), next_right_.data(), row_stride, on_device))) return rc;
+    }
     t1 = now_s(); t_phase[0] += t1 - t0; t0 = t1;
 
 #pragma omp parallel for schedule(static) num_threads(threads_)
@@ -129,7 +143,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         }
         return 0;
     };
-    t1 = now_s(); t_phase[7] += t1 - t0; t0 = t1;
+    t1 = now_s(); t_phase[7] += t1 - t0; t_host[0] += t1 - t0; t0 = t1;
     if ((rc = run_lk(0, [](const Stream &s) { return s.ran_track; }))) return rc;
     t1 = now_s(); t_phase[1] += t1 - t0; t0 = t1;
 
@@ -145,7 +159,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         ids_.clear();
         for (int b = 0; b < B; b++) if (streams_[b].ran_track) ids_.push_back(b);
         int np = (int)ids_.size();
-        t1 = now_s(); t_phase[7] += t1 - t0; t0 = t1;
+        t1 = now_s(); t_phase[7] += t1 - t0; t_host[1] += t1 - t0; t0 = t1;
         if (np > 0) {
             off_.assign(np + 1, 0);
             for (int k = 0; k < np; k++) off_[k + 1] = off_[k] + (int)streams_[ids_[k]].pose.feat_index.size();
@@ -185,7 +199,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         ids_.clear();
         for (int b = 0; b < B; b++) if (streams_[b].ran_detect) ids_.push_back(b);
         int ns = (int)ids_.size();
-        t1 = now_s(); t_phase[7] += t1 - t0; t0 = t1;
+        t1 = now_s(); t_phase[7] += t1 - t0; t_host[2] += t1 - t0; t0 = t1;
         if (ns > 0) {
             const int mc = cfg_.num_features;
             off_.assign(ns + 1, 0);
@@ -215,7 +229,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         s.frontend->finish_DetectFeatures(s.det);
         s.frontend->prepare_FindFeaturesInRight(s.lk);
     }
-    t1 = now_s(); t_phase[7] += t1 - t0; t0 = t1;
+    t1 = now_s(); t_phase[7] += t1 - t0; t_host[3] += t1 - t0; t0 = t1;
     if ((rc = run_lk(1, [](const Stream &s) { return s.ran_detect; }))) return rc;
     t1 = now_s(); t_phase[4] += t1 - t0; t0 = t1;
     // ---------------- triangulation of new landmarks (src/frontend.cpp:174, :286)
@@ -230,7 +244,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         off_.assign(B + 1, 0);
         for (int b = 0; b < B; b++) off_[b + 1] = off_[b] + (streams_[b].ran_detect ? (int)streams_[b].tri.feat_index.size() : 0);
         int tot = off_[B];
-        t1 = now_s(); t_phase[7] += t1 - t0; t0 = t1;
+        t1 = now_s(); t_phase[7] += t1 - t0; t_host[4] += t1 - t0; t0 = t1;
         if (tot > 0) {
             f0_.resize((size_t)2 * tot); f1_.resize((size_t)2 * tot); d0_.resize((size_t)3 * tot); u0_.resize(tot);
             for (int b = 0; b < B; b++) {
@@ -264,7 +278,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         ids_.clear();
         for (int b = 0; b < B; b++) if (streams_[b].ran_backend) ids_.push_back(b);
         int np = (int)ids_.size();
-        t1 = now_s(); t_phase[7] += t1 - t0; t0 = t1;
+        t1 = now_s(); t_phase[7] += t1 - t0; t_host[5] += t1 - t0; t0 = t1;
         if (np > 0) {
             off_.assign(np + 1, 0); off2_.assign(np + 1, 0); off3_.assign(np + 1, 0);
             for (int k = 0; k < np; k++) {
@@ -314,7 +328,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
     }
     keyframes += nkf;
     frames += B;
-    t1 = now_s(); t_phase[7] += t1 - t0;
+    t1 = now_s(); t_phase[7] += t1 - t0; t_host[6] += t1 - t0;
     return 0;
 }
 
@@ -444,6 +458,20 @@ int svs_slam_get_counters(svs_slam *s, double *phase_seconds /* 8 */, long long 
         counters[3] = b.ba_iterations; counters[4] = b.ba_trials; counters[5] = b.ba_edges;
         counters[6] = b.ba_lms; counters[7] = b.ba_kfs; counters[8] = b.lk_points; counters[9] = b.pose_edges;
     }
+    return SVS_OK;
+}
+
+int svs_slam_hint_next(svs_slam *s, const uint8_t *const *next_left, const uint8_t *const *next_right)
+{
+    if (!s || !next_left || !next_right) return SVS_ERR_ARG;
+    s->batch->hint_next(next_left, next_right);
+    return SVS_OK;
+}
+
+int svs_slam_get_host_seconds(svs_slam *s, double *host_seconds /* 8 */)
+{
+    if (!s || !host_seconds) return SVS_ERR_ARG;
+    memcpy(host_seconds, s->batch->t_host, sizeof(s->batch->t_host));
     return SVS_OK;
 }
 

@@ -83,10 +83,10 @@ void MapPoint::RemoveObservation(const Observation &o)
 
 MapPoint *Map::CreateNewMappoint()
 {
-    std::unique_ptr<MapPoint> mp(new MapPoint());
-    mp->id_ = landmarks_store_.size();
-    landmarks_store_.push_back(std::move(mp));
-    return landmarks_store_.back().get();
+    if (n_points_ % kChunk == 0) chunks_.emplace_back(new MapPoint[kChunk]);
+    MapPoint *mp = GetMapPoint((long)n_points_);
+    mp->id_ = n_points_++;
+    return mp;
 }
 void Map::InsertMapPoint(MapPoint *mp) { landmarks_[mp->id_] = mp; active_landmarks_[mp->id_] = mp; }
 
@@ -142,6 +142,7 @@ Frame::Ptr Frontend::CreateFrame()
 {
     Frame::Ptr f = std::make_shared<Frame>();
     f->id_ = frame_factory_id_++;
+    f->feature_left_.reserve(256);      // tracked + newly detected features of one frame: one allocation
     return f;
 }
 
@@ -167,7 +168,10 @@ void Frontend::begin_AddFrame(Frame::Ptr frame, int img_w, int img_h)
 void Frontend::prepare_TrackLastFrame(LkRequest &rq)
 {
     rq.prev_xy.clear(); rq.next_xy.clear();
-    for (Feature &f : last_frame_->feature_left_) {
+    const std::vector<Feature> &lf = last_frame_->feature_left_;
+    for (size_t i = 0; i < lf.size(); i++) {
+        const Feature &f = lf[i];
+        if (i + 8 < lf.size()) map_->PrefetchMapPoint(lf[i + 8].map_point_);
         rq.prev_xy.push_back(f.x); rq.prev_xy.push_back(f.y);
         if (MapPoint *mp = map_->GetMapPoint(f.map_point_)) {
             Vec2 px = camera_left_->world2pixel(mp->pos_, current_frame_->Pose());
@@ -204,6 +208,7 @@ void Frontend::prepare_EstimateCurrentPose(PoseRequest &rq)
     for (int i = 0; i < 7; i++) rq.T0[i] = T.d[i];
     for (size_t i = 0; i < current_frame_->feature_left_.size(); i++) {
         Feature &f = current_frame_->feature_left_[i];
+        if (i + 8 < current_frame_->feature_left_.size()) map_->PrefetchMapPoint(current_frame_->feature_left_[i + 8].map_point_);
         if (MapPoint *mp = map_->GetMapPoint(f.map_point_)) {
             rq.feat_index.push_back((int)i);
             rq.pts_w.push_back(mp->pos_.x); rq.pts_w.push_back(mp->pos_.y); rq.pts_w.push_back(mp->pos_.z);
@@ -274,7 +279,10 @@ int Frontend::finish_DetectFeatures(const DetectRequest &rq)
 void Frontend::prepare_FindFeaturesInRight(LkRequest &rq)
 {
     rq.prev_xy.clear(); rq.next_xy.clear();
-    for (Feature &f : current_frame_->feature_left_) {
+    const std::vector<Feature> &cf = current_frame_->feature_left_;
+    for (size_t i = 0; i < cf.size(); i++) {
+        const Feature &f = cf[i];
+        if (i + 8 < cf.size()) map_->PrefetchMapPoint(cf[i + 8].map_point_);
         rq.prev_xy.push_back(f.x); rq.prev_xy.push_back(f.y);
         if (MapPoint *mp = map_->GetMapPoint(f.map_point_)) {
             Vec2 px = camera_right_->world2pixel(mp->pos_, current_frame_->Pose());
@@ -364,7 +372,8 @@ void Frontend::end_AddFrame()
 // ------------------------------------------------------------------ Backend
 bool Backend::prepare_Optimize(BaRequest &rq)
 {
-    rq = BaRequest();
+    rq.poses.clear(); rq.lms.clear(); rq.edge_uv.clear(); rq.chi2.clear(); rq.edge_kf.clear(); rq.edge_lm.clear();
+    rq.edge_cam.clear(); rq.kf_ids.clear(); rq.lm_ids.clear(); rq.edge_obs.clear();     // keep the capacity of the last window
     const Map::KeyframesType &keyframes = map_->GetActiveKeyFrames();
     const Map::LandmarksType &landmarks = map_->GetActiveMapPoints();
     std::map<unsigned long, int> vertices;

@@ -128,14 +128,20 @@ public:
     void InsertKeyFrame(Frame::Ptr frame);            // map.cpp:53-67
     MapPoint *CreateNewMappoint();                    // mappoint.cpp:88-97 (id factory is per map = per stream)
     void InsertMapPoint(MapPoint *mp);                // map.cpp:69-74
-    MapPoint *GetMapPoint(long id) { return id >= 0 ? landmarks_store_[(size_t)id].get() : nullptr; }
+    // Landmarks live in fixed chunks (stable addresses, creation order = memory order): features tracked from the same
+    // keyframe have neighbouring ids, so the per-feature lookups of a frame walk a few cache lines instead of chasing one
+    // heap pointer per landmark.
+    MapPoint *GetMapPoint(long id) { return id >= 0 ? &chunks_[(size_t)id / kChunk][(size_t)id % kChunk] : nullptr; }
+    void PrefetchMapPoint(long id) const { if (id >= 0) __builtin_prefetch(&chunks_[(size_t)id / kChunk][(size_t)id % kChunk]); }
     const LandmarksType &GetAllMapPoints() const { return landmarks_; }
     const KeyframesType &GetAllKeyFrames() const { return keyframes_; }
     const LandmarksType &GetActiveMapPoints() const { return active_landmarks_; }
     const KeyframesType &GetActiveKeyFrames() const { return active_keyframes_; }
 private:
     void RemoveOldKeyframe();                         // map.cpp:76-181
-    std::vector<std::unique_ptr<MapPoint>> landmarks_store_;
+    static constexpr size_t kChunk = 256;
+    std::vector<std::unique_ptr<MapPoint[]>> chunks_;
+    size_t n_points_ = 0;
     LandmarksType landmarks_, active_landmarks_;
     KeyframesType keyframes_, active_keyframes_;
     Frame::Ptr current_frame_;

@@ -111,6 +111,14 @@ class FrameSet:
         self.ctx._chk(self.ctx.lib.svs_frameset_push_ptrs(
             C.c_void_p(self.ctx.h), C.c_void_p(self.h), lp, rp, C.c_size_t(row_stride or self.in_w), int(on_device)))
 
+    def prefetch_ptrs(self, left_ptrs, right_ptrs, on_device, row_stride=None):
+        """Start the ingest of the NEXT pair on the ingest stream (svs_frameset_prefetch_ptrs)."""
+        n = self.n_streams
+        lp = (C.c_void_p * n)(*[int(x) for x in left_ptrs])
+        rp = (C.c_void_p * n)(*[int(x) for x in right_ptrs])
+        self.ctx._chk(self.ctx.lib.svs_frameset_prefetch_ptrs(
+            C.c_void_p(self.ctx.h), C.c_void_p(self.h), lp, rp, C.c_size_t(row_stride or self.in_w), int(on_device)))
+
     def download(self, stream, which, level):
         w, h = self.w, self.hgt
         for _ in range(level):
@@ -364,8 +372,13 @@ class Slam:
         self.is_kf = np.zeros(n_streams, np.int32)
         self.inliers = np.zeros(n_streams, np.int32)
 
-    def add_frames_ptrs(self, left_ptrs, right_ptrs, on_device=False, row_stride=None):
-        """left_ptrs/right_ptrs: one address per stream (host pinned or device memory)."""
+    def add_frames_ptrs(self, left_ptrs, right_ptrs, on_device=False, row_stride=None, next_left_ptrs=None, next_right_ptrs=None):
+        """left_ptrs/right_ptrs: one address per stream (host pinned or device memory).  next_*: the frames of the
+        FOLLOWING call (svs_slam_hint_next): their ingest overlaps this step's kernels."""
+        if next_left_ptrs is not None:
+            nl = (C.c_void_p * self.n)(*[int(x) for x in next_left_ptrs])
+            nr = (C.c_void_p * self.n)(*[int(x) for x in next_right_ptrs])
+            self.ctx._chk(self.ctx.lib.svs_slam_hint_next(C.c_void_p(self.h), nl, nr))
         for i in range(self.n):
             self._lp[i] = int(left_ptrs[i])
             self._rp[i] = int(right_ptrs[i])
@@ -407,7 +420,13 @@ class Slam:
         self.ctx._chk(self.ctx.lib.svs_slam_get_counters(C.c_void_p(self.h), _p(ph), _p(cn)))
         names = ("push", "track_lk", "pose_lm", "detect", "right_lk", "triangulate", "ba", "host")
         cnames = ("frames", "keyframes", "ba_problems", "ba_iterations", "ba_trials", "ba_edges", "ba_lms", "ba_kfs", "lk_points", "pose_edges")
-        return dict(zip(names, ph.tolist())), dict(zip(cnames, cn.tolist()))
+        phases = dict(zip(names, ph.tolist()))
+        hs = np.zeros(8)
+        self.ctx._chk(self.ctx.lib.svs_slam_get_host_seconds(C.c_void_p(self.h), _p(hs)))
+        hnames = ("host:begin+prep_track", "host:fin_track+prep_pose", "host:fin_pose+prep_detect", "host:fin_detect+prep_right",
+                  "host:fin_right+prep_tri", "host:fin_tri+prep_ba", "host:fin_ba+end")
+        phases.update(dict(zip(hnames, hs.tolist())))
+        return phases, dict(zip(cnames, cn.tolist()))
 
     def set_threads(self, n):
         self.ctx._chk(self.ctx.lib.svs_slam_set_threads(C.c_void_p(self.h), int(n)))

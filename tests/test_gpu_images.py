@@ -129,6 +129,46 @@ def test_frameset_ingest_modes(ctx, H, W, pad, mode):
     del t
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_frameset_prefetch(ctx, mode):
+    """svs_frameset_prefetch_ptrs (double-buffered ingest on the second stream): a push of the prefetched pointers only
+    rotates buffers; a push of other pointers discards the prefetch.  Current / previous / right buffers always hold what
+    a plain sequence of pushes would give."""
+    import torch
+    B, H, W, T = 3, 370, 1226, 5
+    buf = np.stack([np.stack([np.stack([texture(H, W, 1000 * e + 10 * t + b) for b in range(B)]) for t in range(T)]) for e in range(2)])
+    t_ = torch.from_numpy(buf)
+    t_ = t_.cuda() if mode == 1 else (t_.pin_memory() if mode == 2 else t_)
+    base = t_.data_ptr()
+    ptr = lambda e, t: [base + ((e * T + t) * B + b) * H * W for b in range(B)]
+    want = lambda e, t, b, lvl: o.build_pyramid(o.half_nearest(buf[e, t, b]))[lvl]
+    fs = ctx.frameset(B, W, H, half=True)
+    try:
+        fs.push_ptrs(ptr(0, 0), ptr(1, 0), mode)
+        fs.prefetch_ptrs(ptr(0, 1), ptr(1, 1), mode)
+        assert np.array_equal(fs.download(1, 0, 1), want(0, 0, 1, 1))       # current is still frame 0 while 1 is in flight
+        fs.push_ptrs(ptr(0, 1), ptr(1, 1), mode)                            # hit
+        fs.prefetch_ptrs(ptr(0, 2), ptr(1, 2), mode)
+        for b in range(B):
+            for lvl in range(fs.n_levels):
+                assert np.array_equal(fs.download(b, 0, lvl), want(0, 1, b, lvl))
+                assert np.array_equal(fs.download(b, 1, lvl), want(0, 0, b, lvl))
+                assert np.array_equal(fs.download(b, 2, lvl), want(1, 1, b, lvl))
+        fs.push_ptrs(ptr(0, 3), ptr(1, 3), mode)                            # miss: prefetch of frame 2 is discarded
+        assert np.array_equal(fs.download(2, 0, 0), want(0, 3, 2, 0))
+        assert np.array_equal(fs.download(2, 1, 2), want(0, 1, 2, 2))
+        assert np.array_equal(fs.download(2, 2, 3), want(1, 3, 2, 3))
+        fs.prefetch_ptrs(ptr(0, 4), ptr(1, 4), mode)
+        fs.prefetch_ptrs(ptr(0, 2), ptr(1, 2), mode)                        # re-issued before being consumed
+        fs.push_ptrs(ptr(0, 2), ptr(1, 2), mode)
+        assert np.array_equal(fs.download(0, 0, 1), want(0, 2, 0, 1))
+        assert np.array_equal(fs.download(0, 1, 1), want(0, 3, 0, 1))
+        assert np.array_equal(fs.download(0, 2, 0), want(1, 2, 0, 0))
+    finally:
+        fs.close()
+    del t_
+
+
 @pytest.mark.parametrize("h,w,seed", [(188, 620, 1), (185, 613, 2), (376, 1241, 3), (30, 40, 4)])
 def test_lk_bit_identical_to_oracle(ctx, h, w, seed):
     a, b = moved_pair(h, w, seed)
