@@ -298,6 +298,25 @@ def run_gpu(args, rank, world, local_rank):
         idx = [pingpong(starts[b] + step, nclip) for b in range(goff[g], goff[g + 1])]
         return [base_l + j * img_bytes for j in idx], [base_r + j * img_bytes for j in idx]
 
+    # ctypes pointer arrays per (memory, group, clip phase), built once: the per-step Python work of the 16 driver threads
+    # would otherwise serialise on the interpreter lock (measured: ~6 ms of a 30 ms step)
+    period = 2 * nclip - 2
+    ptr_cache = {}
+
+    def ptr_arrays(on_device, step, g):
+        key = (bool(on_device), g, step % period)
+        v = ptr_cache.get(key)
+        if v is None:
+            bl, br = (Ld.data_ptr(), Rd.data_ptr()) if on_device else (Lh.data_ptr(), Rh.data_ptr())
+            lp, rp = ptrs(bl, br, step, g)
+            v = ptr_cache[key] = (svslam.Slam.ptr_array(lp), svslam.Slam.ptr_array(rp))
+        return v
+
+    for on_dev in (True, False):
+        for g in range(G):
+            for ph in range(period):
+                ptr_arrays(on_dev, ph, g)
+
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -310,8 +329,12 @@ def run_gpu(args, rank, world, local_rank):
     for s in slams:
         s.set_threads(host_threads)
     cursor = [0]
+    # Independent streams do not insert keyframes in phase; the synthetic streams would (same age, same speed), which
+    # makes the BA load arrive in bursts of one step in ~40.  Group g therefore runs gstag[g] extra untimed steps first,
+    # spreading the groups' keyframe phases over one keyframe period.
+    gstag = [(g * args.stagger) // G for g in range(G)]
 
-    def run_steps(n, on_device):
+    def run_steps(n, on_device, stagger=False):
         bl, br = (Ld.data_ptr(), Rd.data_ptr()) if on_device else (Lh.data_ptr(), Rh.data_ptr())
         # e2e ingest: 2 = zero-copy kernel reads of the pinned host frames, 0 = staged strided DMA copies,
         # 3 = mixed (even groups zero-copy, odd groups DMA) so SM-initiated reads and the copy engines share PCIe
@@ -324,14 +347,17 @@ def run_gpu(args, rank, world, local_rank):
 
         def loop(g):
             try:
-                nxt = ptrs(bl, br, lo, g)
-                for s in range(lo, lo + n):
+                first = lo + (0 if stagger else gstag[g])
+                last = lo + gstag[g] + n
+                nxt = ptr_arrays(on_device, first, g)
+                mode = mode_of(g)
+                for s in range(first, last):
                     lp, rp = nxt
-                    nxt = ptrs(bl, br, s + 1, g)
+                    nxt = ptr_arrays(on_device, s + 1, g)
                     if args.no_prefetch:
-                        slams[g].add_frames_ptrs(lp, rp, on_device=mode_of(g))
+                        slams[g].add_frames_arrays(lp, rp, mode)
                     else:   # double-buffered ingest: frame s+1 crosses PCIe / is resized while frame s is tracked
-                        slams[g].add_frames_ptrs(lp, rp, on_device=mode_of(g), next_left_ptrs=nxt[0], next_right_ptrs=nxt[1])
+                        slams[g].add_frames_arrays(lp, rp, mode, nxt[0], nxt[1])
             except Exception as e:      # surface worker failures in the main thread
                 errors.append(e)
 
@@ -392,8 +418,8 @@ def run_gpu(args, rank, world, local_rank):
     # priming (untimed, before any warm-up): run until the sliding BA window of every stream is full so that the timed
     # steps see steady-state problem sizes (10 keyframes); timing a cold pipeline would overstate.  The priming steps
     # also grow every grow-only device / pinned buffer to its steady-state size (regrowing is a device-wide sync).
-    run_steps(args.priming, True)
-    log("primed %d steps" % args.priming)
+    run_steps(args.priming, True, stagger=True)
+    log("primed %d steps (+ up to %d per group to stagger the keyframe phases)" % (args.priming, max(gstag)))
     if args.profile_window:   # profiling aid (never a bench number): one device-resident region inside a profiler window
         timed_region(True, False, profile_window=True)
         log("profile window done")
@@ -490,7 +516,7 @@ def run_gpu(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "streams_per_gpu": B, "context_groups": G, "frames_per_step": B * world, "num_features": 150,
                    "num_active_keyframes": 10, "ba": "synchronous, analytic Jacobians",
                    "ingest": "per-step push" if args.no_prefetch else "double-buffered: frame t+1 is ingested on a second stream during step t", "clip_frames": nclip,
-                   "priming_steps": args.priming,
+                   "priming_steps": args.priming, "group_stagger_steps": args.stagger,
                    "l2": "per-step input %.0f MB per GPU > 126 MB L2 (inputs larger than L2)" % (in_bytes / 1e6)
                    if in_bytes > 126e6 else "per-step input %.0f MB per GPU (< L2; distinct frames every step)" % (in_bytes / 1e6)},
         "clocks": clocks,
@@ -518,7 +544,9 @@ def run_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60,
+                    help="timed steps per region (the 16 context groups run unsynchronised and a region ends with the slowest "
+                         "group, so short regions measure the luckiest / unluckiest keyframe phase rather than the mean)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=int(os.environ.get("SVS_BENCH_STREAMS", "4096")))
@@ -528,6 +556,8 @@ def main():
                     help="e2e transfer of the pinned host frames: 2 zero-copy kernel reads over PCIe, 0 staged DMA copies")
     ap.add_argument("--clip-frames", type=int, default=48)
     ap.add_argument("--priming", type=int, default=150, help="untimed steps before warm-up so the BA window is full")
+    ap.add_argument("--stagger", type=int, default=40,
+                    help="spread the context groups' stream ages over this many steps (about one keyframe period); 0 = all in phase")
     ap.add_argument("--no-prefetch", action="store_true", help="disable the double-buffered ingest (svs_slam_hint_next)")
     ap.add_argument("--diag", action="store_true", help="repeat the value / e2e regions a second time (detail.diag)")
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames per stream per process for the CPU baseline sample")

@@ -271,6 +271,16 @@ SVS_API svs_frameset *svs_slam_frameset(svs_slam *s);
  * stepped concurrently from different host threads (their kernels and copies overlap on the device). */
 SVS_API int svs_slam_set_threads(svs_slam *s, int n);
 
+/* ---------------------------------------------------------------- data formats either side of the path (host only)
+ * svs_kitti_read_calib     Dataset::initialize (src/dataset.cpp:24-80): calib.txt -> per camera (fx fy cx cy), translation
+ *                          t = K^-1 P[:,3] and baseline |t|; K is halved when half != 0 (the reference always does, :73).
+ * svs_write_keyframes_txt  / svs_write_landmarks_pcd: the two files of VisualOdometry::saveSLAMOutputInFile
+ *                          (src/visual_odometry.cpp:198-310), from the arrays svs_slam_get_keyframes / _landmarks return. */
+SVS_API int svs_kitti_read_calib(const char *calib_path, int half, double K_out[16], double t_out[12], double baseline_out[4]);
+SVS_API int svs_write_keyframes_txt(const char *path, const char *dataset_dir, int left_cam_index, int n, const int64_t *frame_ids,
+                                    const double *poses /* 7n */);
+SVS_API int svs_write_landmarks_pcd(const char *path, int n, const double *xyz /* 3n */);
+
 #ifdef __cplusplus
 }
 #endif

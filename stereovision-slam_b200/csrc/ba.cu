@@ -175,11 +175,14 @@ k_ba_window(BaArgs A)
 #pragma unroll
                     for (int y = 0; y < 3; y++) H[x * 3 + y] += r1 * (Jl[x] * Jl[y] + Jl[3 + x] * Jl[3 + y]);
                 }
-                double *W = Hpl + 18 * (size_t)e;
+                double Wv[18];
 #pragma unroll
                 for (int x = 0; x < 6; x++)
 #pragma unroll
-                    for (int y = 0; y < 3; y++) W[x * 3 + y] = r1 * (Jp[x] * Jl[y] + Jp[6 + x] * Jl[3 + y]);
+                    for (int y = 0; y < 3; y++) Wv[x * 3 + y] = r1 * (Jp[x] * Jl[y] + Jp[6 + x] * Jl[3 + y]);
+                double2 *W = reinterpret_cast<double2 *>(Hpl + 18 * (size_t)e);
+#pragma unroll
+                for (int x = 0; x < 9; x++) W[x] = make_double2(Wv[2 * x], Wv[2 * x + 1]);
             }
 #pragma unroll
             for (int x = 0; x < 9; x++) Hll[9 * (size_t)l + x] = H[x];
@@ -285,11 +288,24 @@ k_ba_window(BaArgs A)
                 for (int t = tid; t < 4 * P.nch; t += BA_T) {
                     int ch = t >> 2, qr = (t >> 1) & 1, qc = t & 1;
                     double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
-                    int p1 = ch_off[ch + 1];
-                    for (int p = ch_off[ch]; p < p1; p++) {
-                        const double *X = WD + 18 * (size_t)pr_e1[p] + 9 * qr, *Y = Hpl + 18 * (size_t)pr_e2[p] + 9 * qc;
-                        double x0 = X[0], x1 = X[1], x2 = X[2], x3 = X[3], x4 = X[4], x5 = X[5], x6 = X[6], x7 = X[7], x8 = X[8];
-                        double y0 = Y[0], y1 = Y[1], y2 = Y[2], y3 = Y[3], y4 = Y[4], y5 = Y[5], y6 = Y[6], y7 = Y[7], y8 = Y[8];
+                    // software pipeline: the indices of pair p+2 and the 2 x 9 operands of pair p+1 are in flight while pair p
+                    // is accumulated (every load is an L2 round trip; the chain index -> operand -> FMA is what costs)
+                    const int p0 = ch_off[ch], p1 = ch_off[ch + 1];
+                    int e1n = pr_e1[p0], e2n = pr_e2[p0];
+                    const double *X = WD + 18 * (size_t)e1n + 9 * qr, *Y = Hpl + 18 * (size_t)e2n + 9 * qc;
+                    double xn[9], yn[9];
+#pragma unroll
+                    for (int u = 0; u < 9; u++) { xn[u] = X[u]; yn[u] = Y[u]; }
+                    if (p0 + 1 < p1) { e1n = pr_e1[p0 + 1]; e2n = pr_e2[p0 + 1]; }
+                    for (int p = p0; p < p1; p++) {
+                        double x0 = xn[0], x1 = xn[1], x2 = xn[2], x3 = xn[3], x4 = xn[4], x5 = xn[5], x6 = xn[6], x7 = xn[7], x8 = xn[8];
+                        double y0 = yn[0], y1 = yn[1], y2 = yn[2], y3 = yn[3], y4 = yn[4], y5 = yn[5], y6 = yn[6], y7 = yn[7], y8 = yn[8];
+                        if (p + 1 < p1) {
+                            X = WD + 18 * (size_t)e1n + 9 * qr; Y = Hpl + 18 * (size_t)e2n + 9 * qc;
+#pragma unroll
+                            for (int u = 0; u < 9; u++) { xn[u] = X[u]; yn[u] = Y[u]; }
+                            if (p + 2 < p1) { e1n = pr_e1[p + 2]; e2n = pr_e2[p + 2]; }
+                        }
                         a00 += x0 * y0 + x1 * y1 + x2 * y2; a01 += x0 * y3 + x1 * y4 + x2 * y5; a02 += x0 * y6 + x1 * y7 + x2 * y8;
                         a10 += x3 * y0 + x4 * y1 + x5 * y2; a11 += x3 * y3 + x4 * y4 + x5 * y5; a12 += x3 * y6 + x4 * y7 + x5 * y8;
                         a20 += x6 * y0 + x7 * y1 + x8 * y2; a21 += x6 * y3 + x7 * y4 + x8 * y5; a22 += x6 * y6 + x7 * y7 + x8 * y8;
@@ -331,7 +347,7 @@ k_ba_window(BaArgs A)
             }
             __syncthreads();
             bool ok = s_flag != 0;
-            if (ok) ok = block_ldlt_solve(S, pitch, np, g, xp, tr, tmp, &s_piv);
+            if (ok) ok = (np <= 128) ? warp_ldlt_solve(S, pitch, np, g, xp, tr, tmp, &s_piv) : block_ldlt_solve(S, pitch, np, g, xp, tr, tmp, &s_piv);
             st_sol++;
             if (!ok) { for (int i = tid; i < np; i += BA_T) xp[i] = 0.0; __syncthreads(); }
             // ---- back-substitution, trial state, scale term

@@ -371,6 +371,7 @@ class Slam:
         self.status = np.zeros(n_streams, np.int32)
         self.is_kf = np.zeros(n_streams, np.int32)
         self.inliers = np.zeros(n_streams, np.int32)
+        self._pp, self._ps, self._pk, self._pi = _p(self.poses), _p(self.status), _p(self.is_kf), _p(self.inliers)
 
     def add_frames_ptrs(self, left_ptrs, right_ptrs, on_device=False, row_stride=None, next_left_ptrs=None, next_right_ptrs=None):
         """left_ptrs/right_ptrs: one address per stream (host pinned or device memory).  next_*: the frames of the
@@ -385,6 +386,21 @@ class Slam:
         rc = self.ctx.lib.svs_slam_add_frames(C.c_void_p(self.h), self._lp, self._rp, C.c_size_t(row_stride or self.in_w),
                                               int(on_device), _p(self.poses), _p(self.status), _p(self.is_kf), _p(self.inliers))
         self.ctx._chk(rc)
+        return self.poses
+
+    @staticmethod
+    def ptr_array(ptrs):
+        """A reusable ctypes pointer array for add_frames_arrays (build once, pass every step)."""
+        return (C.c_void_p * len(ptrs))(*[int(x) for x in ptrs])
+
+    def add_frames_arrays(self, lp, rp, on_device, next_lp=None, next_rp=None, row_stride=None):
+        """add_frames_ptrs with prebuilt ctypes arrays (Slam.ptr_array): no per-step Python work, so many pipelines can be
+        stepped from Python threads without serialising on the interpreter lock."""
+        lib, h = self.ctx.lib, C.c_void_p(self.h)
+        if next_lp is not None:
+            self.ctx._chk(lib.svs_slam_hint_next(h, next_lp, next_rp))
+        self.ctx._chk(lib.svs_slam_add_frames(h, lp, rp, C.c_size_t(row_stride or self.in_w), int(on_device), self._pp, self._ps,
+                                              self._pk, self._pi))
         return self.poses
 
     def add_frames(self, left, right):

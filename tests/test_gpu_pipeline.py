@@ -126,3 +126,55 @@ def test_pipeline_free_running_accuracy(ctx, granule, clip):
         assert abs(nk - wnk) <= 1 and slam.status[0] == 1
     finally:
         slam.close()
+
+
+def test_prefetch_hint_gives_identical_results(ctx, granule, clip):
+    """svs_slam_hint_next (double-buffered ingest on the second stream) must not change a single bit of the results:
+    two pipelines over the same pinned frames, one with hints, one without."""
+    import torch
+    cor, L, R, T = clip
+    n = 14
+    Lt, Rt = torch.from_numpy(L[:n + 1].copy()).pin_memory(), torch.from_numpy(R[:n + 1].copy()).pin_memory()
+    img = cor.W * cor.H
+    a = ctx.slam(2, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, oracle_simd_granule=granule)
+    b = ctx.slam(2, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, oracle_simd_granule=granule)
+    try:
+        for i in range(n):
+            # stream 1 lags one frame behind stream 0; mode alternates between zero-copy (2) and staged DMA (0)
+            mode = 2 if (i // 4) % 2 == 0 else 0
+            lp = [Lt.data_ptr() + i * img, Lt.data_ptr() + max(i - 1, 0) * img]
+            rp = [Rt.data_ptr() + i * img, Rt.data_ptr() + max(i - 1, 0) * img]
+            nl = [Lt.data_ptr() + (i + 1) * img, Lt.data_ptr() + i * img]
+            nr = [Rt.data_ptr() + (i + 1) * img, Rt.data_ptr() + i * img]
+            pa = a.add_frames_ptrs(lp, rp, on_device=mode, next_left_ptrs=nl, next_right_ptrs=nr).copy()
+            pb = b.add_frames_ptrs(lp, rp, on_device=mode).copy()
+            assert np.array_equal(pa, pb), i
+            assert np.array_equal(a.status, b.status) and np.array_equal(a.is_kf, b.is_kf) and np.array_equal(a.inliers, b.inliers)
+        for s in range(2):
+            assert np.array_equal(a.features(s)[0], b.features(s)[0])
+            assert np.array_equal(a.landmarks(s)[1], b.landmarks(s)[1])
+    finally:
+        a.close(); b.close()
+
+
+def test_save_slam_output(ctx, granule, clip, tmp_path):
+    """keyframes.txt / landmarks.pcd (reference src/visual_odometry.cpp:198-310) written from a finished run."""
+    from svslam import kitti
+    cor, L, R, T = clip
+    slam = ctx.slam(1, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, oracle_simd_granule=granule)
+    try:
+        est = [slam.add_frames(L[i:i + 1], R[i:i + 1])[0].copy() for i in range(20)]
+        nk, nl = kitti.save_slam_output(slam, 0, str(tmp_path), "/data/sequences/05", 0)
+        kid, fid, kposes = slam.keyframes(0)
+        lines = open(str(tmp_path / "keyframes.txt")).read().splitlines()
+        assert nk == len(kid) >= 2 and len(lines) == 2 + nk and [int(l.split()[0]) for l in lines[2:]] == list(fid)
+        Tcw = np.array([[float(v) for v in l.split()[1:]] for l in lines[2:]]).reshape(-1, 3, 4)
+        assert np.allclose(Tcw[:, :, 3], kposes[:, 4:], rtol=1e-5, atol=1e-5)
+        pcd = open(str(tmp_path / "landmarks.pcd")).read().splitlines()
+        assert pcd[6] == "WIDTH %d" % nl and len(pcd) == 11 + nl and nl == len(slam.landmarks(0)[0])
+        c, _ = kitti.pose7_to_Twc(np.array(est))
+        gt_c, _ = kitti.pose7_to_Twc(np.asarray(T)[:20])
+        ate = kitti.ate_rmse(c, gt_c)
+        assert ate < 0.10 and abs(ate - synth.ate_rmse(est, T[:20])) < 1e-9
+    finally:
+        slam.close()
