@@ -147,9 +147,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def _cpu_worker(args):
-    """One independent stream on one host core: the reference's CPU path on `n` frames starting at `start`."""
-    start, n, clip_path, backend_on = args
+def _cpu_stream_proc(idx, clip_path, prime, conn):
+    """One independent stream on one host core: the reference's CPU path (persistent: the pipeline is primed once so
+    that its BA window is full, like the GPU arm's streams, then it runs `n` more frames per request)."""
     import cv2
     cv2.setNumThreads(1)
     from oracle import pipeline as op
@@ -158,34 +158,58 @@ def _cpu_worker(args):
     L, R = d["L"], d["R"]
     cal = synth.CALIB[CALIB]
     K = np.array([cal[2] * 0.5, cal[2] * 0.5, cal[3] * 0.5, cal[4] * 0.5])
-    p = op.Pipeline(K, cal[5], op.Cfg(backend_on=backend_on), stages="cv2", cv2=cv2)
+    p = op.Pipeline(K, cal[5], op.Cfg(backend_on=1), stages="cv2", cv2=cv2)
     nclip = len(L)
-    t0 = time.perf_counter()
-    kfs = 0
-    for i in range(n):
-        j = pingpong(start + i, nclip)
+    cur = (7 * idx) % 24
+    for _ in range(prime):
+        j = pingpong(cur, nclip); cur += 1
         p.add_frame(L[j], R[j])
-        kfs += int(p.is_kf)
-    return time.perf_counter() - t0, n, kfs, p.status
+    conn.send(("ready", len(p.active_kfs)))
+    while True:
+        n = conn.recv()
+        if n <= 0:
+            break
+        t0 = time.perf_counter()
+        kfs = 0
+        for _ in range(n):
+            j = pingpong(cur, nclip); cur += 1
+            p.add_frame(L[j], R[j])
+            kfs += int(p.is_kf)
+        conn.send((time.perf_counter() - t0, n, kfs, p.status))
 
 
-def cpu_reference_run(clip_path, frames_per_stream, n_procs, starts=None):
-    """Aggregate frames/s of n_procs independent CPU streams (one process per core)."""
-    import multiprocessing as mp
-    from oracle import geom
-    geom.build()
-    starts = starts or [(7 * i) % 24 for i in range(n_procs)]
-    jobs = [(starts[i], frames_per_stream, clip_path, 1) for i in range(n_procs)]
-    t0 = time.perf_counter()
-    if n_procs == 1:
-        res = [_cpu_worker(jobs[0])]
-    else:
-        with mp.get_context("spawn").Pool(n_procs) as pool:
-            res = pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t0
-    frames = sum(r[1] for r in res)
-    busy = max(r[0] for r in res)
-    return frames / busy, frames, wall, sum(r[2] for r in res)
+class CpuStreams:
+    """n_procs persistent CPU streams (one process per core)."""
+
+    def __init__(self, clip_path, n_procs, prime):
+        import multiprocessing as mp
+        from oracle import geom
+        geom.build()
+        ctx = mp.get_context("spawn")
+        self.procs, self.conns = [], []
+        for i in range(n_procs):
+            a, b = ctx.Pipe()
+            pr = ctx.Process(target=_cpu_stream_proc, args=(i, clip_path, prime, b), daemon=True)
+            pr.start()
+            self.procs.append(pr); self.conns.append(a)
+        self.window = [c.recv()[1] for c in self.conns]     # wait until every stream is primed
+
+    def step(self, n):
+        """Every stream runs n frames concurrently -> (aggregate frames/s, frames, keyframes)."""
+        for c in self.conns:
+            c.send(n)
+        res = [c.recv() for c in self.conns]
+        frames = sum(r[1] for r in res)
+        return frames / max(r[0] for r in res), frames, sum(r[2] for r in res)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(0)
+            except Exception:
+                pass
+        for pr in self.procs:
+            pr.join(timeout=5)
 
 
 def save_clip(L, R):
@@ -194,31 +218,39 @@ def save_clip(L, R):
     return path
 
 
+CPU_PRIME = 150
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     cor, L, R, T = make_clip(args.clip_frames)
     path = save_clip(L, R)
-    fps_list = []
-    # warm-up + K "steps": each step = every core runs `cpu_frames` frames of an independent stream
+    # each step = every core runs `n` frames of its own (primed, steady-state) stream; n is sized so that the whole
+    # warm-up + K steps run stays within a few minutes whatever K is
+    n = args.cpu_frames if args.cpu_frames > 0 else max(2, min(40, 2400 // (args.warmup + args.steps)))
+    cs = CpuStreams(path, cores, CPU_PRIME)
+    res = []
     for s in range(args.warmup + args.steps):
-        fps, frames, wall, kfs = cpu_reference_run(path, args.cpu_frames, cores, [(7 * i + 3 * s) % 24 for i in range(cores)])
+        r = cs.step(n)
         if s >= args.warmup:
-            fps_list.append((fps, frames, wall))
+            res.append(r)
+    cs.close()
     os.remove(path)
-    frames = sum(f[1] for f in fps_list)
-    busy = sum(f[1] / f[0] for f in fps_list)
+    frames = sum(r[1] for r in res)
+    busy = sum(r[1] / r[0] for r in res)
     value = frames / busy
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * busy / max(1, len(fps_list)), "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * busy / max(1, len(res)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cpu_frames_per_stream_per_step": args.cpu_frames, "processes": cores},
+        "config": {"workload": WORKLOAD, "cpu_frames_per_stream_per_step": n, "processes": cores, "priming_frames": CPU_PRIME,
+                   "active_keyframes_after_priming": int(np.median(cs.window))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d processes x %d frames x %d steps; OpenCV stages through cv2 %s (the library the "
-                                   "reference calls), g2o blocks through oracle/geom.c (g2o is not installable here)" % (
-                                       cores, args.cpu_frames, args.steps, __import__("cv2").__version__)},
+                         "sample": "%d processes x %d frames x %d steps after %d priming frames each (BA window full); OpenCV stages "
+                                   "through cv2 %s (the library the reference calls), g2o blocks through oracle/geom.c (g2o is not "
+                                   "installable here)" % (cores, n, args.steps, CPU_PRIME, __import__("cv2").__version__)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
@@ -482,11 +514,26 @@ def run_gpu(args, rank, world, local_rank):
     if dom and dom in alg_total:
         ms_tot, n_l = kern[dom]
         ach = alg_total[dom] / (ms_tot * 1e-3) / 1e9
-        limiter = {"k_ba_window": "dependent FP64 latency at 2 CTAs/SM (ncu: 12 % issue-active, 9 % FP64 pipe, 0.02 % DRAM)",
-                   "k_pose_only_lm": "dependent FP64 latency, one warp per problem (ncu: 18 % issue-active)",
-                   "k_lk_track": "integer instruction issue (ncu: 79 % issue-active, <1 % DRAM)"}.get(dom, "HBM streaming")
+        limiter = {"k_ba_window": "dependent FP64 + L2 latency, one 512-thread CTA per window (ncu: ~13 % issue-active, ~12 % FP64 pipe, 0.01 % DRAM)",
+                   "k_pose_only_lm": "dependent FP64 latency, one warp per problem (ncu: 22 % issue-active, 20 % FP64 pipe)",
+                   "k_lk_track": "integer instruction issue (ncu: 79 % issue-active, 0.7 % DRAM)"}.get(dom, "HBM streaming")
+        # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/), scaled by the units per launch
+        units = {"k_ba_window": cnt["ba_problems"], "k_lk_track": cnt["lk_points"], "k_pose_only_lm": cnt["frames"]}.get(dom)
+        traffic, traffic_src = None, None
+        try:
+            import csv
+            for row in csv.DictReader(l for l in open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.csv")) if not l.startswith("#")):
+                if row["kernel"].replace("void ", "").split("<")[0] == dom and units:
+                    per_launch = (float(row["dram_rd_MB"]) + float(row["dram_wr_MB"])) * 1e6
+                    grid = float(row["grid"])
+                    per_unit = per_launch / (grid * {"k_ba_window": 1, "k_lk_track": 4, "k_pose_only_lm": 4}[dom])
+                    traffic = per_unit * units / max(1, n_l)
+                    traffic_src = "profiles/r01_ncu_full_summary.csv: %.0f B per %s x %.1f per launch" % (
+                        per_unit, {"k_ba_window": "window", "k_lk_track": "keypoint", "k_pose_only_lm": "problem"}[dom], units / max(1, n_l))
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "avg_launch_ms": ms_tot / max(1, n_l), "launches": n_l,
+                "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": ms_tot / max(1, n_l), "launches": n_l,
                 "algorithmic_bytes_per_launch": alg_total[dom] / max(1, n_l), "peak_source": peak_src,
                 "note": "launch durations overlap across %d context groups; actual limiter: %s (DESIGN.md §4)" % (G, limiter)}
     dev_total = sum(v[0] for v in kern.values())
@@ -560,7 +607,8 @@ def main():
                     help="spread the context groups' stream ages over this many steps (about one keyframe period); 0 = all in phase")
     ap.add_argument("--no-prefetch", action="store_true", help="disable the double-buffered ingest (svs_slam_hint_next)")
     ap.add_argument("--diag", action="store_true", help="repeat the value / e2e regions a second time (detail.diag)")
-    ap.add_argument("--cpu-frames", type=int, default=40, help="frames per stream per process for the CPU baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=0,
+                    help="frames per stream per step of the CPU arms (0 = automatic: 40 for the in-run baseline, sized by K for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba4", action="store_true", help="skip the config-4 sharded-BA detail block")
     ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "none"], help="clock / throttle-reason sampler")
@@ -576,12 +624,18 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.cpu_baseline_clip:
         cores = os.cpu_count() or 1
-        fps, frames, wall, kfs = cpu_reference_run(args.cpu_baseline_clip, args.cpu_frames, cores)
-        fps1, _, _, _ = cpu_reference_run(args.cpu_baseline_clip, args.cpu_frames, 1)
+        n = args.cpu_frames if args.cpu_frames > 0 else 40
+        cs = CpuStreams(args.cpu_baseline_clip, cores, CPU_PRIME)
+        fps, frames, kfs = cs.step(n)
+        cs.close()
+        c1 = CpuStreams(args.cpu_baseline_clip, 1, CPU_PRIME)
+        fps1, _, _ = c1.step(n)
+        c1.close()
         print(json.dumps({"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "single_core_value": fps1,
-                          "sample": "%d processes x %d frames of the same workload (OpenCV stages through cv2 %s = the library "
-                                    "the reference calls, 1 thread each; g2o blocks through oracle/geom.c); one core alone: %.1f frames/s"
-                                    % (cores, args.cpu_frames, __import__("cv2").__version__, fps1)}))
+                          "sample": "%d processes x %d frames of the same workload after %d priming frames each (BA window full: %d "
+                                    "active keyframes); OpenCV stages through cv2 %s = the library the reference calls, 1 thread each; "
+                                    "g2o blocks through oracle/geom.c; one core alone: %.1f frames/s"
+                                    % (cores, n, CPU_PRIME, int(np.median(cs.window)), __import__("cv2").__version__, fps1)}))
         return
     if args.impl == "reference":
         run_reference(args, rank, world)

@@ -5,9 +5,12 @@
 // Solver semantics: SURVEY.md Appendix B (upstream g2o; un-vendored, parity unpinned).
 //
 // k_ba_window: ONE persistent CTA per window problem runs the whole LM loop on-device (no host round trips):
-//   linearise   landmark-parallel: residuals, 2x6 / 2x3 Jacobian blocks, Huber weights -> Hll (3x3), bl, Hpl (6x3/edge)
+//   linearise   landmark-parallel: residuals, 2x6 / 2x3 Jacobian blocks, Huber weights -> Hll (3x3), bl, and the 6x3
+//               pose-landmark block W summed per GROUP = (landmark, keyframe): the left and right observation of a
+//               landmark in one keyframe share the pose, so everything downstream (Schur, g, back-substitution) works
+//               on ~0.6 E groups and ~0.4x the (edge, edge) pairs
 //               pose-parallel (warp per keyframe, butterfly reduction) -> Hpp (6x6), bp
-//   schur       landmark-parallel V^-1 = (Hll + lambda I)^-1, W V^-1 per edge; the (edge, edge) pairs of every 6x6 block
+//   schur       landmark-parallel V^-1 = (Hll + lambda I)^-1, W V^-1 per group; the (group, group) pairs of every 6x6 block
 //               (i,j) of the reduced system are listed by the host, sorted by block and cut into chunks of <= BA_CH
 //               pairs; 4 threads own a chunk (one 3x3 quadrant each) and accumulate (W V^-1)_e1 W_e2^T in registers,
 //               then 36 threads per block add the chunk partials in a fixed order -> no atomics, bitwise
@@ -30,7 +33,10 @@ struct BaProb {
     int loff0;      // l_off[loff0 + l .. ] (L+1 entries), values relative to e0
     int poff0;      // p_off[poff0 + a ..] (NA+1 entries), values relative to e0
     int blk0;       // blk_i/blk_j[blk0 + b]
-    int pair0;      // pr_e1/pr_e2[pair0 + p]: the (edge, edge) pairs of this problem, sorted by block
+    int G, grp0;    // groups = (landmark, active pose) with >= 1 edge, numbered landmark-major / pose-ascending; global offset
+    int lgoff0;     // lg_off[lgoff0 + l ..] (L+1 entries): groups of landmark l
+    int pgoff0;     // pg_off[pgoff0 + a ..] (NA+1 entries) into pg_groups[grp0 + ..]: groups of active pose a
+    int pair0;      // pr_e1/pr_e2[pair0 + p]: the (group, group) pairs of this problem, sorted by block
     int nch, ch0;   // chunks: ch_blk[ch0 + c] = block of chunk c, pairs [ch_off[choff0 + c], ch_off[choff0 + c + 1])
     int choff0;
     int bch0;       // blk_ch[bch0 + b .. ] (nblk+1 entries): chunk range of block b
@@ -47,8 +53,9 @@ struct BaArgs {
     const double *edge_uv;
     const int32_t *l_off, *l_edges, *p_off, *p_edges;
     const int32_t *blk_i, *blk_j, *blk_ch, *pr_e1, *pr_e2, *ch_blk, *ch_off;
+    const int32_t *lg_off, *g_lm, *g_pose, *pg_off, *pg_groups;
     double *part;                   // 36 doubles per chunk
-    double *Hpl, *WD;               // 18 / edge
+    double *Hpl, *WD;               // 18 / group: W and W V^-1
     double *Hll, *Dinv;             // 9 / landmark
     double *bl, *xl, *lmT;          // 3 / landmark
     double *S_glob;
@@ -57,10 +64,20 @@ struct BaArgs {
     double K[2][4], ext[2][7];
     double huber_delta;
     int max_iter, jac_mode;
+    int smem_bytes;                 // dynamic shared memory of this launch
 };
 
 #define BA_T 512    // one CTA per SM: a window problem is latency-bound, so it gets as many threads as 128 registers each allow
-#define BA_CH 16    // (edge, edge) pairs per Schur chunk
+#define BA_CH 16    // (group, group) pairs per Schur chunk
+
+// dynamic shared memory of a window with NA active poses: reductions + poses + Hpp/bp/g/xp/tmp + tr, plus n_S copies of
+// the reduced system (0: it lives in global memory, 1: in-place pivoting LDLT, 2: pre-permuted LDLT)
+__host__ __device__ inline size_t ba_smem_need(int NA, int n_S)
+{
+    size_t np = 6 * (size_t)NA, pitch = np | 1;
+    size_t d = BA_T + 14 * (size_t)NA + 36 * (size_t)NA + 4 * np;
+    return d * 8 + ((np + 1) & ~(size_t)1) * 4 + (size_t)n_S * np * pitch * 8 + 16;
+}
 #include "ba_ldlt.cuh"
 
 __device__ __forceinline__ double block_sum(double v, double *red)
@@ -109,6 +126,8 @@ k_ba_window(BaArgs A)
     int *tr = reinterpret_cast<int *>(tmp + np);   // np ints
     double *Ssm = reinterpret_cast<double *>(tr + ((np + 1) & ~1));
     double *S = (P.S_off >= 0) ? A.S_glob + P.S_off : Ssm;
+    // second buffer for the pre-permuted LDLT when this launch's shared memory has room for it
+    double *S2 = (P.S_off < 0 && ba_smem_need(NA, 2) <= (size_t)A.smem_bytes) ? Ssm + np * pitch : nullptr;
     __shared__ int s_piv, s_flag, s_q;
     __shared__ double s_lambda, s_ni, s_cur, s_rho;
 
@@ -120,7 +139,10 @@ k_ba_window(BaArgs A)
     double *lms = A.lms + 3 * (size_t)P.lm0, *lmT = A.lmT + 3 * (size_t)P.lm0;
     double *Hll = A.Hll + 9 * (size_t)P.lm0, *Dinv = A.Dinv + 9 * (size_t)P.lm0;
     double *bl = A.bl + 3 * (size_t)P.lm0, *xl = A.xl + 3 * (size_t)P.lm0;
-    double *Hpl = A.Hpl + 18 * (size_t)P.e0, *WD = A.WD + 18 * (size_t)P.e0;
+    double *Hpl = A.Hpl + 18 * (size_t)P.grp0, *WD = A.WD + 18 * (size_t)P.grp0;
+    const int32_t *lg_off = A.lg_off + P.lgoff0, *g_lm = A.g_lm + P.grp0, *g_pose = A.g_pose + P.grp0;
+    const int32_t *pg_off = A.pg_off + P.pgoff0, *pg_groups = A.pg_groups + P.grp0;
+    const int G = P.G;
     const double hd = A.huber_delta;
 
     for (int i = tid; i < 7 * NA; i += BA_T) {
@@ -159,9 +181,13 @@ k_ba_window(BaArgs A)
             if (s0 == s1) continue;
             double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b3[3] = {0, 0, 0};
             const double *pl = lms + 3 * l;
+            int gi = lg_off[l] - 1, cur_p = -1;      // the edges of a landmark are listed pose-ascending: one run per group
             for (int s = s0; s < s1; s++) {
                 int e = l_edges[s], cam = edge_cam[e];
-                const double *T = poseA + 7 * edge_p[e];
+                const int ep = edge_p[e];
+                const bool first = ep != cur_p;
+                if (first) { gi++; cur_p = ep; }
+                const double *T = poseA + 7 * ep;
                 double er[2], a[3], c[3], Jp[12], Jl[6];
                 gd::ba_error(T, A.ext[cam], A.K[cam], pl, edge_uv + 2 * e, er, a, c);
                 if (A.jac_mode == 1) gd::ba_jac_numeric(T, A.ext[cam], A.K[cam], pl, edge_uv + 2 * e, Jp, Jl);
@@ -180,9 +206,14 @@ k_ba_window(BaArgs A)
                 for (int x = 0; x < 6; x++)
 #pragma unroll
                     for (int y = 0; y < 3; y++) Wv[x * 3 + y] = r1 * (Jp[x] * Jl[y] + Jp[6 + x] * Jl[3 + y]);
-                double2 *W = reinterpret_cast<double2 *>(Hpl + 18 * (size_t)e);
+                double2 *W = reinterpret_cast<double2 *>(Hpl + 18 * (size_t)gi);
+                if (first) {
 #pragma unroll
-                for (int x = 0; x < 9; x++) W[x] = make_double2(Wv[2 * x], Wv[2 * x + 1]);
+                    for (int x = 0; x < 9; x++) W[x] = make_double2(Wv[2 * x], Wv[2 * x + 1]);
+                } else {      // second observation of the landmark in the same keyframe (this thread wrote the first one)
+#pragma unroll
+                    for (int x = 0; x < 9; x++) { double2 t = W[x]; W[x] = make_double2(t.x + Wv[2 * x], t.y + Wv[2 * x + 1]); }
+                }
             }
 #pragma unroll
             for (int x = 0; x < 9; x++) Hll[9 * (size_t)l + x] = H[x];
@@ -266,9 +297,9 @@ k_ba_window(BaArgs A)
                 for (int x = 0; x < 9; x++) Dinv[9 * (size_t)l + x] = Di[x];
             }
             __syncthreads();
-            // ---- per EDGE: W V^-1
-            for (int e = tid; e < E; e += BA_T) {
-                const double *Di = Dinv + 9 * (size_t)edge_l[e], *W = Hpl + 18 * (size_t)e;
+            // ---- per GROUP: W V^-1
+            for (int e = tid; e < G; e += BA_T) {
+                const double *Di = Dinv + 9 * (size_t)g_lm[e], *W = Hpl + 18 * (size_t)e;
                 double X[18];
 #pragma unroll
                 for (int x = 0; x < 6; x++)
@@ -333,9 +364,9 @@ k_ba_window(BaArgs A)
             // ---- g_i = bp_i - sum_e (W V^-1)_e bl
             for (int a = warp; a < NA; a += BA_T / 32) {
                 double s6[6] = {0, 0, 0, 0, 0, 0};
-                for (int s = p_off[a] + lane; s < p_off[a + 1]; s += 32) {
-                    int e = p_edges[s];
-                    const double *O = WD + 18 * (size_t)e, *b3 = bl + 3 * (size_t)edge_l[e];
+                for (int s = pg_off[a] + lane; s < pg_off[a + 1]; s += 32) {
+                    int e = pg_groups[s];
+                    const double *O = WD + 18 * (size_t)e, *b3 = bl + 3 * (size_t)g_lm[e];
 #pragma unroll
                     for (int x = 0; x < 6; x++) s6[x] += O[x * 3] * b3[0] + O[x * 3 + 1] * b3[1] + O[x * 3 + 2] * b3[2];
                 }
@@ -347,7 +378,7 @@ k_ba_window(BaArgs A)
             }
             __syncthreads();
             bool ok = s_flag != 0;
-            if (ok) ok = (np <= 128) ? warp_ldlt_solve(S, pitch, np, g, xp, tr, tmp, &s_piv) : block_ldlt_solve(S, pitch, np, g, xp, tr, tmp, &s_piv);
+            if (ok) ok = S2 ? block_ldlt_solve_pp(S, S2, pitch, np, g, xp, tr, tmp) : block_ldlt_solve(S, pitch, np, g, xp, tr, tmp, &s_piv);
             st_sol++;
             if (!ok) { for (int i = tid; i < np; i += BA_T) xp[i] = 0.0; __syncthreads(); }
             // ---- back-substitution, trial state, scale term
@@ -358,9 +389,8 @@ k_ba_window(BaArgs A)
                 double c3[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
                 double x3[3] = {0, 0, 0};
                 if (ok) {
-                    for (int s = s0; s < s1; s++) {
-                        int e = l_edges[s];
-                        const double *W = Hpl + 18 * (size_t)e, *xx = xp + 6 * edge_p[e];
+                    for (int e = lg_off[l]; e < lg_off[l + 1]; e++) {
+                        const double *W = Hpl + 18 * (size_t)e, *xx = xp + 6 * g_pose[e];
 #pragma unroll
                         for (int y = 0; y < 3; y++) {
                             double sm2 = 0;
@@ -428,15 +458,6 @@ k_ba_window(BaArgs A)
 }
 
 // ---------------------------------------------------------------------------------------------
-static size_t ba_smem_bytes(int NA, bool with_S)
-{
-    size_t np = 6 * (size_t)NA, pitch = np | 1;
-    size_t d = BA_T + 14 * (size_t)NA + 36 * (size_t)NA + 4 * np;
-    size_t bytes = d * 8 + ((np + 1) & ~(size_t)1) * 4;
-    if (with_S) bytes += np * pitch * 8;
-    return bytes + 16;
-}
-
 extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, double *poses, const int32_t *lm_off, double *lms,
                                const int32_t *e_off, const int32_t *edge_kf, const int32_t *edge_lm, const uint8_t *edge_cam,
                                const double *edge_uv, const double K_left[4], const double K_right[4], const double ext_left[7],
@@ -451,7 +472,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
 
     // ---- host-side structure: active poses, CSR by landmark / pose, per-block pair lists
     std::vector<BaProb> probs(n_prob);
-    std::vector<int32_t> act_pose, edge_p(sumE), l_off, l_edges(sumE), p_off, p_edges(sumE), blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off;
+    std::vector<int32_t> act_pose, edge_p(sumE), l_off, l_edges(sumE), p_off, p_edges(sumE), blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off, lg_off, g_lm, g_pose, pg_off, pg_groups;
     long long pairs_total = 0;
     const size_t smem_cap = 200 * 1024;
     size_t max_smem = 0;
@@ -470,7 +491,8 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
         for (int k = 0; k < N; k++) if (pidx[k] == 0) { pidx[k] = NA++; act_pose.push_back(k); }
         P.NA = NA; P.L = L; P.E = E; P.pose0 = kf_off[b]; P.lm0 = lm_off[b]; P.e0 = e0;
         for (int e = 0; e < E; e++) edge_p[e0 + e] = pidx[edge_kf[e0 + e]];
-        // CSR by landmark (creation order inside a landmark)
+        // CSR by landmark; inside a landmark the edges are listed pose-ascending (stable: creation order inside a pose),
+        // so that the edges of one GROUP = (landmark, pose) form a run
         P.loff0 = (int)l_off.size();
         std::vector<int> cnt(L + 1, 0);
         for (int e = 0; e < E; e++) cnt[edge_lm[e0 + e] + 1]++;
@@ -478,6 +500,9 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
         for (int l = 0; l <= L; l++) l_off.push_back(cnt[l]);
         { std::vector<int> fill(cnt.begin(), cnt.end() - 1);
           for (int e = 0; e < E; e++) l_edges[e0 + fill[edge_lm[e0 + e]]++] = e; }
+        for (int l = 0; l < L; l++)
+            std::stable_sort(l_edges.begin() + e0 + cnt[l], l_edges.begin() + e0 + cnt[l + 1],
+                             [&](int x, int y) { return edge_p[e0 + x] < edge_p[e0 + y]; });
         // CSR by active pose
         P.poff0 = (int)p_off.size();
         std::vector<int> pc(NA + 1, 0);
@@ -486,18 +511,35 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
         for (int a = 0; a <= NA; a++) p_off.push_back(pc[a]);
         { std::vector<int> fill(pc.begin(), pc.end() - 1);
           for (int e = 0; e < E; e++) p_edges[e0 + fill[edge_p[e0 + e]]++] = e; }
-        // (edge, edge) pairs per upper block (i <= j), sorted by block id i*NA + j (counting sort; inside a block in
-        // landmark / list order), then cut into chunks of <= BA_CH pairs that never span two blocks
+        // groups, landmark-major / pose-ascending; CSR by landmark and by pose
+        P.grp0 = (int)g_lm.size(); P.lgoff0 = (int)lg_off.size(); P.pgoff0 = (int)pg_off.size();
+        int G = 0;
+        std::vector<int> pgc(NA + 1, 0);
+        for (int l = 0; l < L; l++) {
+            lg_off.push_back(G);
+            int cur = -1;
+            for (int s1 = cnt[l]; s1 < cnt[l + 1]; s1++) {
+                int pp = edge_p[e0 + l_edges[e0 + s1]];
+                if (pp != cur) { cur = pp; g_lm.push_back(l); g_pose.push_back(pp); pgc[pp + 1]++; G++; }
+            }
+        }
+        lg_off.push_back(G);
+        P.G = G;
+        for (int a = 0; a < NA; a++) pgc[a + 1] += pgc[a];
+        for (int a = 0; a <= NA; a++) pg_off.push_back(pgc[a]);
+        { std::vector<int> fill(pgc.begin(), pgc.end() - 1);
+          pg_groups.resize((size_t)P.grp0 + G);
+          for (int g = 0; g < G; g++) pg_groups[P.grp0 + fill[g_pose[P.grp0 + g]]++] = g; }
+        // (group, group) pairs per upper block (i <= j): the groups of a landmark have distinct, ascending poses, so the
+        // pairs are (a, b) with a <= b in list order.  Sorted by block id i*NA + j (counting sort; inside a block in
+        // landmark order), then cut into chunks of <= BA_CH pairs that never span two blocks
         P.blk0 = (int)blk_i.size(); P.bch0 = (int)blk_ch.size(); P.pair0 = (int)pr_e1.size();
         P.ch0 = (int)ch_blk.size(); P.choff0 = (int)ch_off.size(); P.part0 = (long long)ch_blk.size();
         std::vector<int> bcount((size_t)NA * NA + 1, 0);
-        const int32_t *lo = l_off.data() + P.loff0;
+        const int32_t *lgo = lg_off.data() + P.lgoff0, *gp = g_pose.data() + P.grp0;
         for (int l = 0; l < L; l++)
-            for (int s1 = lo[l]; s1 < lo[l + 1]; s1++)
-                for (int s2 = lo[l]; s2 < lo[l + 1]; s2++) {
-                    int i = edge_p[e0 + l_edges[e0 + s1]], j = edge_p[e0 + l_edges[e0 + s2]];
-                    if (i <= j) bcount[(size_t)i * NA + j + 1]++;
-                }
+            for (int g1 = lgo[l]; g1 < lgo[l + 1]; g1++)
+                for (int g2 = g1; g2 < lgo[l + 1]; g2++) bcount[(size_t)gp[g1] * NA + gp[g2] + 1]++;
         int nblk = 0, run = 0, nch = 0;
         std::vector<int> bstart((size_t)NA * NA, 0);
         for (size_t k = 0; k < (size_t)NA * NA; k++) {
@@ -516,16 +558,15 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
         size_t pbase = pr_e1.size();
         pr_e1.resize(pbase + run); pr_e2.resize(pbase + run);
         for (int l = 0; l < L; l++)
-            for (int s1 = lo[l]; s1 < lo[l + 1]; s1++)
-                for (int s2 = lo[l]; s2 < lo[l + 1]; s2++) {
-                    int e1 = l_edges[e0 + s1], e2 = l_edges[e0 + s2];
-                    int i = edge_p[e0 + e1], j = edge_p[e0 + e2];
-                    if (i <= j) { int q = bstart[(size_t)i * NA + j]++; pr_e1[pbase + q] = e1; pr_e2[pbase + q] = e2; }
+            for (int g1 = lgo[l]; g1 < lgo[l + 1]; g1++)
+                for (int g2 = g1; g2 < lgo[l + 1]; g2++) {
+                    int q = bstart[(size_t)gp[g1] * NA + gp[g2]]++;
+                    pr_e1[pbase + q] = g1; pr_e2[pbase + q] = g2;
                 }
         pairs_total += run;
-        size_t with = ba_smem_bytes(NA, true);
-        if (with <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, with); }
-        else { P.S_off = S_tot; size_t np = 6 * (size_t)NA; S_tot += (long long)(np * (np | 1)); max_smem = std::max(max_smem, ba_smem_bytes(NA, false)); }
+        if (ba_smem_need(NA, 2) <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, ba_smem_need(NA, 2)); }
+        else if (ba_smem_need(NA, 1) <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, ba_smem_need(NA, 1)); }
+        else { P.S_off = S_tot; size_t np = 6 * (size_t)NA; S_tot += (long long)(np * (np | 1)); max_smem = std::max(max_smem, ba_smem_need(NA, 0)); }
     }
     if (max_smem > 220 * 1024) SVS_FAIL(c, SVS_ERR_CAPACITY, "ba: window too large for the single-CTA solver");
 
@@ -551,6 +592,12 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     size_t o_p2 = add(pr_e2.data(), pr_e2.size() * 4);
     size_t o_cb = add(ch_blk.data(), ch_blk.size() * 4);
     size_t o_co = add(ch_off.data(), ch_off.size() * 4);
+    size_t o_lg = add(lg_off.data(), lg_off.size() * 4);
+    size_t o_gl = add(g_lm.data(), g_lm.size() * 4);
+    size_t o_gp = add(g_pose.data(), g_pose.size() * 4);
+    size_t o_pgo = add(pg_off.data(), pg_off.size() * 4);
+    size_t o_pgg = add(pg_groups.data(), pg_groups.size() * 4);
+    const size_t sumG = g_lm.size();
     size_t o_pose = add(poses, (size_t)sumN * 56);
     size_t o_lm = add(lms, (size_t)sumL * 24);
     SVS_CUDA(c, c->h_in.reserve(tot + 16));
@@ -559,7 +606,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     for (const Seg &s : segs) if (s.bytes) memcpy(hb + s.off, s.src, s.bytes);
     SVS_CUDA(c, cudaMemcpyAsync(db, hb, tot, cudaMemcpyHostToDevice, c->stream));
     // scratch
-    size_t sc_b = ((size_t)sumE * 36 + (size_t)sumL * 27 + (size_t)S_tot + ch_blk.size() * 36) * 8 + 64;
+    size_t sc_b = (sumG * 36 + (size_t)sumL * 27 + (size_t)S_tot + ch_blk.size() * 36) * 8 + 64;
     SVS_CUDA(c, c->d_tmp.reserve(sc_b));
     size_t out_b = (size_t)sumE * 8 + (size_t)n_prob * sizeof(svs_ba_stats);
     SVS_CUDA(c, c->d_out.reserve(out_b + 16));
@@ -577,8 +624,11 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     A.blk_ch = reinterpret_cast<int32_t *>(db + o_bc);
     A.pr_e1 = reinterpret_cast<int32_t *>(db + o_p1); A.pr_e2 = reinterpret_cast<int32_t *>(db + o_p2);
     A.ch_blk = reinterpret_cast<int32_t *>(db + o_cb); A.ch_off = reinterpret_cast<int32_t *>(db + o_co);
-    A.Hpl = scr; A.WD = A.Hpl + (size_t)sumE * 18;
-    A.Hll = A.WD + (size_t)sumE * 18; A.Dinv = A.Hll + (size_t)sumL * 9;
+    A.lg_off = reinterpret_cast<int32_t *>(db + o_lg); A.g_lm = reinterpret_cast<int32_t *>(db + o_gl);
+    A.g_pose = reinterpret_cast<int32_t *>(db + o_gp); A.pg_off = reinterpret_cast<int32_t *>(db + o_pgo);
+    A.pg_groups = reinterpret_cast<int32_t *>(db + o_pgg);
+    A.Hpl = scr; A.WD = A.Hpl + sumG * 18;
+    A.Hll = A.WD + sumG * 18; A.Dinv = A.Hll + (size_t)sumL * 9;
     A.bl = A.Dinv + (size_t)sumL * 9; A.xl = A.bl + (size_t)sumL * 3; A.lmT = A.xl + (size_t)sumL * 3;
     A.S_glob = A.lmT + (size_t)sumL * 3;
     A.part = A.S_glob + (size_t)S_tot;
@@ -586,7 +636,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     A.stats = reinterpret_cast<svs_ba_stats *>(c->d_out.as<uint8_t>() + (size_t)sumE * 8);
     for (int i = 0; i < 4; i++) { A.K[0][i] = K_left[i]; A.K[1][i] = K_right[i]; }
     for (int i = 0; i < 7; i++) { A.ext[0][i] = ext_left[i]; A.ext[1][i] = ext_right[i]; }
-    A.huber_delta = huber_delta; A.max_iter = max_iter; A.jac_mode = jacobian_mode;
+    A.huber_delta = huber_delta; A.max_iter = max_iter; A.jac_mode = jacobian_mode; A.smem_bytes = (int)max_smem;
     static size_t attr_set = 0;
     if (max_smem > attr_set) {
         SVS_CUDA(c, cudaFuncSetAttribute(k_ba_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));

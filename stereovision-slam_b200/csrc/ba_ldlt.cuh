@@ -5,84 +5,83 @@
 #define BA_T 256
 #endif
 
-// Single-warp variant for small systems (n <= 128, i.e. windows of up to 21 keyframes): the factorisation is a chain of n
-// dependent steps with O(n) work each, so a 512-thread CTA spends it in __syncthreads (measured: 76 us of a 450 us LM
-// iteration at n = 60).  One warp with __syncwarp only does the same steps in ~1/6 of the time; the other warps wait at
-// the barrier below.  Same pivoting and the same left-looking update order as block_ldlt_solve, lane = row.
-__device__ __forceinline__ bool warp_ldlt_solve(double *S, int pitch, int n, const double *g, double *x, int *tr, double *tmp, int *s_flag)
+// Pre-permuted variant (needs a second n x pitch buffer S2 and n ints).  Eigen's unblocked LDLT picks, at step k, the
+// largest |diagonal| entry of the trailing part, and that part of the diagonal is NOT updated before its turn
+// (left-looking): the pivot order is simply the diagonal sorted by decreasing magnitude, known before any arithmetic.
+// So: rank the diagonal in parallel, write the symmetrically permuted matrix into S2 once, then run the left-looking
+// factorisation without pivoting.  Every row group recomputes the pivot row's dot product redundantly (same lanes, same
+// order => identical bits), which leaves ONE __syncthreads per step instead of five (a step has O(n) work, so the
+// block-wide version is barrier-bound: measured 76 us per solve at n = 60 with 512 threads).  Arithmetic is identical to
+// block_ldlt_solve except for the order of exactly equal pivots.  The pivots d_k go to the unused upper-triangle slot
+// S2[k][k+1] (the pitch is n + 1) so that S2[k][k] stays read-only while the groups of step k still read it.
+__device__ __forceinline__ bool block_ldlt_solve_pp(const double *S, double *S2, int pitch, int n, const double *g, double *x,
+                                                    int *perm, double *tmp)
 {
     const int tid = threadIdx.x, lane = tid & 31;
-    if (tid < 32) {
-        int sign = 0;
-        bool zero_first = false;
-        for (int k = 0; k < n; k++) {
-            double best = -1.0;
-            int bi = k;
-            for (int i = k + lane; i < n; i += 32) { double v = fabs(S[i * pitch + i]); if (v > best) { best = v; bi = i; } }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
-            const int piv = bi;
-            if (lane == 0) tr[k] = piv;
-            if (piv != k) {
-                for (int t = lane; t < n + 1; t += 32) {
-                    if (t < k) { double a = S[k * pitch + t]; S[k * pitch + t] = S[piv * pitch + t]; S[piv * pitch + t] = a; }
-                    else if (t == k) { double a = S[k * pitch + k]; S[k * pitch + k] = S[piv * pitch + piv]; S[piv * pitch + piv] = a; }
-                    else if (t < piv) { double a = S[t * pitch + k]; S[t * pitch + k] = S[piv * pitch + t]; S[piv * pitch + t] = a; }
-                    else if (t > piv && t < n) { double a = S[t * pitch + k]; S[t * pitch + k] = S[t * pitch + piv]; S[t * pitch + piv] = a; }
-                }
-                __syncwarp();
-            }
-            for (int j = lane; j < k; j += 32) tmp[j] = S[j * pitch + j] * S[k * pitch + j];
-            __syncwarp();
-            if (k > 0) {
-                for (int i = k + lane; i < n; i += 32) {
-                    const double *row = S + i * pitch;
-                    double a0 = 0, a1 = 0;
-                    int j = 0;
-                    for (; j + 1 < k; j += 2) { a0 += row[j] * tmp[j]; a1 += row[j + 1] * tmp[j + 1]; }
-                    if (j < k) a0 += row[j] * tmp[j];
-                    S[i * pitch + k] -= a0 + a1;
-                }
-                __syncwarp();
-            }
-            double akk = S[k * pitch + k];
-            bool valid = fabs(akk) > 0.0;
-            if (k == 0 && !valid) { for (int j = lane; j < n; j += 32) tr[j] = j; sign = 0; zero_first = true; __syncwarp(); break; }
-            if (valid) for (int i = k + 1 + lane; i < n; i += 32) S[i * pitch + k] /= akk;
-            if (sign == 1) { if (akk < 0) sign = 2; }
-            else if (sign == -1) { if (akk > 0) sign = 2; }
-            else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = -1; }
-            __syncwarp();
-        }
-        (void)zero_first;
-        bool ok = (sign == 1 || sign == 0);
-        if (ok) {
-            for (int i = lane; i < n; i += 32) x[i] = g[i];
-            __syncwarp();
-            if (lane == 0) for (int k = 0; k < n; k++) if (tr[k] != k) { double t = x[k]; x[k] = x[tr[k]]; x[tr[k]] = t; }
-            __syncwarp();
-            for (int i = 0; i < n; i++) {
-                double xi = x[i];
-                for (int j = i + 1 + lane; j < n; j += 32) x[j] -= S[j * pitch + i] * xi;
-                __syncwarp();
-            }
-            for (int i = lane; i < n; i += 32) { double d = S[i * pitch + i]; x[i] = (fabs(d) > DBL_MIN) ? x[i] / d : 0.0; }
-            __syncwarp();
-            for (int i = n - 1; i >= 0; i--) {
-                double xi = x[i];
-                for (int j = lane; j < i; j += 32) x[j] -= S[i * pitch + j] * xi;
-                __syncwarp();
-            }
-            if (lane == 0) for (int k = n - 1; k >= 0; k--) if (tr[k] != k) { double t = x[k]; x[k] = x[tr[k]]; x[tr[k]] = t; }
-        }
-        if (lane == 0) *s_flag = ok ? 1 : 0;
+    // rank of |S_ii| in decreasing order (ties: lower index first)
+    for (int i = tid; i < n; i += BA_T) {
+        const double di = fabs(S[i * pitch + i]);
+        int r = 0;
+        for (int j = 0; j < n; j++) { double dj = fabs(S[j * pitch + j]); r += (dj > di || (dj == di && j < i)) ? 1 : 0; }
+        perm[r] = i;
     }
     __syncthreads();
-    bool ok = *s_flag != 0;
+    for (int t = tid; t < n * n; t += BA_T) {
+        int a = t / n, b = t - a * n;
+        if (b <= a) S2[a * pitch + b] = S[perm[a] * pitch + perm[b]];
+    }
+    __syncthreads();
+    int sign = 0;
+    bool zero_first = false;
+    const int sub = tid & 3, grp = tid >> 2;
+    for (int k = 0; k < n; k++) {
+        const double *rowk = S2 + k * pitch;
+        const int trips = (n - k + (BA_T >> 2) - 1) / (BA_T >> 2);
+        double akk = 0;
+        for (int m = 0; m < trips; m++) {
+            const int i = k + grp + m * (BA_T >> 2);
+            const double *rowi = S2 + (i < n ? i : k) * pitch;
+            double acc_i = 0, acc_k = 0;
+            for (int j = sub; j < k; j += 4) {
+                const double lk = rowk[j], t = S2[j * pitch + j + 1] * lk;
+                acc_k += lk * t;
+                acc_i += rowi[j] * t;
+            }
+            acc_i += __shfl_xor_sync(0xffffffffu, acc_i, 1); acc_k += __shfl_xor_sync(0xffffffffu, acc_k, 1);
+            acc_i += __shfl_xor_sync(0xffffffffu, acc_i, 2); acc_k += __shfl_xor_sync(0xffffffffu, acc_k, 2);
+            akk = rowk[k] - acc_k;
+            const bool valid = fabs(akk) > 0.0;
+            if (i < n && sub == 0) {
+                if (i == k) S2[k * pitch + k + 1] = akk;
+                else { double v = S2[i * pitch + k] - acc_i; S2[i * pitch + k] = valid ? v / akk : v; }
+            }
+        }
+        if (k == 0 && !(fabs(akk) > 0.0)) { zero_first = true; break; }
+        if (sign == 1) { if (akk < 0) sign = 2; }
+        else if (sign == -1) { if (akk > 0) sign = 2; }
+        else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = -1; }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (zero_first) sign = 0;
+    bool ok = (sign == 1 || sign == 0);
+    if (ok && tid < 32) {   // triangular solves on one warp, in the permuted order
+        for (int i = lane; i < n; i += 32) tmp[i] = g[perm[i]];
+        __syncwarp();
+        for (int i = 0; i < n; i++) {
+            double xi = tmp[i];
+            for (int j = i + 1 + lane; j < n; j += 32) tmp[j] -= S2[j * pitch + i] * xi;
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) { double d = S2[i * pitch + i + 1]; tmp[i] = (fabs(d) > DBL_MIN) ? tmp[i] / d : 0.0; }
+        __syncwarp();
+        for (int i = n - 1; i >= 0; i--) {
+            double xi = tmp[i];
+            for (int j = lane; j < i; j += 32) tmp[j] -= S2[i * pitch + j] * xi;
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) x[perm[i]] = tmp[i];
+    }
     __syncthreads();
     return ok;
 }

@@ -178,3 +178,31 @@ def test_save_slam_output(ctx, granule, clip, tmp_path):
         assert ate < 0.10 and abs(ate - synth.ate_rmse(est, T[:20])) < 1e-9
     finally:
         slam.close()
+
+
+def test_pipeline_config4_shape_lockstep(ctx, granule, clip):
+    """BASELINE config 4 frontend shape: FULL-resolution processing (1226x370, no half-resolution resize), 2000 requested
+    features with minDistance 5 (the deviation SURVEY.md §0 documents), BA window 10.  Teacher-forced like the test
+    above: identical discrete results, poses within 1e-5 relative."""
+    cor, L, R, T = clip
+    kw = dict(num_features=2000, gftt_min_distance=5.0, num_features_needed_for_keyframe=800, num_features_init=200,
+              num_features_tracking=200, num_features_tracking_bad=80)
+    slam = ctx.slam(1, cor.W, cor.H, cor.K_full(), cor.baseline, half=False, oracle_simd_granule=granule, **kw)
+    o = op.Pipeline(cor.K_full(), cor.baseline, op.Cfg(granule=granule, **kw), stages="oracle", half=False)
+    try:
+        nk = 0
+        for i in range(8):
+            est = slam.add_frames(L[i:i + 1], R[i:i + 1])[0].copy()
+            west = o.add_frame(L[i], R[i])
+            assert slam.status[0] == o.status and bool(slam.is_kf[0]) == o.is_kf, i
+            assert i == 0 or slam.inliers[0] == o.tracking_inliers, i
+            xy, ids, _ = slam.features(0, cap=8192)
+            wxy, wids = o.current_features()
+            assert len(xy) == len(wxy) and np.array_equal(ids, wids), i
+            assert np.abs(xy - wxy).max() < 2e-2, i
+            assert np.abs(est - west).max() < 1e-5 * max(1.0, np.abs(west[4:]).max()), i
+            nk += int(o.is_kf)
+            _sync(slam, 0, o)
+        assert len(xy) > 700 and nk >= 2
+    finally:
+        slam.close()
