@@ -300,18 +300,20 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank
     torch.cuda.set_device(dev)
-    G = max(1, min(args.groups, args.streams))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    # one context group per host core this rank can count on: a group's driver thread does the per-stream bookkeeping of its
+    # streams and spin-waits on its CUDA stream in between, so more groups than cores only adds contention
+    G = max(1, min(args.groups, args.streams, max(1, cores // max(1, local_world))))
     ctxs = [svslam.Context(dev) for _ in range(G)]   # raises if libsvslam.so / a B200 is missing: no fallback
     lib = ctxs[0].lib
     lib.svs_kernel_name.restype = C.c_char_p
     B = args.streams
     gsz = [B // G + (1 if g < B % G else 0) for g in range(G)]
     goff = np.concatenate([[0], np.cumsum(gsz)]).astype(int)
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        cores = os.cpu_count() or 1
     host_threads = max(1, cores // (max(1, local_world) * G))
     log("rendering clip ...")
     cor, L, R, T = make_clip(args.clip_frames)

@@ -8,12 +8,6 @@
 namespace slam {
 
 // ------------------------------------------------------------------ SE3 (Sophus::SE3d formulas)
-Vec3 SE3::rotate(const Vec3 &p) const
-{   // Eigen QuaternionBase::_transformVector
-    double ux = 2.0 * (d[1] * p.z - d[2] * p.y), uy = 2.0 * (d[2] * p.x - d[0] * p.z), uz = 2.0 * (d[0] * p.y - d[1] * p.x);
-    return {p.x + d[3] * ux + (d[1] * uz - d[2] * uy), p.y + d[3] * uy + (d[2] * ux - d[0] * uz), p.z + d[3] * uz + (d[0] * uy - d[1] * ux)};
-}
-Vec3 SE3::operator*(const Vec3 &p) const { Vec3 r = rotate(p); return {r.x + d[4], r.y + d[5], r.z + d[6]}; }
 SE3 SE3::operator*(const SE3 &o) const
 {
     const double *A = d, *B = o.d;
@@ -167,55 +161,70 @@ void Frontend::begin_AddFrame(Frame::Ptr frame, int img_w, int img_h)
 
 void Frontend::prepare_TrackLastFrame(LkRequest &rq)
 {
-    rq.prev_xy.clear(); rq.next_xy.clear();
     const std::vector<Feature> &lf = last_frame_->feature_left_;
-    for (size_t i = 0; i < lf.size(); i++) {
+    const size_t n = lf.size();
+    rq.prev_xy.resize(2 * n); rq.next_xy.resize(2 * n);
+    float *pv = rq.prev_xy.data(), *nx = rq.next_xy.data();
+    const SE3 Tcw = current_frame_->Pose();
+    for (size_t i = 0; i < n; i++) {
         const Feature &f = lf[i];
-        if (i + 8 < lf.size()) map_->PrefetchMapPoint(lf[i + 8].map_point_);
-        rq.prev_xy.push_back(f.x); rq.prev_xy.push_back(f.y);
+        if (i + 8 < n) map_->PrefetchMapPoint(lf[i + 8].map_point_);
+        pv[2 * i] = f.x; pv[2 * i + 1] = f.y;
         if (MapPoint *mp = map_->GetMapPoint(f.map_point_)) {
-            Vec2 px = camera_left_->world2pixel(mp->pos_, current_frame_->Pose());
-            rq.next_xy.push_back((float)px.x); rq.next_xy.push_back((float)px.y);
+            Vec2 px = camera_left_->world2pixel(mp->pos_, Tcw);
+            nx[2 * i] = (float)px.x; nx[2 * i + 1] = (float)px.y;
         } else {
-            rq.next_xy.push_back(f.x); rq.next_xy.push_back(f.y);
+            nx[2 * i] = f.x; nx[2 * i + 1] = f.y;
         }
     }
-    rq.status.assign(last_frame_->feature_left_.size(), 0);
+    rq.status.assign(n, 0);
 }
 
 int Frontend::finish_TrackLastFrame(const LkRequest &rq)
 {
+    const size_t n = rq.status.size();
+    const float w = (float)img_w_, h = (float)img_h_;
+    const Feature *lf = last_frame_->feature_left_.data();
+    std::vector<Feature> &cf = current_frame_->feature_left_;
+    cf.resize(n);
+    Feature *out = cf.data();
     int num_good_pts = 0;
-    for (size_t i = 0; i < rq.status.size(); i++) {
+    for (size_t i = 0; i < n; i++) {
         if (!rq.status[i]) continue;
         float x = rq.next_xy[2 * i], y = rq.next_xy[2 * i + 1];
-        if (y < 0 || y >= (float)img_h_ || x < 0 || x >= (float)img_w_) continue;
-        Feature f;
+        if (y < 0 || y >= h || x < 0 || x >= w) continue;
+        Feature &f = out[num_good_pts++];
         f.x = x; f.y = y; f.size = 7;
-        f.map_point_ = last_frame_->feature_left_[i].map_point_;
-        current_frame_->feature_left_.push_back(f);
-        num_good_pts++;
+        f.map_point_ = lf[i].map_point_;
     }
+    cf.resize((size_t)num_good_pts);
     last_tracked = num_good_pts;
     return num_good_pts;
 }
 
 void Frontend::prepare_EstimateCurrentPose(PoseRequest &rq)
 {
-    rq.pts_w.clear(); rq.uv.clear(); rq.feat_index.clear();
     camera_left_->K(rq.K);
     SE3 T = current_frame_->Pose();
     for (int i = 0; i < 7; i++) rq.T0[i] = T.d[i];
-    for (size_t i = 0; i < current_frame_->feature_left_.size(); i++) {
-        Feature &f = current_frame_->feature_left_[i];
-        if (i + 8 < current_frame_->feature_left_.size()) map_->PrefetchMapPoint(current_frame_->feature_left_[i + 8].map_point_);
+    const std::vector<Feature> &cf = current_frame_->feature_left_;
+    const size_t n = cf.size();
+    rq.pts_w.resize(3 * n); rq.uv.resize(2 * n); rq.feat_index.resize(n);
+    double *pw = rq.pts_w.data(), *uv = rq.uv.data();
+    int *fi = rq.feat_index.data();
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++) {
+        const Feature &f = cf[i];
+        if (i + 8 < n) map_->PrefetchMapPoint(cf[i + 8].map_point_);
         if (MapPoint *mp = map_->GetMapPoint(f.map_point_)) {
-            rq.feat_index.push_back((int)i);
-            rq.pts_w.push_back(mp->pos_.x); rq.pts_w.push_back(mp->pos_.y); rq.pts_w.push_back(mp->pos_.z);
-            rq.uv.push_back((double)f.x); rq.uv.push_back((double)f.y);
+            fi[m] = (int)i;
+            pw[3 * m] = mp->pos_.x; pw[3 * m + 1] = mp->pos_.y; pw[3 * m + 2] = mp->pos_.z;
+            uv[2 * m] = (double)f.x; uv[2 * m + 1] = (double)f.y;
+            m++;
         }
     }
-    rq.outlier.assign(rq.feat_index.size(), 0);
+    rq.pts_w.resize(3 * m); rq.uv.resize(2 * m); rq.feat_index.resize(m);
+    rq.outlier.assign(m, 0);
 }
 
 int Frontend::finish_EstimateCurrentPose(const PoseRequest &rq)

@@ -44,8 +44,15 @@ struct SE3 {
     SE3() {}
     static SE3 fromArray(const double *p) { SE3 T; for (int i = 0; i < 7; i++) T.d[i] = p[i]; return T; }
     static SE3 fromTranslation(const Vec3 &t) { SE3 T; T.d[4] = t.x; T.d[5] = t.y; T.d[6] = t.z; return T; }
-    Vec3 rotate(const Vec3 &p) const;
-    Vec3 operator*(const Vec3 &p) const;           // point action
+    // Eigen QuaternionBase::_transformVector; inline: called once or twice per feature per frame
+    Vec3 rotate(const Vec3 &p) const
+    {
+        double ux = 2.0 * (d[1] * p.z - d[2] * p.y), uy = 2.0 * (d[2] * p.x - d[0] * p.z), uz = 2.0 * (d[0] * p.y - d[1] * p.x);
+        return {p.x + d[3] * ux + (d[1] * uz - d[2] * uy), p.y + d[3] * uy + (d[2] * ux - d[0] * uz), p.z + d[3] * uz + (d[0] * uy - d[1] * ux)};
+    }
+    Vec3 operator*(const Vec3 &p) const { Vec3 r = rotate(p); return {r.x + d[4], r.y + d[5], r.z + d[6]}; }   // point action
+    // a pure translation (the rectified cameras' extrinsics): rotate() returns its argument bit for bit, so it can be skipped
+    bool rotation_is_identity() const { return d[0] == 0.0 && d[1] == 0.0 && d[2] == 0.0 && d[3] == 1.0; }
     SE3 operator*(const SE3 &o) const;             // composition (Sophus renormalisation included)
     SE3 inverse() const;
     Vec3 translation() const { return {d[4], d[5], d[6]}; }
@@ -60,11 +67,21 @@ public:
     double fx_ = 0, fy_ = 0, cx_ = 0, cy_ = 0, baseline_ = 0;
     SE3 pose_, pose_inv_;   // extrinsic: stereo-system frame -> this camera
     Camera() {}
+    bool pure_translation_ = false;
     Camera(double fx, double fy, double cx, double cy, double baseline, const SE3 &pose)
-        : fx_(fx), fy_(fy), cx_(cx), cy_(cy), baseline_(baseline), pose_(pose) { pose_inv_ = pose_.inverse(); }
+        : fx_(fx), fy_(fy), cx_(cx), cy_(cy), baseline_(baseline), pose_(pose)
+    {
+        pose_inv_ = pose_.inverse();
+        pure_translation_ = pose_.rotation_is_identity();
+    }
     SE3 pose() const { return pose_; }
     void K(double k4[4]) const { k4[0] = fx_; k4[1] = fy_; k4[2] = cx_; k4[3] = cy_; }
-    Vec3 world2camera(const Vec3 &p_w, const SE3 &T_c_w) const { return pose_ * (T_c_w * p_w); }
+    Vec3 world2camera(const Vec3 &p_w, const SE3 &T_c_w) const
+    {
+        Vec3 v = T_c_w * p_w;
+        if (pure_translation_) return {v.x + pose_.d[4], v.y + pose_.d[5], v.z + pose_.d[6]};   // == pose_ * v, bit for bit
+        return pose_ * v;
+    }
     Vec3 camera2world(const Vec3 &p_c, const SE3 &T_c_w) const { return T_c_w.inverse() * (pose_inv_ * p_c); }
     Vec2 camera2pixel(const Vec3 &p_c) const { return {fx_ * p_c.x / p_c.z + cx_, fy_ * p_c.y / p_c.z + cy_}; }
     Vec3 pixel2camera(const Vec2 &p_p, double depth = 1) const { return {(p_p.x - cx_) * depth / fx_, (p_p.y - cy_) * depth / fy_, depth}; }
