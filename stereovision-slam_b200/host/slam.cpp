@@ -64,9 +64,9 @@ void SE3::log(double *a) const
 // ------------------------------------------------------------------ MapPoint / Map
 void MapPoint::RemoveObservation(const Observation &o)
 {   // src/mappoint.cpp:38-78
-    for (auto it = observations_.begin(); it != observations_.end(); ++it) {
+    for (auto it = observations_->begin(); it != observations_->end(); ++it) {
         if (*it == o) {
-            observations_.erase(it);
+            observations_->erase(it);
             Feature &f = o.feature();
             if (f.outlier_) f.map_point_ = -1;
             observed_times_--;
@@ -77,19 +77,17 @@ void MapPoint::RemoveObservation(const Observation &o)
 
 MapPoint *Map::CreateNewMappoint()
 {
-    if (n_points_ % kChunk == 0) chunks_.emplace_back(new MapPoint[kChunk]);
+    if (n_points_ % kChunk == 0) { chunks_.emplace_back(new MapPoint[kChunk]); obs_chunks_.emplace_back(new ObsList[kChunk]); }
     MapPoint *mp = GetMapPoint((long)n_points_);
+    mp->observations_ = &obs_chunks_[n_points_ / kChunk][n_points_ % kChunk];
     mp->id_ = n_points_++;
     return mp;
 }
-void Map::InsertMapPoint(MapPoint *mp) { landmarks_[mp->id_] = mp; active_landmarks_[mp->id_] = mp; }
+void Map::InsertMapPoint(MapPoint *mp) { landmarks_.insert_or_assign(mp->id_, mp); active_landmarks_.insert_or_assign(mp->id_, mp); }
 
 void Map::CleanMap()
 {
-    for (auto it = active_landmarks_.begin(); it != active_landmarks_.end();) {
-        if (it->second->observed_times_ == 0) it = active_landmarks_.erase(it);
-        else ++it;
-    }
+    active_landmarks_.erase_if([](const LandmarkMap::value_type &kv) { return kv.second->observed_times_ == 0; });
 }
 
 void Map::InsertKeyFrame(Frame::Ptr frame)
@@ -385,10 +383,10 @@ bool Backend::prepare_Optimize(BaRequest &rq)
     rq.edge_cam.clear(); rq.kf_ids.clear(); rq.lm_ids.clear(); rq.edge_obs.clear();     // keep the capacity of the last window
     const Map::KeyframesType &keyframes = map_->GetActiveKeyFrames();
     const Map::LandmarksType &landmarks = map_->GetActiveMapPoints();
-    std::map<unsigned long, int> vertices;
+    // window rows: Frame::ba_index_ (reset below for the keyframes of this window; every other frame keeps -1)
     unsigned long max_kf_id = 0, min_kf_id = 10000000000UL;
     for (const auto &kv : keyframes) {
-        vertices[kv.first] = (int)rq.kf_ids.size();
+        kv.second->ba_index_ = (int)rq.kf_ids.size();
         rq.kf_ids.push_back(kv.first);
         SE3 T = kv.second->Pose();
         rq.poses.insert(rq.poses.end(), T.d, T.d + 7);
@@ -409,9 +407,9 @@ bool Backend::prepare_Optimize(BaRequest &rq)
                 Vec3 p = mp->Pos();
                 rq.lms.push_back(p.x); rq.lms.push_back(p.y); rq.lms.push_back(p.z);
             }
-            auto it = vertices.find(obs.frame->keyframe_id_);
-            if (it == vertices.end()) continue;
-            rq.edge_kf.push_back(it->second);
+            const int row = obs.frame->ba_index_;
+            if (row < 0) continue;
+            rq.edge_kf.push_back(row);
             rq.edge_lm.push_back(lm_index);
             rq.edge_cam.push_back(feat.is_on_left_image_ ? 0 : 1);
             rq.edge_uv.push_back((double)feat.x); rq.edge_uv.push_back((double)feat.y);
@@ -419,6 +417,7 @@ bool Backend::prepare_Optimize(BaRequest &rq)
         }
     }
     rq.chi2.assign(rq.edge_kf.size(), 0.0);
+    for (const auto &kv : keyframes) kv.second->ba_index_ = -1;
     return !rq.edge_kf.empty();
 }
 

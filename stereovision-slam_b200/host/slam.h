@@ -19,6 +19,7 @@
 //  * Bundle adjustment runs on the synchronous schedule (inside UpdateMap), SURVEY.md §5.
 //  * Hash-map iteration orders that the reference leaves unspecified are fixed to ascending id.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <map>
@@ -108,6 +109,7 @@ public:
     double time_stamp_ = 0;
     std::vector<Feature> feature_left_, feature_right_;
     long prev_keyframe_ = -1;   // keyframe id of the previous keyframe
+    int ba_index_ = -1;         // row of this keyframe in the window problem being built (Backend::prepare_Optimize)
     SE3 relative_pose_pkf_;
     SE3 Pose() const { return pose_; }
     void SetPose(const SE3 &p) { pose_ = p; }
@@ -121,24 +123,91 @@ struct Observation {            // weak_ptr<Feature> of a keyframe feature
     Feature &feature() const { return left ? frame->feature_left_[index] : frame->feature_right_[index]; }
 };
 
+// Observation list of a landmark (std::list<weak_ptr<Feature>> in the reference): insertion order kept.  The first kInline
+// entries are stored in place (most landmarks are seen 2-4 times) and the lists live in an arena parallel to the landmark
+// arena, so walking the active landmarks of a window (Backend::Optimize) is two linear walks instead of one heap hop per
+// landmark, while the per-frame lookups (position only) touch 48-byte MapPoints.
+class ObsList {
+public:
+    static constexpr int kInline = 4;
+    typedef const Observation *const_iterator;
+    ObsList() {}
+    ObsList(const ObsList &) = delete;
+    ObsList &operator=(const ObsList &) = delete;
+    ~ObsList() { delete[] heap_; }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    const Observation *begin() const { return data(); }
+    const Observation *end() const { return data() + n_; }
+    void push_back(const Observation &o)
+    {
+        if (n_ == cap_) grow();
+        data()[n_++] = o;
+    }
+    void erase(const Observation *it)
+    {
+        Observation *d = data();
+        for (size_t i = (size_t)(it - d); i + 1 < n_; i++) d[i] = d[i + 1];
+        n_--;
+    }
+private:
+    Observation *data() { return heap_ ? heap_ : inline_; }
+    const Observation *data() const { return heap_ ? heap_ : inline_; }
+    void grow()
+    {
+        uint32_t nc = cap_ * 2;
+        Observation *h = new Observation[nc];
+        for (uint32_t i = 0; i < n_; i++) h[i] = data()[i];
+        delete[] heap_;
+        heap_ = h; cap_ = nc;
+    }
+    Observation inline_[kInline];
+    Observation *heap_ = nullptr;
+    uint32_t n_ = 0, cap_ = kInline;
+};
+
+// Sorted flat map id -> MapPoint* with the few std::map operations the path uses (the reference's unordered_map, iterated
+// in ascending id here): landmark ids only grow, so insertion is an append and iteration is a linear scan.
+class LandmarkMap {
+public:
+    typedef std::pair<unsigned long, class MapPoint *> value_type;
+    typedef std::vector<value_type>::const_iterator const_iterator;
+    typedef std::vector<value_type>::iterator iterator;
+    size_t size() const { return v_.size(); }
+    const_iterator begin() const { return v_.begin(); }
+    const_iterator end() const { return v_.end(); }
+    iterator begin() { return v_.begin(); }
+    iterator end() { return v_.end(); }
+    void insert_or_assign(unsigned long id, class MapPoint *mp)
+    {
+        if (v_.empty() || v_.back().first < id) { v_.emplace_back(id, mp); return; }
+        iterator it = std::lower_bound(v_.begin(), v_.end(), id, [](const value_type &a, unsigned long b) { return a.first < b; });
+        if (it != v_.end() && it->first == id) it->second = mp;
+        else v_.insert(it, value_type(id, mp));
+    }
+    template <class Pred> void erase_if(Pred pred) { v_.erase(std::remove_if(v_.begin(), v_.end(), pred), v_.end()); }
+private:
+    std::vector<value_type> v_;
+};
+
 class MapPoint {
 public:
-    unsigned long id_ = 0;
-    bool is_outlier_ = false;
+    unsigned long id_ = 0;                    // 48 bytes: the per-frame path reads pos_ of ~190 landmarks per stream
     Vec3 pos_;
     int observed_times_ = 0;
-    std::vector<Observation> observations_;   // std::list in the reference; insertion order kept
+    bool is_outlier_ = false;
+    ObsList *observations_ = nullptr;         // std::list in the reference; insertion order kept; storage: Map's arena
     Vec3 Pos() const { return pos_; }
     void SetPos(const Vec3 &p) { pos_ = p; }
-    void AddObservation(const Observation &o) { observations_.push_back(o); observed_times_++; }   // mappoint.cpp:22-36
+    void AddObservation(const Observation &o) { observations_->push_back(o); observed_times_++; }  // mappoint.cpp:22-36
     void RemoveObservation(const Observation &o);                                                  // mappoint.cpp:38-78
-    const std::vector<Observation> &GetObs() const { return observations_; }
+    const ObsList &GetObs() const { return *observations_; }
 };
 
 class Map {
 public:
     typedef std::shared_ptr<Map> Ptr;
-    typedef std::map<unsigned long, MapPoint *> LandmarksType;     // ascending id (reference: unordered_map)
+    typedef LandmarkMap LandmarksType;                             // ascending id (reference: unordered_map)
     typedef std::map<unsigned long, Frame::Ptr> KeyframesType;
     explicit Map(int num_active_keyframes) : num_active_keyframes_(num_active_keyframes) {}
     void CleanMap();                                  // map.cpp:21-40
@@ -158,6 +227,7 @@ private:
     void RemoveOldKeyframe();                         // map.cpp:76-181
     static constexpr size_t kChunk = 256;
     std::vector<std::unique_ptr<MapPoint[]>> chunks_;
+    std::vector<std::unique_ptr<ObsList[]>> obs_chunks_;
     size_t n_points_ = 0;
     LandmarksType landmarks_, active_landmarks_;
     KeyframesType keyframes_, active_keyframes_;
