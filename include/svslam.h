@@ -182,6 +182,10 @@ SVS_API int svs_ba_optimize(svs_ctx *ctx, int n_prob, const int32_t *kf_off, dou
                             double huber_delta, int max_iter, int jacobian_mode,
                             double *edge_chi2_out /* sumE */, svs_ba_stats *stats /* n_prob or NULL */);
 
+/* Wall time svs_ba_optimize has spent on this context in: building the problem structure on the host | packing + enqueueing |
+ * waiting for the device and unpacking (diagnostics for bench.py). */
+SVS_API int svs_ba_host_seconds(svs_ctx *ctx, double out[3]);
+
 /* ---------------------------------------------------------------- a7, sharded : large / multi-GPU bundle adjustment
  * Same problem and solver as svs_ba_optimize, for windows too large for one CTA (config 4: N = 50, L = 1e5) and for
  * landmark sharding across GPUs: every shard holds ALL n_kf poses and a disjoint subset of the landmarks

@@ -22,6 +22,7 @@
 #include "svs_internal.h"
 #include "geom_dev.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -469,11 +470,16 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     const int sumN = kf_off[n_prob], sumL = lm_off[n_prob], sumE = e_off[n_prob];
     if (sumE > 0 && (!edge_kf || !edge_lm || !edge_cam || !edge_uv || !edge_chi2_out || !poses || !lms)) return SVS_ERR_ARG;
     SVS_CUDA(c, cudaSetDevice(c->device));
+    auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now_s();
 
     // ---- host-side structure: active poses, CSR by landmark / pose, per-block pair lists
     std::vector<BaProb> probs(n_prob);
     std::vector<int32_t> act_pose, edge_p(sumE), l_off, l_edges(sumE), p_off, p_edges(sumE), blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off, lg_off, g_lm, g_pose, pg_off, pg_groups;
     long long pairs_total = 0;
+    l_off.reserve((size_t)sumL + n_prob); lg_off.reserve((size_t)sumL + n_prob); g_lm.reserve(sumE); g_pose.reserve(sumE);
+    pg_groups.reserve(sumE); pr_e1.reserve(2 * (size_t)sumE); pr_e2.reserve(2 * (size_t)sumE);
+    ch_blk.reserve((size_t)sumE / 4 + 64 * (size_t)n_prob); ch_off.reserve((size_t)sumE / 4 + 65 * (size_t)n_prob);
     const size_t smem_cap = 200 * 1024;
     size_t max_smem = 0;
     long long S_tot = 0;
@@ -500,9 +506,16 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
         for (int l = 0; l <= L; l++) l_off.push_back(cnt[l]);
         { std::vector<int> fill(cnt.begin(), cnt.end() - 1);
           for (int e = 0; e < E; e++) l_edges[e0 + fill[edge_lm[e0 + e]]++] = e; }
-        for (int l = 0; l < L; l++)
-            std::stable_sort(l_edges.begin() + e0 + cnt[l], l_edges.begin() + e0 + cnt[l + 1],
-                             [&](int x, int y) { return edge_p[e0 + x] < edge_p[e0 + y]; });
+        for (int l = 0; l < L; l++) {      // stable insertion sort: a landmark has a handful of edges
+            int32_t *a = l_edges.data() + e0 + cnt[l];
+            const int m = cnt[l + 1] - cnt[l];
+            for (int i = 1; i < m; i++) {
+                const int32_t v = a[i], pv = edge_p[e0 + v];
+                int j = i - 1;
+                while (j >= 0 && edge_p[e0 + a[j]] > pv) { a[j + 1] = a[j]; j--; }
+                a[j + 1] = v;
+            }
+        }
         // CSR by active pose
         P.poff0 = (int)p_off.size();
         std::vector<int> pc(NA + 1, 0);
@@ -570,6 +583,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     }
     if (max_smem > 220 * 1024) SVS_FAIL(c, SVS_ERR_CAPACITY, "ba: window too large for the single-CTA solver");
 
+    const double t_built = now_s();
     // ---- pack host -> device
     struct Seg { const void *src; size_t bytes; size_t off; };
     std::vector<Seg> segs;
@@ -648,10 +662,20 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     size_t ho_pose = align_up(out_b, 16), ho_lm = ho_pose + (size_t)sumN * 56;
     SVS_CUDA(c, cudaMemcpyAsync(ho + ho_pose, A.poses, (size_t)sumN * 56, cudaMemcpyDeviceToHost, c->stream));
     if (sumL) SVS_CUDA(c, cudaMemcpyAsync(ho + ho_lm, A.lms, (size_t)sumL * 24, cudaMemcpyDeviceToHost, c->stream));
+    const double t_queued = now_s();
     SVS_CUDA(c, cudaStreamSynchronize(c->stream));
     if (sumE) memcpy(edge_chi2_out, ho, (size_t)sumE * 8);
     if (stats) memcpy(stats, ho + (size_t)sumE * 8, (size_t)n_prob * sizeof(svs_ba_stats));
     memcpy(poses, ho + ho_pose, (size_t)sumN * 56);
     if (sumL) memcpy(lms, ho + ho_lm, (size_t)sumL * 24);
+    const double t_end = now_s();
+    c->ba_host_s[0] += t_built - t_begin; c->ba_host_s[1] += t_queued - t_built; c->ba_host_s[2] += t_end - t_queued;
+    return SVS_OK;
+}
+
+extern "C" int svs_ba_host_seconds(svs_ctx *c, double out[3])
+{
+    if (!c || !out) return SVS_ERR_ARG;
+    for (int i = 0; i < 3; i++) out[i] = c->ba_host_s[i];
     return SVS_OK;
 }

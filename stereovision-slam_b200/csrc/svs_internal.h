@@ -69,6 +69,7 @@ struct svs_ctx {
     cudaStream_t stream_in = nullptr;   // ingest stream: prefetch of the NEXT frame pair overlaps this step's compute
     std::string err;
     long long launches = 0;
+    double ba_host_s[3] = {0, 0, 0};   // svs_ba_optimize wall time: structure build | pack + enqueue | wait for the device + unpack
     // scratch (named by user)
     DevBuf d_in, d_in2, d_out, d_out2, d_tmp, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_tmp6;
     PinBuf h_in, h_out;
