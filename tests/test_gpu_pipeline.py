@@ -206,3 +206,34 @@ def test_pipeline_config4_shape_lockstep(ctx, granule, clip):
         assert len(xy) > 700 and nk >= 2
     finally:
         slam.close()
+
+
+def test_kitti_directory_end_to_end(ctx, clip, tmp_path):
+    """The data formats either side of the path, end to end: a KITTI-layout sequence directory (calib.txt, image_0/,
+    image_1/ PNGs, ground-truth poses file) -> KittiSequence -> engine -> keyframes.txt / landmarks.pcd -> ATE."""
+    import cv2
+    import json
+    import os
+    import subprocess
+    import sys
+    from svslam import kitti
+    cor, L, R, T = clip
+    d = str(tmp_path / "05")
+    for cam, imgs in ((0, L), (1, R)):
+        os.makedirs(os.path.join(d, "image_%d" % cam))
+        for i in range(24):
+            cv2.imwrite(os.path.join(d, "image_%d" % cam, "%06d.png" % i), imgs[i])
+    f, cx, cy, b = cor.f, cor.cx, cor.cy, cor.baseline
+    with open(os.path.join(d, "calib.txt"), "w") as fh:
+        for i, tx in enumerate((0.0, -f * b, 0.0, -f * b)):
+            fh.write("P%d: %.12e 0 %.12e %.12e 0 %.12e %.12e 0 0 0 1 0\n" % (i, f, cx, tx, f, cy))
+    _, Twc = kitti.pose7_to_Twc(np.asarray(T)[:24])
+    np.savetxt(str(tmp_path / "05.txt"), Twc.reshape(24, 12))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "run_kitti.py"), d, "--poses", str(tmp_path / "05.txt"),
+                        "--out", str(tmp_path / "out")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["frames"] == 24 and not out["lost"] and out["keyframes"] >= 2 and out["landmarks"] > 100
+    assert out["ate_rmse_m"] < 0.10 and out["rpe_trans_m"] < 0.05
+    assert os.path.exists(str(tmp_path / "out" / "keyframes.txt")) and os.path.exists(str(tmp_path / "out" / "landmarks.pcd"))
