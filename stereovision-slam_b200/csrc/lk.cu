@@ -19,12 +19,17 @@ __device__ __forceinline__ int lk_refl101(int i, int n)
     while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
     return i;
 }
-__device__ __forceinline__ long long warp_sum_i32_exact(int s)
-{   // exact 64-bit sum of 32 int32 partials via two hardware 32-bit reductions
+// f32( (sum over the warp of s) * 2^-20 ), correctly rounded from the EXACT integer sum (which may exceed 32 bits):
+// the low 16 bits and the signed high part are reduced separately with the hardware 32-bit reductions (< 2^21 and < 2^27
+// in magnitude, so both convert to f32 exactly), and ONE fused multiply-add combines them: hi * 2^-4 + lo * 2^-20 is the
+// exact scaled sum rounded once — the same value as __ll2float_rn(sum) * 2^-20 (scaling by a power of two commutes with
+// the rounding), in 8 instructions instead of a 64-bit recombination and conversion.
+__device__ __forceinline__ float warp_sum_scaled_exact(int s)
+{
     int lo = s & 0xFFFF, hi = s >> 16;
     int slo = __reduce_add_sync(0xffffffffu, lo);
     int shi = __reduce_add_sync(0xffffffffu, hi);
-    return (long long)shi * 65536ll + (long long)slo;
+    return __fmaf_rn((float)shi, 0.0625f, __fmul_rn((float)slo, 1.f / (1 << 20)));
 }
 __device__ __forceinline__ int cvfloor(float v) { return __float2int_rd(v); }
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
@@ -33,8 +38,8 @@ __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1)
 #define LK_MARGIN 6      // the next-image region staged per level extends this many pixels around the first window
 
 template <int WIN>
-__global__ void __launch_bounds__(LK_WARPS * 32)
-k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const float *__restrict__ prev_xy,
+__global__ void __launch_bounds__(LK_WARPS * 32, WIN <= 11 ? 6 : 1)
+k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc next, const int32_t *__restrict__ pt_img, const float *__restrict__ prev_xy,
            float *__restrict__ next_xy, int n_pts, int max_iter, double eps2, uint8_t *__restrict__ status)
 {
     constexpr int PW = WIN + 3;                 // previous-image patch (window + bilinear + Scharr halo)
@@ -52,9 +57,9 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
     constexpr int NPL = (WIN * WIN + 31) / 32;  // window samples per lane
     __shared__ __align__(16) uint8_t sI[LK_WARPS][PW * IP];
     __shared__ short2 sD[LK_WARPS][DW * DW];
+    __shared__ short2 sT[LK_WARPS][DW * PW];     // separable Scharr: vertical pass
     __shared__ __align__(16) uint8_t sJ[LK_WARPS][RH * RP];
     const int W_BITS = 14;
-    const float FLT_SCALE = 1.f / (1 << 20);
     const float half = (WIN - 1) * 0.5f;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int pt = blockIdx.x * LK_WARPS + warp;
@@ -64,7 +69,7 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
     float nxt_x = next_xy[2 * pt], nxt_y = next_xy[2 * pt + 1];
     bool st = true;
     uint8_t *mI = sI[warp], *mJ = sJ[warp];
-    short2 *mD = sD[warp];
+    short2 *mD = sD[warp], *mT = sT[warp];
     int nlev = min(prev.nlev, next.nlev);
     // this lane's window samples: smem offsets in the previous-image patch and in the next-image region
     int offI[NPL], offJ[NPL], offD[NPL];
@@ -147,22 +152,41 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
             }
         }
         __syncwarp();
-        // Scharr derivative patch (zero outside the image: BORDER_CONSTANT on the derivative buffer)
-        for (int k = lane; k < DW * DW; k += 32) {
-            int j = k / DW, i = k - j * DW;
-            int X = ix + i, Y = iy + j;
-            short2 d = make_short2(0, 0);
-            if (X >= 0 && X < Iw && Y >= 0 && Y < Ih) {
-                const uint8_t *p = mI + j * IP + i + ioff;   // top-left of the 3x3 neighbourhood
-                int v00 = p[0], v01 = p[1], v02 = p[2];
-                int v10 = p[IP], v12 = p[IP + 2];
-                int v20 = p[2 * IP], v21 = p[2 * IP + 1], v22 = p[2 * IP + 2];
-                int s0l = (v00 + v20) * 3 + v10 * 10, s0r = (v02 + v22) * 3 + v12 * 10;
-                int s1l = v20 - v00, s1c = v21 - v01, s1r = v22 - v02;
-                d.x = (short)(s0r - s0l);
-                d.y = (short)((s1l + s1r) * 3 + s1c * 10);
+        // Scharr derivative patch (zero outside the image: BORDER_CONSTANT on the derivative buffer), separable:
+        //   pass 1  (PW columns x DW rows)  c = 3 (p[j] + p[j+2]) + 10 p[j+1]   (vertical smoothing, for dx)
+        //                                   d = p[j+2] - p[j]                  (vertical difference, for dy)
+        //   pass 2  (DW x DW)               dx = c[i+2] - c[i],  dy = 3 (d[i] + d[i+2]) + 10 d[i+1]
+        // exact integers either way; ~1/4 of the instructions of the direct 3x3 form
+        // lane = (half-warp hw, column i): each half-warp walks half of the rows with a sliding 3-row register window,
+        // so there is no index arithmetic in the loops
+        {
+            constexpr int HR = (DW + 1) / 2;                  // rows per half-warp
+            const int hw = lane >> 4, i = lane & 15;
+            const int j0 = hw * HR, j1 = min(DW, j0 + HR);
+            for (int ib = i; ib < PW; ib += 16) {              // one pass for WIN <= 13 (PW <= 16), column blocks beyond
+                const uint8_t *p = mI + j0 * IP + ib + ioff;
+                int p0 = p[0], p1 = p[IP];
+                for (int j = j0; j < j1; j++) {
+                    int p2 = p[2 * IP];
+                    mT[j * PW + ib] = make_short2((short)(3 * (p0 + p2) + 10 * p1), (short)(p2 - p0));
+                    p0 = p1; p1 = p2; p += IP;
+                }
             }
-            mD[k] = d;
+            __syncwarp();
+            const bool inside = ix >= 0 && iy >= 0 && ix + DW <= Iw && iy + DW <= Ih;   // every derivative sample is in the image
+            for (int ib = i; ib < DW; ib += 16) {
+                const short2 *t = mT + j0 * PW + ib;
+                for (int j = j0; j < j1; j++) {
+                    short2 t0 = t[0], t1 = t[1], t2 = t[2];
+                    short2 d = make_short2((short)(t2.x - t0.x), (short)(3 * (t0.y + t2.y) + 10 * t1.y));
+                    if (!inside) {
+                        int X = ix + ib, Y = iy + j;
+                        if (!(X >= 0 && X < Iw && Y >= 0 && Y < Ih)) d = make_short2(0, 0);
+                    }
+                    mD[j * DW + ib] = d;
+                    t += PW;
+                }
+            }
         }
         __syncwarp();
         int Iv[NPL], Ixv[NPL], Iyv[NPL];
@@ -182,9 +206,7 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
                 pA11 += Ixv[q] * Ixv[q]; pA12 += Ixv[q] * Iyv[q]; pA22 += Iyv[q] * Iyv[q];
             }
         }
-        float A11 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pA11)), FLT_SCALE);
-        float A12 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pA12)), FLT_SCALE);
-        float A22 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pA22)), FLT_SCALE);
+        float A11 = warp_sum_scaled_exact(pA11), A12 = warp_sum_scaled_exact(pA12), A22 = warp_sum_scaled_exact(pA22);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         float dd = __fsub_rn(A11, A22);
         float rad = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -192,16 +214,26 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
         if ((double)minEig < 1e-4 || D < FLT_EPSILON) { if (level == 0) st = false; continue; }
         D = __fdiv_rn(1.f, D);
         float pdx = 0.f, pdy = 0.f;
+        // window origins (jx, jy) that are interior AND covered by the staged region: one unsigned range test per axis
+        int fx_lo = 0, fx_n = -1, fy_lo = 0, fy_n = -1;
+        if (reg_valid) {
+            fx_lo = max(0, rx0); fx_n = min(Jw - DW, rx0 + RP - DW) - fx_lo;
+            fy_lo = max(0, ry0); fy_n = min(Jh - DW, ry0 + RH - DW) - fy_lo;
+            if (fx_n < 0 || fy_n < 0) fx_n = fy_n = -1;
+        }
         for (int j = 0; j < max_iter; j++) {
             int jx = cvfloor(nx), jy = cvfloor(ny);
-            if (jx < -WIN || jx >= Jw || jy < -WIN || jy >= Jh) { if (level == 0) st = false; break; }
+            const bool fast = fx_n >= 0 && (unsigned)(jx - fx_lo) <= (unsigned)fx_n && (unsigned)(jy - fy_lo) <= (unsigned)fy_n;
+            if (!fast && (jx < -WIN || jx >= Jw || jy < -WIN || jy >= Jh)) { if (level == 0) st = false; break; }
             a = __fsub_rn(nx, (float)jx); b = __fsub_rn(ny, (float)jy);
             w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
             w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
             w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), (float)(1 << W_BITS)));
             w11 = (1 << W_BITS) - w00 - w01 - w10;
             const uint8_t *pJ;
-            if (jx >= 0 && jy >= 0 && jx + DW <= Jw && jy + DW <= Jh) {
+            if (fast) {
+                pJ = mJ + (jy - ry0) * RP + (jx - rx0);
+            } else if (jx >= 0 && jy >= 0 && jx + DW <= Jw && jy + DW <= Jh) {
                 if (!(reg_valid && jx >= rx0 && jx + DW <= rx0 + RP && jy >= ry0 && jy + DW <= ry0 + RH)) {
                     // the window left the staged region (or there is none yet): restage around the current window
                     __syncwarp();
@@ -212,6 +244,9 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
                         reinterpret_cast<uint32_t *>(mJ)[k] = __ldg(reinterpret_cast<const uint32_t *>(J + (size_t)y * Js + x));
                     }
                     reg_valid = true;
+                    fx_lo = max(0, rx0); fx_n = min(Jw - DW, rx0 + RP - DW) - fx_lo;
+                    fy_lo = max(0, ry0); fy_n = min(Jh - DW, ry0 + RH - DW) - fy_lo;
+                    if (fx_n < 0 || fy_n < 0) fx_n = fy_n = -1;
                     __syncwarp();
                 }
                 pJ = mJ + (jy - ry0) * RP + (jx - rx0);
@@ -222,6 +257,7 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
                     mJ[r * RP + i] = __ldg(J + (size_t)lk_refl101(jy + r, Jh) * Js + lk_refl101(jx + i, Jw));
                 }
                 reg_valid = false;
+                fx_n = fy_n = -1;
                 __syncwarp();
                 pJ = mJ;
             }
@@ -235,8 +271,7 @@ k_lk_track(PyrDesc prev, PyrDesc next, const int32_t *__restrict__ pt_img, const
                     pb1 += diff * Ixv[q]; pb2 += diff * Iyv[q];
                 }
             }
-            float b1 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pb1)), FLT_SCALE);
-            float b2 = __fmul_rn(__ll2float_rn(warp_sum_i32_exact(pb2)), FLT_SCALE);
+            float b1 = warp_sum_scaled_exact(pb1), b2 = warp_sum_scaled_exact(pb2);
             float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
