@@ -4,6 +4,9 @@
 #include "svs_internal.h"
 #include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -12,6 +15,20 @@
 int svs_i_gftt_overflow(svs_ctx *c, int n_img, int *flag_host);
 
 static std::string g_create_err;
+static std::mutex g_mutex;                       // guards g_create_err and g_smem_opted
+static std::set<std::pair<int, const void *>> g_smem_opted;
+
+cudaError_t svs_i_opt_in_smem(svs_ctx *c, const void *func)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (g_smem_opted.count({c->device, func})) return cudaSuccess;
+    int max_optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+    if (e == cudaSuccess) g_smem_opted.insert({c->device, func});
+    return e;
+}
 static std::atomic<int> g_live_ctx{0};
 
 int svs_i_zc_grid(const svs_ctx *c)
@@ -92,6 +109,7 @@ const char *svs_create_error(void) { return g_create_err.c_str(); }
 
 svs_ctx *svs_create(int device)
 {
+    std::lock_guard<std::mutex> create_lock(g_mutex);
     // one hardware work queue per stream (a context owns two): with the default of 8, streams of different contexts share
     // a queue and wait behind each other's long ingest kernels.  Only effective if the CUDA context does not exist yet.
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);

@@ -651,11 +651,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     for (int i = 0; i < 4; i++) { A.K[0][i] = K_left[i]; A.K[1][i] = K_right[i]; }
     for (int i = 0; i < 7; i++) { A.ext[0][i] = ext_left[i]; A.ext[1][i] = ext_right[i]; }
     A.huber_delta = huber_delta; A.max_iter = max_iter; A.jac_mode = jacobian_mode; A.smem_bytes = (int)max_smem;
-    static size_t attr_set = 0;
-    if (max_smem > attr_set) {
-        SVS_CUDA(c, cudaFuncSetAttribute(k_ba_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-        attr_set = max_smem;
-    }
+    SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_ba_window)));
     SVS_KERNEL(c, KID_BA_WINDOW, k_ba_window<<<n_prob, BA_T, max_smem, c->stream>>>(A));
     uint8_t *ho = c->h_out.as<uint8_t>();
     SVS_CUDA(c, cudaMemcpyAsync(ho, c->d_out.p, out_b, cudaMemcpyDeviceToHost, c->stream));

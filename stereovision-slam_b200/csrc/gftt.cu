@@ -313,11 +313,7 @@ int svs_i_gftt(svs_ctx *c, const uint8_t *img, int w, int h, int stride, size_t 
     {
         size_t smem = GR_SMEM_KEYS * sizeof(unsigned long long) + ((P + 31) / 32) * 4;
         if (smem > 200 * 1024) SVS_FAIL(c, SVS_ERR_CAPACITY, "gftt: image too large for the shared-memory blocked bitmap");
-        static size_t attr_set = 0;
-        if (smem > attr_set) {
-            SVS_CUDA(c, cudaFuncSetAttribute(k_corner_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = smem;
-        }
+        SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_corner_greedy)));
         SVS_KERNEL(c, KID_CORNER_GREEDY, k_corner_greedy<<<n_img, GR_T, smem, c->stream>>>(cand, cap, count, w, h, max_corners, min_distance, out_xy,
                                                           out_resp, out_n, overflow));
     }

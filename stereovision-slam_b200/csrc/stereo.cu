@@ -234,11 +234,7 @@ int svs_i_stereo_bm(svs_ctx *c, const uint8_t *l_dev, const uint8_t *r_dev, int 
     int cpitch = CW | 1;
     size_t colb = (size_t)(ndisp + 1) * cpitch;
     size_t smem = (colb + (colb & 1) + (size_t)BM_TW * ndisp) * 2 + BM_TW * 4;
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-        SVS_CUDA(c, cudaFuncSetAttribute(k_bm_sad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_bm_sad)));
     dim3 g((nx + BM_TW - 1) / BM_TW, (ny + BM_RS - 1) / BM_RS, n);
     SVS_KERNEL(c, KID_BM_SAD, k_bm_sad<<<g, BM_T, smem, c->stream>>>(Lp, Rp, w, h, ndisp, r, cap, 10, 15, disp_dev));
     return SVS_OK;

@@ -124,6 +124,10 @@ void svs_i_prof_end(svs_ctx *c);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Opt a kernel in to the device's maximum dynamic shared memory, once per (device, kernel), thread-safe: contexts are
+// stepped from several host threads, and the attribute is per device.
+cudaError_t svs_i_opt_in_smem(svs_ctx *c, const void *func);
+
 // ---- internal device-level entry points (all asynchronous on ctx->stream) ----
 // images.cu
 int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t *bytes_per_image);
