@@ -359,7 +359,8 @@ def run_gpu(args, rank, world, local_rank):
     # ONE set of pipelines, primed once (untimed) until every stream's sliding BA window is full, then timed in several
     # regions that only differ in where the frames live / whether launches are instrumented.  Every region does its own
     # W warm-up steps first; the stream state simply continues from region to region (steady state).
-    slams = [ctxs[g].slam(gsz[g], cor.W, cor.H, Kh, cor.baseline, half=True, backend_on=1) for g in range(G)]
+    slams = [ctxs[g].slam(gsz[g], cor.W, cor.H, Kh, cor.baseline, half=True, backend_on=1, lazy_right_ingest=0 if args.eager_right else 1)
+             for g in range(G)]
     for s in slams:
         s.set_threads(host_threads)
     cursor = [0]
@@ -596,7 +597,9 @@ def run_gpu(args, rank, world, local_rank):
         finally:
             os.remove(path)
 
-    h2d = 2 * (cor.W * ((cor.H + 1) // 2)) * B      # only the even rows the half-resolution resize reads are copied
+    # image bytes the engine actually read from host memory in the e2e region (counted by the frame sets): the even rows of
+    # every left frame + the even rows of the right frame of the streams that inserted a keyframe in that step
+    h2d = int(e2e_pass["counts"]["h2d_image_bytes"] // args.steps)
     in_bytes = 2 * img_bytes * B
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -604,12 +607,16 @@ def run_gpu(args, rank, world, local_rank):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "streams_per_gpu": B, "context_groups": G, "frames_per_step": B * world, "num_features": 150,
                    "num_active_keyframes": 10, "ba": "synchronous, analytic Jacobians",
-                   "ingest": "per-step push" if args.no_prefetch else "double-buffered: frame t+1 is ingested on a second stream during step t", "clip_frames": nclip,
+                   "ingest": ("per-step push" if args.no_prefetch else "double-buffered: frame t+1 is ingested on a second stream during step t") +
+                             ("; both eyes of every frame" if args.eager_right else
+                              "; right images are ingested lazily, only for the streams that insert a keyframe in the step "
+                              "(the frontend reads the right image nowhere else; results are bit-identical)"), "clip_frames": nclip,
                    "priming_steps": args.priming, "group_stagger_steps": args.stagger,
                    "l2": "per-step input %.0f MB per GPU > 126 MB L2 (inputs larger than L2)" % (in_bytes / 1e6)
                    if in_bytes > 126e6 else "per-step input %.0f MB per GPU (< L2; distinct frames every step)" % (in_bytes / 1e6)},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * (56 + 12),
+                "right_images_per_step": e2e_pass["counts"]["right_images"] / args.steps,
                 "h2d": {2: "zero-copy: the resize kernel reads the pinned host frames over PCIe", 0: "staged strided DMA copies of the even rows", 3: "mixed: even context groups zero-copy, odd groups strided DMA"}[args.h2d_mode],
                 "ms_per_step": e2e_pass["ms"] / args.steps},
         "gpu_launches": int(dev_pass["launches"]),
@@ -647,6 +654,8 @@ def main():
     ap.add_argument("--priming", type=int, default=150, help="untimed steps before warm-up so the BA window is full")
     ap.add_argument("--stagger", type=int, default=40,
                     help="spread the context groups' stream ages over this many steps (about one keyframe period); 0 = all in phase")
+    ap.add_argument("--eager-right", action="store_true",
+                    help="ingest the right image of every frame (default: only for the streams that insert a keyframe in the step)")
     ap.add_argument("--no-prefetch", action="store_true", help="disable the double-buffered ingest (svs_slam_hint_next)")
     ap.add_argument("--diag", action="store_true", help="repeat the value / e2e regions a second time (detail.diag)")
     ap.add_argument("--cpu-frames", type=int, default=0,

@@ -84,6 +84,14 @@ SVS_API int svs_frameset_push(svs_ctx *ctx, svs_frameset *fs, const uint8_t *lef
  *                  reads the frames directly over PCIe, each needed row exactly once */
 SVS_API int svs_frameset_push_ptrs(svs_ctx *ctx, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right,
                                    size_t row_stride, int on_device);
+/* Lazy right-eye ingest.  The frontend reads the right image only when a stream inserts a keyframe
+ * (Frontend::FindFeaturesInRight, src/frontend.cpp:72-141), i.e. for a few percent of the frames: svs_frameset_push_ptrs and
+ * svs_frameset_prefetch_ptrs accept right == NULL (left eye only), and this call ingests the CURRENT right image
+ * (resize + pyramids) of the selected streams only: right[k] belongs to stream stream_ids[k]. */
+SVS_API int svs_frameset_fetch_right_ptrs(svs_ctx *ctx, svs_frameset *fs, const int32_t *stream_ids, int n_sel,
+                                          const uint8_t *const *right, size_t row_stride, int on_device);
+/* Image bytes this frame set has read from HOST memory so far (bench.py's h2d_bytes_per_step). */
+SVS_API long long svs_frameset_h2d_bytes(const svs_frameset *fs);
 /* Asynchronous ingest of the NEXT stereo pair (double buffering): starts the resize + pyramids of the pair the caller will
  * push next into spare buffers on the context's second (ingest) stream and returns immediately, so that the PCIe
  * transfer of frame t+1 overlaps the tracking / optimisation kernels of frame t.  The following
@@ -240,6 +248,9 @@ typedef struct {
     int32_t num_features_needed_for_keyframe, num_active_keyframes, backend_on;
     int32_t lk_win, lk_max_level, lk_max_iter, ba_max_iter, ba_jacobian_mode, oracle_simd_granule;
     double max_triangulation_depth, chi2_th, gftt_quality, gftt_min_distance, lk_eps;
+    /* 1 (default): right images are ingested only for the streams that insert a keyframe in this step (identical results,
+     * ~half the image traffic); 0: both eyes of every frame are ingested, as Dataset::NextFrame resizes both */
+    int32_t lazy_right_ingest, reserved_;
 } svs_slam_config;
 typedef struct svs_slam svs_slam;
 SVS_API void svs_slam_default_config(svs_slam_config *cfg);
@@ -263,8 +274,8 @@ SVS_API int svs_slam_get_keyframes(svs_slam *s, int stream, int active_only, int
 SVS_API int svs_slam_get_landmarks(svs_slam *s, int stream, int active_only, int64_t *ids, double *xyz,
                                    int32_t *observed_times, int cap, int *n);
 /* phase_seconds[8]: push, track-LK, pose LM, detect, right-LK, triangulate, BA, host bookkeeping (wall clock, includes
- * device time).  counters[10]: frames, keyframes, BA problems, BA iterations, BA trials, BA edges, BA landmarks,
- * BA keyframes, LK points, pose-LM edges. */
+ * device time).  counters[12]: frames, keyframes, BA problems, BA iterations, BA trials, BA edges, BA landmarks,
+ * BA keyframes, LK points, pose-LM edges, image bytes read from host memory, right images ingested (12 values). */
 SVS_API int svs_slam_get_counters(svs_slam *s, double *phase_seconds, long long *counters);
 /* host_seconds[8]: the "host bookkeeping" phase split by section (begin + prepare track, finish track + prepare pose,
  * finish pose + prepare detect, finish detect + prepare right, finish right + prepare triangulate, finish triangulate +

@@ -25,7 +25,10 @@ cudaError_t svs_i_opt_in_smem(svs_ctx *c, const void *func)
     int max_optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, func)) != cudaSuccess) return e;
+    // the opt-in limit covers static + dynamic shared memory of the kernel
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - (int)fa.sharedSizeBytes);
     if (e == cudaSuccess) g_smem_opted.insert({c->device, func});
     return e;
 }
@@ -70,9 +73,9 @@ static void prof_harvest(svs_ctx *c)
 
 extern "C" {
 
-static int frameset_fill(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const PyrDesc &Rc, const uint8_t *dl, const uint8_t *dr,
-                         size_t rs, size_t is, const uint8_t *const *pl, const uint8_t *const *pr, int aligned4,
-                         int rows_decimated = 0, int zero_copy = 0);
+static int frameset_fill(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const PyrDesc *Rc, const uint8_t *dl, const uint8_t *dr,
+                         size_t rs, size_t is, const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated,
+                         int zero_copy, int n_img, const int32_t *ids_dev);
 static int frameset_begin_push(svs_ctx *c, svs_frameset *fs);
 
 int svs_version(void) { return 100; }
@@ -247,27 +250,29 @@ int svs_frameset_push(svs_ctx *c, svs_frameset *fs, const uint8_t *left, const u
         dl = sl; dr = sr; rs = fs->in_w; is = dense; decim = fs->half ? 1 : 0;
     }
     SVS_TRY(frameset_begin_push(c, fs));
-    return frameset_fill(c, fs, fs->L[fs->il_cur], fs->R[fs->ir_cur], dl, dr, rs, is, nullptr, nullptr, 0, decim);
+    if (!on_device) fs->h2d_bytes += 2ll * fs->B * fs->in_w * (fs->half ? fs->H : fs->in_h);
+    return frameset_fill(c, fs, fs->L[fs->il_cur], &fs->R[fs->ir_cur], dl, dr, rs, is, nullptr, nullptr, 0, decim, 0, fs->B, nullptr);
 }
 
-// resize (or copy) + pyramids of one stereo pair per stream into the given target buffers, on c->stream
-static int frameset_fill(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const PyrDesc &Rc, const uint8_t *dl, const uint8_t *dr,
+// resize (or copy) + pyramids of n_img images per eye into the given target buffers, on c->stream.  Rc == nullptr: one eye
+// only (the images go to Lc).  ids_dev != nullptr: source image k goes to pyramid slot ids_dev[k] (a subset of the streams).
+static int frameset_fill(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const PyrDesc *Rc, const uint8_t *dl, const uint8_t *dr,
                          size_t rs, size_t is, const uint8_t *const *pl, const uint8_t *const *pr, int aligned4, int rows_decimated,
-                         int zero_copy)
+                         int zero_copy, int n_img, const int32_t *ids_dev)
 {
-    if (fs->half && zero_copy && pl && pr == pl + fs->B) {
+    if (fs->half && zero_copy && pl && (!Rc || pr == pl + n_img)) {
         // frames live in pinned host memory: small persistent grid, both eyes in one launch (images.cu)
-        SVS_TRY(svs_i_half_nearest_zc(c, pl, fs->B, fs->in_w, fs->in_h, rs, Lc.base + Lc.off[0], Rc.base + Rc.off[0], fs->W, fs->H,
-                                      Lc.stride[0], Lc.img_pitch, aligned4));
+        SVS_TRY(svs_i_half_nearest_zc(c, pl, n_img, fs->in_w, fs->in_h, rs, Lc.base + Lc.off[0], Rc ? Rc->base + Rc->off[0] : nullptr,
+                                      fs->W, fs->H, Lc.stride[0], Lc.img_pitch, aligned4, ids_dev));
     } else if (fs->half) {
-        SVS_TRY(svs_i_half_nearest(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc.base + Lc.off[0], fs->W, fs->H, Lc.stride[0], Lc.img_pitch, pl, aligned4, rows_decimated));
-        SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, Rc.base + Rc.off[0], fs->W, fs->H, Rc.stride[0], Rc.img_pitch, pr, aligned4, rows_decimated));
+        SVS_TRY(svs_i_half_nearest(c, dl, fs->in_w, fs->in_h, rs, is, n_img, Lc.base + Lc.off[0], fs->W, fs->H, Lc.stride[0], Lc.img_pitch, pl, aligned4, rows_decimated, ids_dev));
+        if (Rc) SVS_TRY(svs_i_half_nearest(c, dr, fs->in_w, fs->in_h, rs, is, n_img, Rc->base + Rc->off[0], fs->W, fs->H, Rc->stride[0], Rc->img_pitch, pr, aligned4, rows_decimated, ids_dev));
     } else {
-        SVS_TRY(svs_i_copy_level0(c, dl, fs->in_w, fs->in_h, rs, is, fs->B, Lc, pl));
-        SVS_TRY(svs_i_copy_level0(c, dr, fs->in_w, fs->in_h, rs, is, fs->B, Rc, pr));
+        SVS_TRY(svs_i_copy_level0(c, dl, fs->in_w, fs->in_h, rs, is, n_img, Lc, pl, ids_dev));
+        if (Rc) SVS_TRY(svs_i_copy_level0(c, dr, fs->in_w, fs->in_h, rs, is, n_img, *Rc, pr, ids_dev));
     }
-    SVS_TRY(svs_i_build_pyramid(c, Lc, fs->B));
-    SVS_TRY(svs_i_build_pyramid(c, Rc, fs->B));
+    SVS_TRY(svs_i_build_pyramid(c, Lc, n_img, ids_dev));
+    if (Rc) SVS_TRY(svs_i_build_pyramid(c, *Rc, n_img, ids_dev));
     return SVS_OK;
 }
 
@@ -287,52 +292,63 @@ static int frameset_begin_push(svs_ctx *c, svs_frameset *fs)
 
 // Host pointers (pinned or pageable) -> staged copies of the rows the resize reads; device / zero-copy pointers ->
 // pointer table.  Everything is enqueued on c->stream (the caller may have swapped in the ingest stream).
-static int frameset_ingest_ptrs(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const PyrDesc &Rc, const uint8_t *const *left,
+// right == nullptr / Rc == nullptr: one eye.  ids_host != nullptr: n_img images for the pyramid slots ids_host[k].
+static int frameset_ingest_ptrs(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const PyrDesc *Rc, const uint8_t *const *left,
                                 const uint8_t *const *right, size_t row_stride, int on_device, DevBuf &ptr_table, PinBuf &ptr_table_h,
-                                DevBuf &staging, bool table_may_be_in_flight)
+                                DevBuf &staging, bool table_may_be_in_flight, int n_img, const int32_t *ids_host)
 {
-    const int B = fs->B;
+    const int eyes = Rc ? 2 : 1;
+    const int rows = fs->half ? fs->H : fs->in_h;
+    if (on_device != 1) fs->h2d_bytes += (long long)eyes * n_img * fs->in_w * rows;     // image bytes that cross PCIe
+    // table: [left pointers | right pointers | slot ids]
+    const size_t ptr_b = (size_t)eyes * n_img * sizeof(void *), ids_b = ids_host ? align_up((size_t)n_img * 4, 8) : 0;
+    SVS_CUDA(c, ptr_table.reserve(ptr_b + ids_b + 16));
+    SVS_CUDA(c, ptr_table_h.reserve(ptr_b + ids_b + 16));
+    // the previous table copy must have been consumed before the pinned table is overwritten
+    if (table_may_be_in_flight) SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    const uint8_t **hp = ptr_table_h.as<const uint8_t *>();
+    int aligned4 = 1;
+    for (int b = 0; b < n_img; b++) {
+        hp[b] = left[b];
+        if (Rc) hp[n_img + b] = right[b];
+        if ((reinterpret_cast<uintptr_t>(left[b]) | (Rc ? reinterpret_cast<uintptr_t>(right[b]) : 0)) & 3) aligned4 = 0;
+    }
+    if (ids_host) memcpy(ptr_table_h.as<uint8_t>() + ptr_b, ids_host, (size_t)n_img * 4);
+    const int32_t *ids_dev = ids_host ? reinterpret_cast<const int32_t *>(ptr_table.as<uint8_t>() + ptr_b) : nullptr;
     // on_device == 2: the pointers are PINNED HOST memory that the device can address (cudaHostAlloc / UVA): the resize
     // kernel reads the frames straight over PCIe (each needed row exactly once), no staging copy.
     if (on_device) {
-        SVS_CUDA(c, ptr_table.reserve((size_t)2 * B * sizeof(void *)));
-        SVS_CUDA(c, ptr_table_h.reserve((size_t)2 * B * sizeof(void *)));
-        const uint8_t **hp = ptr_table_h.as<const uint8_t *>();
-        int aligned4 = 1;
-        // the previous table copy must have been consumed before the pinned table is overwritten
-        if (table_may_be_in_flight) SVS_CUDA(c, cudaStreamSynchronize(c->stream));
-        for (int b = 0; b < B; b++) {
-            hp[b] = left[b]; hp[B + b] = right[b];
-            if ((reinterpret_cast<uintptr_t>(left[b]) | reinterpret_cast<uintptr_t>(right[b])) & 3) aligned4 = 0;
-        }
-        SVS_CUDA(c, cudaMemcpyAsync(ptr_table.p, hp, (size_t)2 * B * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+        SVS_CUDA(c, cudaMemcpyAsync(ptr_table.p, hp, ptr_b + ids_b, cudaMemcpyHostToDevice, c->stream));
         const uint8_t *const *dp = ptr_table.as<const uint8_t *>();
-        return frameset_fill(c, fs, Lc, Rc, nullptr, nullptr, row_stride, 0, dp, dp + B, aligned4, 0, on_device == 2);
+        return frameset_fill(c, fs, Lc, Rc, nullptr, nullptr, row_stride, 0, dp, Rc ? dp + n_img : nullptr, aligned4, 0, on_device == 2,
+                             n_img, ids_dev);
     }
     // Staged path: only the even rows the half-resolution resize reads cross PCIe (strided 2-D DMA copies); the kernel
     // then reads the staged rows with a unit row step.
-    const int rows = fs->half ? fs->H : fs->in_h;
+    if (ids_host) SVS_CUDA(c, cudaMemcpyAsync(ptr_table.as<uint8_t>() + ptr_b, ptr_table_h.as<uint8_t>() + ptr_b, ids_b, cudaMemcpyHostToDevice, c->stream));
     const size_t src_pitch = fs->half ? 2 * row_stride : row_stride;
     size_t dense = (size_t)fs->in_w * rows;
-    SVS_CUDA(c, staging.reserve(2 * dense * B));
-    uint8_t *sl = staging.as<uint8_t>(), *sr = sl + dense * B;
-    for (int b = 0; b < B; b++) {
+    SVS_CUDA(c, staging.reserve((size_t)eyes * dense * n_img));
+    uint8_t *sl = staging.as<uint8_t>(), *sr = sl + dense * n_img;
+    for (int b = 0; b < n_img; b++) {
         SVS_CUDA(c, cudaMemcpy2DAsync(sl + dense * b, fs->in_w, left[b], src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
-        SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right[b], src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
+        if (Rc) SVS_CUDA(c, cudaMemcpy2DAsync(sr + dense * b, fs->in_w, right[b], src_pitch, fs->in_w, rows, cudaMemcpyHostToDevice, c->stream));
     }
-    return frameset_fill(c, fs, Lc, Rc, sl, sr, fs->in_w, dense, nullptr, nullptr, 0, fs->half ? 1 : 0);
+    return frameset_fill(c, fs, Lc, Rc, sl, sr, fs->in_w, dense, nullptr, nullptr, 0, fs->half ? 1 : 0, 0, n_img, ids_dev);
 }
 
+// right == NULL: LEFT eye only (the right images are fetched later, for the streams that need them, with
+// svs_frameset_fetch_right_ptrs).
 int svs_frameset_push_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right, size_t row_stride,
                            int on_device)
 {
-    if (!c || !fs || !left || !right) return SVS_ERR_ARG;
+    if (!c || !fs || !left) return SVS_ERR_ARG;
     if (row_stride < (size_t)fs->in_w) SVS_FAIL(c, SVS_ERR_ARG, "frameset_push_ptrs: bad row stride");
     SVS_CUDA(c, cudaSetDevice(c->device));
     const int B = fs->B;
-    if (fs->pf_pending && fs->pf_mode == on_device && fs->pf_row_stride == row_stride &&
+    if (fs->pf_pending && fs->pf_mode == on_device && fs->pf_row_stride == row_stride && fs->pf_has_right == (right != nullptr) &&
         memcmp(fs->pf_ptrs.data(), left, (size_t)B * sizeof(void *)) == 0 &&
-        memcmp(fs->pf_ptrs.data() + B, right, (size_t)B * sizeof(void *)) == 0) {
+        (!right || memcmp(fs->pf_ptrs.data() + B, right, (size_t)B * sizeof(void *)) == 0)) {
         // this pair was prefetched into the "next" buffers on the ingest stream: rotate and order the main stream after it
         fs->pf_pending = false;
         fs->prefetch_hits++;
@@ -342,33 +358,33 @@ int svs_frameset_push_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *l
         return SVS_OK;
     }
     SVS_TRY(frameset_begin_push(c, fs));
-    return frameset_ingest_ptrs(c, fs, fs->L[fs->il_cur], fs->R[fs->ir_cur], left, right, row_stride, on_device, fs->ptr_table,
-                                fs->ptr_table_h, fs->staging, true);
+    return frameset_ingest_ptrs(c, fs, fs->L[fs->il_cur], right ? &fs->R[fs->ir_cur] : nullptr, left, right, row_stride, on_device,
+                                fs->ptr_table, fs->ptr_table_h, fs->staging, true, B, nullptr);
 }
 
 int svs_frameset_prefetch_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *const *left, const uint8_t *const *right,
                                size_t row_stride, int on_device)
 {
-    if (!c || !fs || !left || !right) return SVS_ERR_ARG;
+    if (!c || !fs || !left) return SVS_ERR_ARG;
     if (row_stride < (size_t)fs->in_w) SVS_FAIL(c, SVS_ERR_ARG, "frameset_prefetch_ptrs: bad row stride");
     SVS_CUDA(c, cudaSetDevice(c->device));
     if (!c->stream_in) SVS_CUDA(c, cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking));
     const int B = fs->B;
-    // a previous prefetch that was never consumed: its kernels (and its pointer-table copy) must be done before its
-    // buffers / tables are reused
-    if (fs->pf_pending) { SVS_CUDA(c, cudaEventSynchronize(fs->pf_done)); fs->pf_pending = false; fs->prefetch_misses++; }
-    else if (fs->pushes > 0 || fs->prefetch_hits > 0) SVS_CUDA(c, cudaEventSynchronize(fs->pf_done));
+    // the previous prefetch's kernels and its pointer-table copy must be done before its buffers / tables are reused
+    // (a never-recorded event is complete)
+    SVS_CUDA(c, cudaEventSynchronize(fs->pf_done));
+    if (fs->pf_pending) { fs->pf_pending = false; fs->prefetch_misses++; }
     // the "next" buffers may still be read by work already queued on the main stream
     SVS_CUDA(c, cudaEventRecord(fs->pf_order, c->stream));
     SVS_CUDA(c, cudaStreamWaitEvent(c->stream_in, fs->pf_order, 0));
     fs->pf_ptrs.resize((size_t)2 * B);
     memcpy(fs->pf_ptrs.data(), left, (size_t)B * sizeof(void *));
-    memcpy(fs->pf_ptrs.data() + B, right, (size_t)B * sizeof(void *));
-    fs->pf_mode = on_device; fs->pf_row_stride = row_stride;
+    if (right) memcpy(fs->pf_ptrs.data() + B, right, (size_t)B * sizeof(void *));
+    fs->pf_mode = on_device; fs->pf_row_stride = row_stride; fs->pf_has_right = right != nullptr;
     cudaStream_t main_stream = c->stream;
     c->stream = c->stream_in;           // every svs_i_* launch below goes to the ingest stream
-    int rc = frameset_ingest_ptrs(c, fs, fs->L[fs->il_next], fs->R[fs->ir_next], left, right, row_stride, on_device, fs->pf_ptr_table,
-                                  fs->pf_ptr_table_h, fs->pf_staging, false);
+    int rc = frameset_ingest_ptrs(c, fs, fs->L[fs->il_next], right ? &fs->R[fs->ir_next] : nullptr, left, right, row_stride, on_device,
+                                  fs->pf_ptr_table, fs->pf_ptr_table_h, fs->pf_staging, false, B, nullptr);
     cudaError_t e = cudaEventRecord(fs->pf_done, c->stream_in);
     c->stream = main_stream;
     if (rc != SVS_OK) return rc;
@@ -376,6 +392,22 @@ int svs_frameset_prefetch_ptrs(svs_ctx *c, svs_frameset *fs, const uint8_t *cons
     fs->pf_pending = true;
     return SVS_OK;
 }
+
+// Lazy right-eye ingest: resize + pyramids of the CURRENT right image of the selected streams only (the frontend reads
+// the right image only when a stream inserts a keyframe: Frontend::FindFeaturesInRight).
+int svs_frameset_fetch_right_ptrs(svs_ctx *c, svs_frameset *fs, const int32_t *stream_ids, int n_sel, const uint8_t *const *right,
+                                  size_t row_stride, int on_device)
+{
+    if (!c || !fs || n_sel < 0 || (n_sel > 0 && (!stream_ids || !right))) return SVS_ERR_ARG;
+    if (n_sel == 0) return SVS_OK;
+    if (row_stride < (size_t)fs->in_w) SVS_FAIL(c, SVS_ERR_ARG, "frameset_fetch_right_ptrs: bad row stride");
+    for (int i = 0; i < n_sel; i++) if (stream_ids[i] < 0 || stream_ids[i] >= fs->B) SVS_FAIL(c, SVS_ERR_ARG, "frameset_fetch_right_ptrs: stream id out of range");
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    return frameset_ingest_ptrs(c, fs, fs->R[fs->ir_cur], nullptr, right, nullptr, row_stride, on_device, fs->ptr_table, fs->ptr_table_h,
+                                fs->staging, true, n_sel, stream_ids);
+}
+
+long long svs_frameset_h2d_bytes(const svs_frameset *fs) { return fs ? fs->h2d_bytes : 0; }
 
 int svs_frameset_download(svs_ctx *c, svs_frameset *fs, int stream, int which, int level, uint8_t *out, int out_stride)
 {

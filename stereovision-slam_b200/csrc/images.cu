@@ -36,16 +36,17 @@ int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t
 // dst[y][x] = src[min(2y,h-1)][min(2x,w-1)]; each thread produces 4 output pixels.
 __global__ void k_half_nearest(const uint8_t *__restrict__ src, const uint8_t *const *__restrict__ src_ptrs, int w, int h,
                                size_t row_stride, size_t img_stride, uint8_t *__restrict__ dst, int dw, int dh, int dst_stride,
-                               size_t dst_img_pitch, int vec_ok, int rows_decimated)
+                               size_t dst_img_pitch, int vec_ok, int rows_decimated, const int32_t *__restrict__ dst_ids)
 {
     int img = blockIdx.z;
+    const int dimg = dst_ids ? dst_ids[img] : img;      // destination slot (stream) of source image `img`
     if (src_ptrs) { src = src_ptrs[img]; img_stride = 0; }
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (y >= dh || x4 >= dw) return;
     int sy = rows_decimated ? y : min(2 * y, h - 1);   // decimated staging already holds rows 0,2,4,...
     const uint8_t *srow = src + (size_t)img * img_stride + (size_t)sy * row_stride;
-    uint8_t *drow = dst + (size_t)blockIdx.z * dst_img_pitch + (size_t)y * dst_stride;
+    uint8_t *drow = dst + (size_t)dimg * dst_img_pitch + (size_t)y * dst_stride;
     if (vec_ok && x4 + 4 <= dw && 2 * x4 + 8 <= w) {
         const uint32_t *s32 = reinterpret_cast<const uint32_t *>(srow + 2 * x4);
         uint32_t a = __ldg(s32), b = __ldg(s32 + 1);
@@ -58,7 +59,7 @@ __global__ void k_half_nearest(const uint8_t *__restrict__ src, const uint8_t *c
 
 int svs_i_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_stride, size_t img_stride,
                        int n, uint8_t *dst, int dw, int dh, int dst_stride, size_t dst_img_pitch,
-                       const uint8_t *const *src_ptrs_dev, int ptrs_aligned4, int rows_decimated)
+                       const uint8_t *const *src_ptrs_dev, int ptrs_aligned4, int rows_decimated, const int32_t *dst_ids_dev)
 {
     if (n <= 0) return SVS_OK;
     int vec_ok = ((reinterpret_cast<uintptr_t>(src) | ((rows_decimated ? 1 : 2) * row_stride) | img_stride) & 3) == 0 &&
@@ -68,7 +69,7 @@ int svs_i_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_
     dim3 blk(32, 8);
     dim3 grd((dw + 4 * 32 - 1) / (4 * 32), (dh + 7) / 8, n);
     SVS_KERNEL(c, KID_HALF, k_half_nearest<<<grd, blk, 0, c->stream>>>(src, src_ptrs_dev, w, h, row_stride, img_stride, dst, dw, dh, dst_stride,
-                                               dst_img_pitch, vec_ok, rows_decimated));
+                                               dst_img_pitch, vec_ok, rows_decimated, dst_ids_dev));
     return SVS_OK;
 }
 
@@ -84,11 +85,12 @@ int svs_i_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_
 #define ZC_U 8
 __global__ void __launch_bounds__(256)
 k_half_nearest_zc(const uint8_t *const *__restrict__ src_ptrs, int n_img_per_eye, int w, int h, size_t row_stride,
-                  uint8_t *__restrict__ dstL, uint8_t *__restrict__ dstR, int dw, int dh, int dst_stride, size_t dst_img_pitch, int vec_ok)
+                  uint8_t *__restrict__ dstL, uint8_t *__restrict__ dstR /* null: one eye only */, int dw, int dh, int dst_stride,
+                  size_t dst_img_pitch, int vec_ok, const int32_t *__restrict__ dst_ids)
 {
     const int chunks = (dw + 3) >> 2;                    // 4 output pixels per item
     const long long per_img = (long long)chunks * dh;
-    const long long total = per_img * 2 * n_img_per_eye;
+    const long long total = per_img * (dstR ? 2 : 1) * n_img_per_eye;
     const long long nthr = (long long)gridDim.x * blockDim.x;
     for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += nthr * ZC_U) {
         uint32_t a[ZC_U], b[ZC_U];
@@ -106,7 +108,9 @@ k_half_nearest_zc(const uint8_t *const *__restrict__ src_ptrs, int n_img_per_eye
             int y = r / chunks;
             x4[u] = (r - y * chunks) * 4;
             srow[u] = src_ptrs[img] + (size_t)min(2 * y, h - 1) * row_stride;
-            uint8_t *dst = img < n_img_per_eye ? dstL + (size_t)img * dst_img_pitch : dstR + (size_t)(img - n_img_per_eye) * dst_img_pitch;
+            const int slot = img < n_img_per_eye ? img : img - n_img_per_eye;
+            const int dimg = dst_ids ? dst_ids[slot] : slot;
+            uint8_t *dst = (img < n_img_per_eye ? dstL : dstR) + (size_t)dimg * dst_img_pitch;
             drow[u] = dst + (size_t)y * dst_stride;
             fast[u] = vec_ok && x4[u] + 4 <= dw && 2 * x4[u] + 8 <= w;
             if (fast[u]) {
@@ -128,39 +132,42 @@ k_half_nearest_zc(const uint8_t *const *__restrict__ src_ptrs, int n_img_per_eye
 }
 
 int svs_i_half_nearest_zc(svs_ctx *c, const uint8_t *const *src_ptrs_dev, int n_per_eye, int w, int h, size_t row_stride,
-                          uint8_t *dstL, uint8_t *dstR, int dw, int dh, int dst_stride, size_t dst_img_pitch, int ptrs_aligned4)
+                          uint8_t *dstL, uint8_t *dstR, int dw, int dh, int dst_stride, size_t dst_img_pitch, int ptrs_aligned4,
+                          const int32_t *dst_ids_dev)
 {
     if (n_per_eye <= 0) return SVS_OK;
     int vec_ok = ptrs_aligned4 && ((2 * row_stride) & 3) == 0 &&
                  ((reinterpret_cast<uintptr_t>(dstL) | reinterpret_cast<uintptr_t>(dstR) | (size_t)dst_stride | dst_img_pitch) & 3) == 0;
-    long long items = (long long)((dw + 3) / 4) * dh * 2 * n_per_eye;
+    long long items = (long long)((dw + 3) / 4) * dh * (dstR ? 2 : 1) * n_per_eye;
     long long want = (items + 256 * ZC_U - 1) / (256 * ZC_U);
     int grid = (int)std::min<long long>(want, svs_i_zc_grid(c));
     SVS_KERNEL(c, KID_HALF, k_half_nearest_zc<<<grid, 256, 0, c->stream>>>(src_ptrs_dev, n_per_eye, w, h, row_stride, dstL, dstR, dw, dh,
-                                                                         dst_stride, dst_img_pitch, vec_ok));
+                                                                         dst_stride, dst_img_pitch, vec_ok, dst_ids_dev));
     return SVS_OK;
 }
 
 __global__ void k_copy2d(const uint8_t *__restrict__ src, const uint8_t *const *__restrict__ src_ptrs, int w, int h,
-                         size_t row_stride, size_t img_stride, uint8_t *__restrict__ dst, int dst_stride, size_t dst_img_pitch)
+                         size_t row_stride, size_t img_stride, uint8_t *__restrict__ dst, int dst_stride, size_t dst_img_pitch,
+                         const int32_t *__restrict__ dst_ids)
 {
     int img = blockIdx.z;
+    const int dimg = dst_ids ? dst_ids[img] : img;
     if (src_ptrs) { src = src_ptrs[img]; img_stride = 0; }
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= h || x >= w) return;
-    dst[(size_t)blockIdx.z * dst_img_pitch + (size_t)y * dst_stride + x] =
+    dst[(size_t)dimg * dst_img_pitch + (size_t)y * dst_stride + x] =
         __ldg(src + (size_t)img * img_stride + (size_t)y * row_stride + x);
 }
 
 int svs_i_copy_level0(svs_ctx *c, const uint8_t *src, int w, int h, size_t row_stride, size_t img_stride, int n,
-                      const PyrDesc &d, const uint8_t *const *src_ptrs_dev)
+                      const PyrDesc &d, const uint8_t *const *src_ptrs_dev, const int32_t *dst_ids_dev)
 {
     if (n <= 0) return SVS_OK;
     dim3 blk(64, 4);
     dim3 grd((w + 63) / 64, (h + 3) / 4, n);
     SVS_KERNEL(c, KID_COPY0, k_copy2d<<<grd, blk, 0, c->stream>>>(src, src_ptrs_dev, w, h, row_stride, img_stride, d.base + d.off[0], d.stride[0],
-                                         d.img_pitch));
+                                         d.img_pitch, dst_ids_dev));
     return SVS_OK;
 }
 
@@ -184,12 +191,13 @@ __device__ __forceinline__ int refl101(int i, int n)
 #define PD_WORDS (PD_TX / 2 + 2)
 __global__ void __launch_bounds__(256)
 k_pyr_down(const uint8_t *__restrict__ src_base, int sw, int sh, int sstride, uint8_t *__restrict__ dst_base,
-           int dw, int dh, int dstride, size_t img_pitch)
+           int dw, int dh, int dstride, size_t img_pitch, const int32_t *__restrict__ img_ids)
 {
     __shared__ uint32_t tile[PD_ROWS][PD_WORDS];
     __shared__ __align__(8) uint32_t hrow[PD_ROWS][PD_TX / 2];
-    const uint8_t *src = src_base + (size_t)blockIdx.z * img_pitch;
-    uint8_t *dst = dst_base + (size_t)blockIdx.z * img_pitch;
+    const int img = img_ids ? img_ids[blockIdx.z] : blockIdx.z;     // pyramid slot (stream)
+    const uint8_t *src = src_base + (size_t)img * img_pitch;
+    uint8_t *dst = dst_base + (size_t)img * img_pitch;
     const int ox0 = blockIdx.x * PD_TX, oy0 = blockIdx.y * PD_TY;
     const int bx0 = 2 * ox0 - 4, iy0 = 2 * oy0 - 2;      // image x of tile byte 0 (4-byte aligned), image y of tile row 0
     const int tid = threadIdx.x;
@@ -234,14 +242,14 @@ k_pyr_down(const uint8_t *__restrict__ src_base, int sw, int sh, int sstride, ui
     }
 }
 
-int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images)
+int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images, const int32_t *img_ids_dev)
 {
     if (n_images <= 0) return SVS_OK;
     for (int l = 1; l < d.nlev; l++) {
         dim3 blk(256);
         dim3 grd((d.w[l] + PD_TX - 1) / PD_TX, (d.h[l] + PD_TY - 1) / PD_TY, n_images);
         SVS_KERNEL(c, KID_PYRDOWN, k_pyr_down<<<grd, blk, 0, c->stream>>>(d.base + d.off[l - 1], d.w[l - 1], d.h[l - 1], d.stride[l - 1],
-                                               d.base + d.off[l], d.w[l], d.h[l], d.stride[l], d.img_pitch));
+                                               d.base + d.off[l], d.w[l], d.h[l], d.stride[l], d.img_pitch, img_ids_dev));
     }
     return SVS_OK;
 }

@@ -92,7 +92,8 @@ struct svs_frameset {
     DevBuf ptr_table;  // per-stream device pointers (push_ptrs with on_device)
     PinBuf ptr_table_h;
     // pending prefetch (svs_frameset_prefetch_ptrs)
-    bool pf_pending = false;
+    bool pf_pending = false, pf_has_right = true;
+    long long h2d_bytes = 0;                // image bytes this frame set has read from host memory
     int pf_mode = 0;
     size_t pf_row_stride = 0;
     std::vector<const uint8_t *> pf_ptrs;   // [left.. | right..] as given by the caller
@@ -133,13 +134,15 @@ cudaError_t svs_i_opt_in_smem(svs_ctx *c, const void *func);
 int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t *bytes_per_image);
 int svs_i_half_nearest(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
                        int n, uint8_t *dst_dev, int dw, int dh, int dst_stride, size_t dst_img_pitch,
-                       const uint8_t *const *src_ptrs_dev = nullptr, int ptrs_aligned4 = 0, int rows_decimated = 0);
+                       const uint8_t *const *src_ptrs_dev = nullptr, int ptrs_aligned4 = 0, int rows_decimated = 0,
+                       const int32_t *dst_ids_dev = nullptr);
 int svs_i_zc_grid(const svs_ctx *c);   // CTAs of the zero-copy ingest kernel: ~32 in total over all live contexts
 int svs_i_half_nearest_zc(svs_ctx *c, const uint8_t *const *src_ptrs_dev, int n_per_eye, int w, int h, size_t row_stride,
-                          uint8_t *dstL, uint8_t *dstR, int dw, int dh, int dst_stride, size_t dst_img_pitch, int ptrs_aligned4);
+                          uint8_t *dstL, uint8_t *dstR /* null: one eye */, int dw, int dh, int dst_stride, size_t dst_img_pitch,
+                          int ptrs_aligned4, const int32_t *dst_ids_dev = nullptr);
 int svs_i_copy_level0(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
-                      int n, const PyrDesc &d, const uint8_t *const *src_ptrs_dev = nullptr);
-int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images);
+                      int n, const PyrDesc &d, const uint8_t *const *src_ptrs_dev = nullptr, const int32_t *dst_ids_dev = nullptr);
+int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images, const int32_t *img_ids_dev = nullptr);
 // gftt.cu
 int svs_i_gftt(svs_ctx *c, const uint8_t *img_dev, int w, int h, int stride, size_t img_pitch, int n_img,
                const int32_t *img_ids_dev /* may be null: identity */,

@@ -69,7 +69,7 @@ public:
     // host bookkeeping by section: begin+prepare track | finish track+prepare pose | finish pose+prepare detect |
     // finish detect+prepare right | finish right+prepare triangulate | finish triangulate+prepare BA | finish BA+end
     double t_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long frames = 0, keyframes = 0, ba_problems = 0, ba_iterations = 0, ba_trials = 0, ba_edges = 0, ba_lms = 0, ba_kfs = 0, lk_points = 0, pose_edges = 0;
+    long long frames = 0, keyframes = 0, ba_problems = 0, ba_iterations = 0, ba_trials = 0, ba_edges = 0, ba_lms = 0, ba_kfs = 0, lk_points = 0, pose_edges = 0, right_images = 0;
 
 private:
     svs_ctx *ctx_;
@@ -80,7 +80,7 @@ private:
     double baseline_ = 0;
     Camera::Ptr cam_left_, cam_right_;
     std::vector<Stream> streams_;
-    std::vector<const uint8_t *> next_left_, next_right_;
+    std::vector<const uint8_t *> next_left_, next_right_, rptr_;
     bool has_next_ = false;
     // gather buffers
     std::vector<int32_t> off_, off2_, off3_, ids_;
@@ -100,11 +100,12 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
 {
     const int B = n();
     double t0 = now_s(), t1;
-    int rc = svs_frameset_push_ptrs(ctx_, fs_, left, right, row_stride, on_device);
+    const bool lazy = cfg_.lazy_right_ingest != 0;
+    int rc = svs_frameset_push_ptrs(ctx_, fs_, left, lazy ? nullptr : right, row_stride, on_device);
     if (rc) return rc;
     if (has_next_) {   // double buffering: the next pair's PCIe transfer / resize / pyramids overlap this step's kernels
         has_next_ = false;
-        if ((rc = svs_frameset_prefetch_ptrs(ctx_, fs_, next_left_.data(), next_right_.data(), row_stride, on_device))) return rc;
+        if ((rc = svs_frameset_prefetch_ptrs(ctx_, fs_, next_left_.data(), lazy ? nullptr : next_right_.data(), row_stride, on_device))) return rc;
     }
     t1 = now_s(); t_phase[0] += t1 - t0; t0 = t1;
 
@@ -230,6 +231,14 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         s.frontend->prepare_FindFeaturesInRight(s.lk);
     }
     t1 = now_s(); t_phase[7] += t1 - t0; t_host[3] += t1 - t0; t0 = t1;
+    if (lazy) {   // the right image is needed now, and only by the streams that are inserting a keyframe (or initialising)
+        ids_.clear(); rptr_.clear();
+        for (int b = 0; b < B; b++) if (streams_[b].ran_detect) { ids_.push_back(b); rptr_.push_back(right[b]); }
+        right_images += (long long)ids_.size();
+        if ((rc = svs_frameset_fetch_right_ptrs(ctx_, fs_, ids_.data(), (int)ids_.size(), rptr_.data(), row_stride, on_device))) return rc;
+    } else {
+        right_images += B;
+    }
     if ((rc = run_lk(1, [](const Stream &s) { return s.ran_detect; }))) return rc;
     t1 = now_s(); t_phase[4] += t1 - t0; t0 = t1;
     // ---------------- triangulation of new landmarks (src/frontend.cpp:174, :286)
@@ -355,6 +364,7 @@ svs_slam *svs_slam_create(svs_ctx *ctx, int n_streams, int in_w, int in_h, int h
     cfg.gftt_min_distance = c->gftt_min_distance; cfg.lk_win = c->lk_win; cfg.lk_max_level = c->lk_max_level;
     cfg.lk_max_iter = c->lk_max_iter; cfg.lk_eps = c->lk_eps; cfg.ba_max_iter = c->ba_max_iter;
     cfg.ba_jacobian_mode = c->ba_jacobian_mode; cfg.oracle_simd_granule = c->oracle_simd_granule;
+    cfg.lazy_right_ingest = c->lazy_right_ingest;
     svs_slam *s = new (std::nothrow) svs_slam();
     if (!s) return nullptr;
     s->ctx = ctx;
@@ -381,6 +391,7 @@ void svs_slam_default_config(svs_slam_config *c)
     c->gftt_min_distance = d.gftt_min_distance; c->lk_win = d.lk_win; c->lk_max_level = d.lk_max_level;
     c->lk_max_iter = d.lk_max_iter; c->lk_eps = d.lk_eps; c->ba_max_iter = d.ba_max_iter;
     c->ba_jacobian_mode = d.ba_jacobian_mode; c->oracle_simd_granule = d.oracle_simd_granule;
+    c->lazy_right_ingest = d.lazy_right_ingest; c->reserved_ = 0;
 }
 
 int svs_slam_add_frames(svs_slam *s, const uint8_t *const *left, const uint8_t *const *right, size_t row_stride, int on_device,
@@ -448,7 +459,7 @@ int svs_slam_get_landmarks(svs_slam *s, int stream, int active_only, int64_t *id
     return SVS_OK;
 }
 
-int svs_slam_get_counters(svs_slam *s, double *phase_seconds /* 8 */, long long *counters /* 10 */)
+int svs_slam_get_counters(svs_slam *s, double *phase_seconds /* 8 */, long long *counters /* 12 */)
 {
     if (!s) return SVS_ERR_ARG;
     slam::StreamBatch &b = *s->batch;
@@ -457,6 +468,7 @@ int svs_slam_get_counters(svs_slam *s, double *phase_seconds /* 8 */, long long 
         counters[0] = b.frames; counters[1] = b.keyframes; counters[2] = b.ba_problems;
         counters[3] = b.ba_iterations; counters[4] = b.ba_trials; counters[5] = b.ba_edges;
         counters[6] = b.ba_lms; counters[7] = b.ba_kfs; counters[8] = b.lk_points; counters[9] = b.pose_edges;
+        counters[10] = svs_frameset_h2d_bytes(b.frameset()); counters[11] = b.right_images;
     }
     return SVS_OK;
 }

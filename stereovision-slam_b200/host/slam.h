@@ -249,6 +249,9 @@ struct Config {
     double lk_eps = 0.01;
     int ba_max_iter = 10, ba_jacobian_mode = 0;                  // src/backend.cpp:164
     int oracle_simd_granule = 32;
+    // The frontend reads the right image only in FindFeaturesInRight (keyframes / init): ingest it only then (identical
+    // results, about half the image traffic).  0 = ingest both eyes of every frame like Dataset::NextFrame.
+    int lazy_right_ingest = 1;
 };
 
 enum class FrontendStatus { INITING, TRACKING_GOOD, TRACKING_BAD, LOST };

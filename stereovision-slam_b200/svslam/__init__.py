@@ -107,7 +107,7 @@ class FrameSet:
         """One pointer per stream.  on_device: 0 host (staged DMA), 1 device, 2 pinned host read zero-copy over PCIe."""
         n = self.n_streams
         lp = (C.c_void_p * n)(*[int(x) for x in left_ptrs])
-        rp = (C.c_void_p * n)(*[int(x) for x in right_ptrs])
+        rp = (C.c_void_p * n)(*[int(x) for x in right_ptrs]) if right_ptrs is not None else None     # None: left eye only
         self.ctx._chk(self.ctx.lib.svs_frameset_push_ptrs(
             C.c_void_p(self.ctx.h), C.c_void_p(self.h), lp, rp, C.c_size_t(row_stride or self.in_w), int(on_device)))
 
@@ -115,9 +115,16 @@ class FrameSet:
         """Start the ingest of the NEXT pair on the ingest stream (svs_frameset_prefetch_ptrs)."""
         n = self.n_streams
         lp = (C.c_void_p * n)(*[int(x) for x in left_ptrs])
-        rp = (C.c_void_p * n)(*[int(x) for x in right_ptrs])
+        rp = (C.c_void_p * n)(*[int(x) for x in right_ptrs]) if right_ptrs is not None else None
         self.ctx._chk(self.ctx.lib.svs_frameset_prefetch_ptrs(
             C.c_void_p(self.ctx.h), C.c_void_p(self.h), lp, rp, C.c_size_t(row_stride or self.in_w), int(on_device)))
+
+    def fetch_right_ptrs(self, stream_ids, right_ptrs, on_device, row_stride=None):
+        """Lazy right-eye ingest for the selected streams (svs_frameset_fetch_right_ptrs)."""
+        ids = np.ascontiguousarray(stream_ids, np.int32)
+        rp = (C.c_void_p * len(ids))(*[int(x) for x in right_ptrs])
+        self.ctx._chk(self.ctx.lib.svs_frameset_fetch_right_ptrs(
+            C.c_void_p(self.ctx.h), C.c_void_p(self.h), _p(ids), len(ids), rp, C.c_size_t(row_stride or self.in_w), int(on_device)))
 
     def download(self, stream, which, level):
         w, h = self.w, self.hgt
@@ -342,7 +349,8 @@ class SlamConfig(C.Structure):
         "num_features", "num_features_init", "num_features_tracking", "num_features_tracking_bad",
         "num_features_needed_for_keyframe", "num_active_keyframes", "backend_on", "lk_win", "lk_max_level",
         "lk_max_iter", "ba_max_iter", "ba_jacobian_mode", "oracle_simd_granule")] + [(n, C.c_double) for n in (
-        "max_triangulation_depth", "chi2_th", "gftt_quality", "gftt_min_distance", "lk_eps")]
+        "max_triangulation_depth", "chi2_th", "gftt_quality", "gftt_min_distance", "lk_eps")] + [
+        ("lazy_right_ingest", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Slam:
@@ -432,10 +440,11 @@ class Slam:
         return ids[:n.value].copy(), xyz[:n.value].copy(), ot[:n.value].copy()
 
     def counters(self):
-        ph = np.zeros(8); cn = np.zeros(10, np.int64)
+        ph = np.zeros(8); cn = np.zeros(12, np.int64)
         self.ctx._chk(self.ctx.lib.svs_slam_get_counters(C.c_void_p(self.h), _p(ph), _p(cn)))
         names = ("push", "track_lk", "pose_lm", "detect", "right_lk", "triangulate", "ba", "host")
-        cnames = ("frames", "keyframes", "ba_problems", "ba_iterations", "ba_trials", "ba_edges", "ba_lms", "ba_kfs", "lk_points", "pose_edges")
+        cnames = ("frames", "keyframes", "ba_problems", "ba_iterations", "ba_trials", "ba_edges", "ba_lms", "ba_kfs", "lk_points", "pose_edges",
+                  "h2d_image_bytes", "right_images")
         phases = dict(zip(names, ph.tolist()))
         hs = np.zeros(8)
         self.ctx._chk(self.ctx.lib.svs_slam_get_host_seconds(C.c_void_p(self.h), _p(hs)))

@@ -169,6 +169,44 @@ def test_frameset_prefetch(ctx, mode):
     del t_
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("half", [True, False])
+def test_frameset_lazy_right(ctx, mode, half):
+    """Left-only push / prefetch + svs_frameset_fetch_right_ptrs for a subset of the streams: the fetched right pyramids
+    equal the oracle's, the other streams' right buffers are untouched, the left buffers behave as in a full push."""
+    import torch
+    B, H, W, T = 5, 370, 1226, 3
+    buf = np.stack([np.stack([np.stack([texture(H, W, 500 * e + 7 * t + b) for b in range(B)]) for t in range(T)]) for e in range(2)])
+    t_ = torch.from_numpy(buf)
+    t_ = t_.cuda() if mode == 1 else (t_.pin_memory() if mode == 2 else t_)
+    base = t_.data_ptr()
+    ptr = lambda e, t: [base + ((e * T + t) * B + b) * H * W for b in range(B)]
+    prep = (lambda im: o.half_nearest(im)) if half else (lambda im: im)
+    want = lambda e, t, b, lvl: o.build_pyramid(prep(buf[e, t, b]))[lvl]
+    fs = ctx.frameset(B, W, H, half=half)
+    try:
+        fs.push_ptrs(ptr(0, 0), ptr(1, 0), mode)                     # full push: both eyes of frame 0
+        fs.push_ptrs(ptr(0, 1), None, mode)                          # left only
+        fs.prefetch_ptrs(ptr(0, 2), None, mode)
+        sel = [3, 0]
+        fs.fetch_right_ptrs(sel, [ptr(1, 1)[b] for b in sel], mode)  # right images of frame 1 for streams 3 and 0
+        for b in range(B):
+            for lvl in range(fs.n_levels):
+                assert np.array_equal(fs.download(b, 0, lvl), want(0, 1, b, lvl)), (b, lvl)
+                assert np.array_equal(fs.download(b, 1, lvl), want(0, 0, b, lvl)), (b, lvl)
+        for b in sel:
+            for lvl in range(fs.n_levels):
+                assert np.array_equal(fs.download(b, 2, lvl), want(1, 1, b, lvl)), (b, lvl)
+        fs.push_ptrs(ptr(0, 2), None, mode)                          # prefetch hit (left only)
+        fs.fetch_right_ptrs([4], [ptr(1, 2)[4]], mode)
+        assert np.array_equal(fs.download(4, 0, 1), want(0, 2, 4, 1))
+        assert np.array_equal(fs.download(4, 1, 0), want(0, 1, 4, 0))
+        assert np.array_equal(fs.download(4, 2, 2), want(1, 2, 4, 2))
+    finally:
+        fs.close()
+    del t_
+
+
 @pytest.mark.parametrize("h,w,seed", [(188, 620, 1), (185, 613, 2), (376, 1241, 3), (30, 40, 4)])
 def test_lk_bit_identical_to_oracle(ctx, h, w, seed):
     a, b = moved_pair(h, w, seed)

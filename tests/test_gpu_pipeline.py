@@ -129,15 +129,16 @@ def test_pipeline_free_running_accuracy(ctx, granule, clip):
 
 
 def test_prefetch_hint_gives_identical_results(ctx, granule, clip):
-    """svs_slam_hint_next (double-buffered ingest on the second stream) must not change a single bit of the results:
-    two pipelines over the same pinned frames, one with hints, one without."""
+    """svs_slam_hint_next (double-buffered ingest on the second stream) and the lazy right-eye ingest must not change a
+    single bit of the results: two pipelines over the same pinned frames, one with hints + lazy right images, one that
+    pushes both eyes of every frame without hints."""
     import torch
     cor, L, R, T = clip
     n = 14
     Lt, Rt = torch.from_numpy(L[:n + 1].copy()).pin_memory(), torch.from_numpy(R[:n + 1].copy()).pin_memory()
     img = cor.W * cor.H
     a = ctx.slam(2, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, oracle_simd_granule=granule)
-    b = ctx.slam(2, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, oracle_simd_granule=granule)
+    b = ctx.slam(2, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, oracle_simd_granule=granule, lazy_right_ingest=0)
     try:
         for i in range(n):
             # stream 1 lags one frame behind stream 0; mode alternates between zero-copy (2) and staged DMA (0)
@@ -153,6 +154,9 @@ def test_prefetch_hint_gives_identical_results(ctx, granule, clip):
         for s in range(2):
             assert np.array_equal(a.features(s)[0], b.features(s)[0])
             assert np.array_equal(a.landmarks(s)[1], b.landmarks(s)[1])
+        ca, cb = a.counters()[1], b.counters()[1]
+        assert cb["right_images"] == 2 * n and 2 <= ca["right_images"] < cb["right_images"]      # only init / keyframe steps
+        assert ca["h2d_image_bytes"] <= 0.8 * cb["h2d_image_bytes"]      # left eyes (+ one unconsumed prefetch) + a few right eyes
     finally:
         a.close(); b.close()
 
