@@ -119,3 +119,53 @@ def test_ba_recovers_ground_truth_without_noise():
     assert np.allclose(rel(p), rel(poses_true), atol=1e-5)
     in0 = lambda P, L: np.array([geom.se3_act(P[0], x) for x in L])
     assert rel_to_norm(in0(p, l), in0(poses_true, lms_true)).max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent cross-check: g2o cannot be imported, so the C restatement of its solvers is checked against a solver
+# that shares no code with it — scipy.optimize.least_squares on the same residuals (projection written here in NumPy,
+# finite-difference Jacobians, a different trust-region algorithm).  With small pixel noise and no gross outliers the
+# Huber kernel is inactive at the optimum, so both must reach the same minimum of sum ||uv - proj||^2.
+def _proj_np(T, pw, K, ext=None):
+    pc = quat_to_R(T[:4]) @ pw + T[4:]
+    if ext is not None:
+        pc = quat_to_R(ext[:4]) @ pc + ext[4:]
+    return np.array([K[0] * pc[0] / pc[2] + K[2], K[1] * pc[1] / pc[2] + K[3]])
+
+
+def test_pose_only_lm_minimum_matches_scipy():
+    from scipy.optimize import least_squares
+    pts, uv, K, T0, T_true = pose_problem(11, m=120, noise=0.2, outlier_frac=0.0)
+    T, outl, ninl, st = geom.pose_only_lm(pts, uv, K, T0)
+    assert outl.sum() == 0 and ninl == len(pts)
+
+    def res(x):            # left-multiplicative update of the oracle's result, like VertexPose::oplusImpl
+        Tx = geom.se3_mul(geom.se3_exp(x), T)
+        return np.concatenate([uv[i] - _proj_np(Tx, pts[i], K) for i in range(len(pts))])
+    sol = least_squares(res, np.zeros(6), method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15)
+    chi_oracle, chi_scipy = float((res(np.zeros(6)) ** 2).sum()), float((sol.fun ** 2).sum())
+    assert chi_oracle <= chi_scipy * (1 + 1e-9)                 # the oracle is at the minimum scipy finds ...
+    assert np.abs(sol.x).max() < 1e-6                           # ... and scipy cannot move the pose from it
+    assert abs(st.chi2 - chi_oracle) < 1e-6 * chi_oracle        # the solver's own chi2 is the chi2 of its pose
+
+
+def test_ba_minimum_matches_scipy():
+    from scipy.optimize import least_squares
+    prob, poses_true, lms_true = ba_problem(21, n_kf=4, n_lm=40, noise=0.2, outlier_frac=0.0, pose_sigma=(0.01, 0.001), lm_sigma=0.05)
+    args = (prob["poses"], prob["lms"], prob["edge_kf"], prob["edge_lm"], prob["edge_cam"], prob["edge_uv"], K05, K05, EXT_L, EXT_R)
+    p, l, c, s = geom.ba_optimize(*args, max_iter=60)
+    ekf, elm, ecam, euv = prob["edge_kf"], prob["edge_lm"], prob["edge_cam"], prob["edge_uv"]
+    nk, nl = len(p), len(l)
+
+    def res(x):
+        P = [geom.se3_mul(geom.se3_exp(x[6 * k:6 * k + 6]), p[k]) for k in range(nk)]
+        Lm = l + x[6 * nk:].reshape(nl, 3)
+        return np.concatenate([euv[e] - _proj_np(P[ekf[e]], Lm[elm[e]], K05, EXT_R if ecam[e] else EXT_L) for e in range(len(ekf))])
+    r0 = res(np.zeros(6 * nk + 3 * nl))
+    chi_oracle = float((r0 ** 2).sum())
+    assert abs(chi_oracle - float(np.sum(c))) < 1e-6 * chi_oracle and (c < 5.991).all()      # Huber inactive, chi2 output consistent
+    sol = least_squares(res, np.zeros(6 * nk + 3 * nl), method="trf", x_scale="jac", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=200)
+    chi_scipy = float((sol.fun ** 2).sum())
+    # the minimum VALUE is gauge-free (no vertex is fixed, 6 gauge freedoms): the oracle's LM after 60 iterations sits at it
+    assert chi_oracle <= chi_scipy * (1 + 1e-6)
+    assert chi_scipy >= chi_oracle * (1 - 1e-4)
