@@ -218,7 +218,7 @@ def save_clip(L, R):
     return path
 
 
-CPU_PRIME = 150
+CPU_PRIME = int(os.environ.get("SVS_CPU_PRIME", "150"))     # frames each CPU stream runs before it is timed (BA window full)
 
 
 def run_reference(args, rank, world):
