@@ -73,8 +73,8 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu, mode="nvml", period=0.2):
-        self.gpu, self.mode, self.period = gpu, mode, period
+    def __init__(self, gpu, mode="nvml", period=0.2, uuid=None):
+        self.gpu, self.mode, self.period, self.uuid = gpu, mode, period, uuid
         self.rows, self.proc, self.t, self.stop_flag = [], None, None, False
         self.sm, self.mx, self.reasons, self.power = [], [], set(), []
 
@@ -86,7 +86,14 @@ class ClockSampler:
                 import pynvml
                 pynvml.nvmlInit()
                 self.nv = pynvml
-                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+                self.h = None
+                if self.uuid:      # CUDA_VISIBLE_DEVICES may renumber the devices: NVML is addressed by UUID
+                    try:
+                        self.h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid.encode() if isinstance(self.uuid, str) else self.uuid)
+                    except Exception:
+                        self.h = None
+                if self.h is None:
+                    self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
                 self.t = threading.Thread(target=self._poll, daemon=True)
                 self.t.start()
                 return
@@ -474,7 +481,11 @@ def run_gpu(args, rank, world, local_rank):
     # three regions over the same workload: (1) frames resident in HBM -> value, (2) frames in pinned host memory -> e2e,
     # both with the clock sampler running and no per-kernel instrumentation; (3) device-resident again with every launch
     # bracketed by CUDA events on its stream -> per-kernel durations for the roofline block (not used for value / e2e)
-    sampler = ClockSampler(dev, args.sampler)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(dev, args.sampler, uuid=gpu_uuid)
     sampler.start()
     dev_pass = timed_region(True, False)
     e2e_pass = timed_region(False, False)
