@@ -47,6 +47,19 @@ void orc_se3_act(const double *T, const double *p, double *o)
     quat_rot(T, p, r);
     o[0] = r[0] + T[4]; o[1] = r[1] + T[5]; o[2] = r[2] + T[6];
 }
+/* Camera::world2pixel (src/camera.cpp:74-80) for n points: pixel = K * (ext * (T * p)), the same operations in the same
+ * order as one orc_se3_act per transform followed by fx * x / z + cx (batched so that the Python pipeline does not pay one
+ * foreign call per feature) */
+void orc_world2pixel_batch(const double *T, const double *ext, const double *K, int n, const double *pw, double *uv)
+{
+    for (int i = 0; i < n; i++) {
+        double a[3], c[3];
+        orc_se3_act(T, pw + 3 * i, a);
+        orc_se3_act(ext, a, c);
+        uv[2 * i] = K[0] * c[0] / c[2] + K[2];
+        uv[2 * i + 1] = K[1] * c[1] / c[2] + K[3];
+    }
+}
 void orc_se3_mul(const double *A, const double *B, double *C)
 { /* C = A * B ; Sophus SO3 product with first-order renormalisation */
     double ax = A[0], ay = A[1], az = A[2], aw = A[3];

@@ -132,6 +132,16 @@ def se3_act(T, p):
     return o
 
 
+def world2pixel_batch(T, ext, K4, pts_w):
+    """Camera::world2pixel for n points (bit-identical to se3_act(ext, se3_act(T, p)) + projection per point)."""
+    pts = np.ascontiguousarray(pts_w, np.float64).reshape(-1, 3)
+    out = np.zeros((len(pts), 2))
+    if len(pts):
+        lib().orc_world2pixel_batch(_p(np.ascontiguousarray(T, np.float64)), _p(np.ascontiguousarray(ext, np.float64)),
+                                    _p(np.ascontiguousarray(K4, np.float64)), len(pts), _p(pts), _p(out))
+    return out
+
+
 def triangulate(left_xy, right_xy, K_left, K_right, baseline):
     """slam::triangulation for a rectified pair (include/StereoVisionSLAM/algorithm.h:59-86) with
     the callers' pixel2camera (src/camera.cpp:58-72): left extrinsic identity, right [I | (-b,0,0)].

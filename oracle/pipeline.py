@@ -177,9 +177,9 @@ class Pipeline:
             f.pyr_r = self._pyr(f.right)
         prev = np.array([[p.x, p.y] for p in f.fl], F32).reshape(-1, 2)
         init = prev.copy()
-        for i, p in enumerate(f.fl):
-            if p.mp is not None:
-                init[i] = self.world2pixel(p.mp.pos, f.pose, True).astype(F32)
+        idx = [i for i, p in enumerate(f.fl) if p.mp is not None]
+        if idx:
+            init[idx] = geom.world2pixel_batch(f.pose, self.ext_r, self.K, np.array([f.fl[i].mp.pos for i in idx])).astype(F32)
         nxt, st = self._lk(f.left, f.right, f.pyr_l, f.pyr_r, prev, init)
         H, W = f.right.shape
         good = 0
@@ -241,9 +241,9 @@ class Pipeline:
         # TrackLastFrame
         prev = np.array([[p.x, p.y] for p in last.fl], F32).reshape(-1, 2)
         init = prev.copy()
-        for i, p in enumerate(last.fl):
-            if p.mp is not None:
-                init[i] = self.world2pixel(p.mp.pos, f.pose, False).astype(F32)
+        idx = [i for i, p in enumerate(last.fl) if p.mp is not None]
+        if idx:     # one batched projection (same arithmetic as world2pixel per point)
+            init[idx] = geom.world2pixel_batch(f.pose, self.ext_l, self.K, np.array([last.fl[i].mp.pos for i in idx])).astype(F32)
         nxt, st = self._lk(last.left, f.left, last.pyr_l, f.pyr_l, prev, init)
         H, W = f.left.shape
         for i in range(len(last.fl)):
