@@ -604,6 +604,23 @@ def run_gpu(args, rank, world, local_rank):
                 "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": ms_tot / max(1, n_l), "launches": n_l,
                 "algorithmic_bytes_per_launch": alg_total[dom] / max(1, n_l), "peak_source": peak_src,
                 "note": "launch durations overlap across %d context groups; actual limiter: %s (DESIGN.md §4)" % (G, limiter)}
+    # per-kernel roofline view: (a) live — algorithmic bytes / summed event-bracketed durations of the instrumented region
+    # (inflated by queueing behind the other groups' kernels), (b) stand-alone — the committed ncu capture of one context
+    kernel_roofline = {}
+    for k, (ms_k, n_k) in kern.items():
+        if k in alg_total and ms_k > 0:
+            a = alg_total[k] / (ms_k * 1e-3) / 1e9
+            kernel_roofline[k] = {"live_gbs": round(a, 2), "live_frac": round(a / peak, 5), "launches": n_k}
+    try:
+        import csv as _csv
+        for row in _csv.DictReader(l for l in open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.csv")) if not l.startswith("#")):
+            k = row["kernel"].replace("void ", "").split("<")[0]
+            kernel_roofline.setdefault(k, {}).setdefault("ncu_standalone", {
+                "dur_us": float(row["dur_us"]), "dram_MB": round(float(row["dram_rd_MB"]) + float(row["dram_wr_MB"]), 3),
+                "dram_pct": float(row["dram_pct"]), "issue_active_pct": float(row["issue_active_pct"]),
+                "fp64_pipe_pct": float(row["fp64_pipe_pct"]), "registers": float(row["regs"])})
+    except Exception:
+        pass
     dev_total = sum(v[0] for v in kern.values())
     shares = {k: round(v[0] / dev_total, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])} if dev_total else {}
 
@@ -652,7 +669,7 @@ def run_gpu(args, rank, world, local_rank):
         "detail": {"phase_seconds": {k: round(v, 4) for k, v in dev_pass["phases"].items()},
                    "e2e_phase_seconds": {k: round(v, 4) for k, v in e2e_pass["phases"].items()},
                    "counts": dev_pass["counts"], "kernel_ms": {k: [round(v[0], 3), v[1]] for k, v in kern.items()},
-                   "kernel_time_share": shares, "ncu_serialized_share": ncu_share, "kernel_pass_ms_per_step": kern_pass["ms"] / args.steps,
+                   "kernel_time_share": shares, "ncu_serialized_share": ncu_share, "kernel_roofline": kernel_roofline, "kernel_pass_ms_per_step": kern_pass["ms"] / args.steps,
                    "summed_kernel_ms_over_wall_ms": dev_total / kern_pass["ms"] if kern_pass["ms"] else None,
                    "lost_streams": dev_pass["lost"], "host_cores": cores, "host_threads_per_group": host_threads,
                    "ba_lm_iterations_per_sec": dev_pass["counts"]["ba_iterations"] * world / (dev_pass["ms"] * 1e-3),
