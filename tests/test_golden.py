@@ -46,3 +46,39 @@ def test_cuda_matches_golden(ctx):
     assert np.abs(q[ok] - G["lk_p1"][ok]).max() < 1e-3
     assert np.array_equal(ctx.stereo_bm(G["bm_l"], G["bm_r"], 128, 15), G["bm_disp"])
     assert np.array_equal(ctx.bgr2gray(G["bgr"]), G["gray"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FP64 geometry: committed outputs of the C oracle (tests/golden/make_golden_geom.py).  g2o cannot be imported, so this
+# pins the oracle build itself (any box, any compiler must reproduce the vectors) and the CUDA path against fixed numbers.
+GG = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_geom.npz"))
+_K05 = np.array([707.0912 * 0.5, 707.0912 * 0.5, 601.8873 * 0.5, 183.1104 * 0.5])
+_EXT_L, _EXT_R, _BASE = np.array([0, 0, 0, 1, 0, 0, 0.0]), np.array([0, 0, 0, 1, -0.5371657, 0, 0.0]), 0.5371657
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+def test_oracle_geometry_matches_golden():
+    xyz, ok = geom.triangulate(GG["tri_l"], GG["tri_r"], _K05, _K05, _BASE)
+    assert np.array_equal(ok, GG["tri_ok"]) and _rel(xyz[ok == 1], GG["tri_xyz"][ok == 1]) < 1e-12
+    T, outl, ninl, st = geom.pose_only_lm(GG["po_pts"], GG["po_uv"], GG["po_K"], GG["po_T0"])
+    assert np.array_equal(outl, GG["po_outlier"]) and ninl == int(GG["po_ninl"]) and _rel(T, GG["po_T"]) < 1e-10
+    P, L, chi2, sb = geom.ba_optimize(GG["ba_poses"], GG["ba_lms"], GG["ba_edge_kf"], GG["ba_edge_lm"], GG["ba_edge_cam"], GG["ba_edge_uv"],
+                                      _K05, _K05, _EXT_L, _EXT_R)
+    assert (sb.iterations, sb.trials) == (int(GG["ba_stats"][0]), int(GG["ba_stats"][1]))
+    assert abs(sb.chi2 - GG["ba_stats"][2]) < 1e-9 * GG["ba_stats"][2] and _rel(P, GG["ba_P"]) < 1e-9 and _rel(L, GG["ba_L"]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_geometry_matches_golden(ctx):
+    xyz, ok = ctx.triangulate(GG["tri_l"], GG["tri_r"], _K05, _K05, _BASE)
+    assert np.array_equal(ok, GG["tri_ok"]) and _rel(xyz[ok == 1], GG["tri_xyz"][ok == 1]) < 1e-9
+    (T, outl, ninl, st), = ctx.pose_only_lm([(GG["po_pts"], GG["po_uv"], GG["po_K"], GG["po_T0"])])
+    assert np.array_equal(outl, GG["po_outlier"]) and ninl == int(GG["po_ninl"]) and _rel(T, GG["po_T"]) < 1e-8
+    prob = {k[3:]: GG[k] for k in ("ba_poses", "ba_lms", "ba_edge_kf", "ba_edge_lm", "ba_edge_cam", "ba_edge_uv")}
+    (P, L, chi2, sb), = ctx.ba_optimize([prob], _K05, _K05, _EXT_L, _EXT_R)
+    assert (sb.iterations, sb.trials) == (int(GG["ba_stats"][0]), int(GG["ba_stats"][1]))
+    assert abs(sb.chi2 - GG["ba_stats"][2]) < 1e-8 * GG["ba_stats"][2] and _rel(P, GG["ba_P"]) < 1e-7 and _rel(L, GG["ba_L"]) < 1e-7
+    assert np.abs(chi2 - GG["ba_chi2"]).max() < 1e-6 * max(1.0, GG["ba_chi2"].max())
