@@ -1,6 +1,6 @@
 """Per-frame diff trace: GPU pipeline vs CPU oracle pipeline (debug aid)."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "stereovision-slam_b200"))
 import numpy as np, cv2
 import svslam
