@@ -57,3 +57,10 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 s = open(os.path.join(dp, f), errors="ignore").read()
                 assert not bad.search(s), f
+    # tools and examples are not allowed to lean on the checker either (only tests/, smoke() and bench.py's CPU legs are)
+    for sub in ("scripts", "examples", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, sub)):
+            for f in fs:
+                if f.endswith((".py", ".c", ".cpp", ".h", ".sh")):
+                    s = open(os.path.join(dp, f), errors="ignore").read()
+                    assert not bad.search(s), os.path.join(sub, f)
