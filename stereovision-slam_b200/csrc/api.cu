@@ -113,9 +113,8 @@ const char *svs_create_error(void) { return g_create_err.c_str(); }
 svs_ctx *svs_create(int device)
 {
     std::lock_guard<std::mutex> create_lock(g_mutex);
-    // one hardware work queue per stream (a context owns two): with the default of 8, streams of different contexts share
-    // a queue and wait behind each other's long ingest kernels.  Only effective if the CUDA context does not exist yet.
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // (CUDA_DEVICE_MAX_CONNECTIONS is the application's to set — bench.py does — a drop-in library must not edit the
+    // process environment.)
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -125,7 +124,9 @@ svs_ctx *svs_create(int device)
     if (device < 0 || device >= n) { g_create_err = "device index out of range"; return nullptr; }
     cudaDeviceProp p;
     if ((e = cudaGetDeviceProperties(&p, device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return nullptr; }
-    if (p.major != 10) {
+    // the library carries ONE cubin, sm_100a: arch-specific ("a") targets are not forward compatible, so any other 10.x part
+    // would fail at the first launch with "no kernel image" instead of here
+    if (p.major != 10 || p.minor != 0) {
         g_create_err = "this library is built for sm_100a (B200) only; found compute capability " +
                        std::to_string(p.major) + "." + std::to_string(p.minor);
         return nullptr;
@@ -157,7 +158,7 @@ void svs_destroy(svs_ctx *c)
     c->h_in.release(); c->h_out.release();
     cudaStreamDestroy(c->stream);
     if (c->stream_in) cudaStreamDestroy(c->stream_in);
-    g_live_ctx--;
+    { std::lock_guard<std::mutex> lk(g_mutex); g_live_ctx--; }
     delete c;
 }
 

@@ -68,6 +68,13 @@ k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc
     float px0 = prev_xy[2 * pt], py0 = prev_xy[2 * pt + 1];
     float nxt_x = next_xy[2 * pt], nxt_y = next_xy[2 * pt + 1];
     bool st = true;
+    // cvFloor(NaN) is INT_MIN in OpenCV (cvtss2si's "integer indefinite"), so a non-finite start point fails every bounds
+    // test below and ends with status 0; __float2int_rd maps NaN to 0 instead.  Inf / huge values saturate to an
+    // out-of-range integer either way, so only NaN needs the explicit exit (warp-uniform: one keypoint per warp).
+    if (px0 != px0 || py0 != py0 || nxt_x != nxt_x || nxt_y != nxt_y) {
+        if (lane == 0) status[pt] = 0;
+        return;
+    }
     uint8_t *mI = sI[warp], *mJ = sJ[warp];
     short2 *mD = sD[warp], *mT = sT[warp];
     int nlev = min(prev.nlev, next.nlev);

@@ -190,7 +190,7 @@ int Frontend::finish_TrackLastFrame(const LkRequest &rq)
     for (size_t i = 0; i < n; i++) {
         if (!rq.status[i]) continue;
         float x = rq.next_xy[2 * i], y = rq.next_xy[2 * i + 1];
-        if (y < 0 || y >= h || x < 0 || x >= w) continue;
+        if (!(y >= 0 && y < h && x >= 0 && x < w)) continue;      // written positively: NaN is out of bounds
         Feature &f = out[num_good_pts++];
         f.x = x; f.y = y; f.size = 7;
         f.map_point_ = lf[i].map_point_;

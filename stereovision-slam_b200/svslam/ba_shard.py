@@ -30,6 +30,9 @@ class Shard:
         self.red = torch.zeros(36 * self.N * self.N + 6 * self.N, dtype=torch.float64, device=dev)
         self.flag = torch.ones(1, dtype=torch.int32, device=dev)
         self.tri = torch.zeros(4, dtype=torch.float64, device=dev)
+        # the fills above run on torch's current stream, the svs_ba_shard_* kernels on the context's own non-blocking stream:
+        # nothing else orders the two, so the fills must have landed before the first kernel writes these buffers
+        torch.cuda.synchronize(dev)
 
     def _v(self, t):
         return C.c_void_p(t.data_ptr())

@@ -221,7 +221,37 @@ def test_lk_bit_identical_to_oracle(ctx, h, w, seed):
                                          flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
     assert np.array_equal(st.ravel(), s)
     ok = s == 1
-    assert np.abs(p1[ok] - q[ok]).max() < 1e-3       # cv2 sums the same integers in f32 lanes
+    # cv2 sums the same integers in f32 SIMD lanes, the engine sums them exactly.  Measured on these inputs (the engine is
+    # bit-identical to the oracle, so this is also oracle vs cv2): 96-99 % of the points bit-identical, median and q95 of
+    # the per-point difference 0, q99 <= 2.7e-5 px (the survey's 2e-5 figure), maximum 1.8e-4 px (one flipped
+    # convergence decision amplified towards LK's own 0.01-px stopping threshold).  Asserted with 2x head room.
+    d = np.abs(p1[ok] - q[ok]).max(1)
+    if h > 40:
+        assert (d == 0).mean() >= 0.93, (d == 0).mean()
+        assert np.quantile(d, 0.95) == 0.0
+        assert np.quantile(d, 0.99) <= 6e-5, np.quantile(d, 0.99)
+    assert d.max() < 4e-4, d.max()
+
+
+def test_lk_nonfinite_points_are_lost(ctx):
+    """cvFloor(NaN) is INT_MIN in OpenCV: a non-finite previous point or initial guess (world2pixel with z == 0, a
+    degenerate triangulation) fails every bounds test and comes back with status 0 and its input value."""
+    a, b = moved_pair(188, 620, 1)
+    p0 = np.array([[100, 100], [np.nan, 50], [200, np.nan], [300, 80], [np.inf, 60], [50, 60], [-np.inf, 20], [1e20, 30],
+                   [150, 90]], np.float32)
+    init = p0.copy()
+    init[3] = [np.nan, 80]; init[5] = [50, np.inf]
+    q, s = ctx.lk_track(a, b, p0, init)
+    p1, st, _ = cv2.calcOpticalFlowPyrLK(a, b, p0, init.copy(), winSize=(11, 11), maxLevel=3,
+                                         criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01),
+                                         flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+    wq, ws, _ = geom.lk_track(o.build_pyramid(a), o.build_pyramid(b), p0, init)
+    assert list(s) == [1, 0, 0, 0, 0, 0, 0, 0, 1]
+    assert np.array_equal(s, st.ravel()) and np.array_equal(s, ws)
+    assert np.array_equal(q[s == 1].view(np.uint32), wq[s == 1].view(np.uint32))
+    lost = s == 0                       # lost points keep their input value, like cv2 (NaN / inf / 1e20 unchanged)
+    assert np.array_equal(np.isnan(q[lost]), np.isnan(p1[lost]))
+    assert np.array_equal(q[lost][~np.isnan(q[lost])], p1[lost][~np.isnan(p1[lost])])
 
 
 def test_lk_batch_pairs(ctx):
