@@ -69,9 +69,10 @@ k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc
     float nxt_x = next_xy[2 * pt], nxt_y = next_xy[2 * pt + 1];
     bool st = true;
     // cvFloor(NaN) is INT_MIN in OpenCV (cvtss2si's "integer indefinite"), so a non-finite start point fails every bounds
-    // test below and ends with status 0; __float2int_rd maps NaN to 0 instead.  Inf / huge values saturate to an
-    // out-of-range integer either way, so only NaN needs the explicit exit (warp-uniform: one keypoint per warp).
-    if (px0 != px0 || py0 != py0 || nxt_x != nxt_x || nxt_y != nxt_y) {
+    // test below and ends with status 0 and its input value; __float2int_rd maps NaN to 0 instead.  Inf saturates to an
+    // out-of-range integer either way but would drag the other coordinate through the iterations: NaN and inf both leave
+    // here (warp-uniform: one keypoint per warp).
+    if (!(fabsf(px0) <= FLT_MAX && fabsf(py0) <= FLT_MAX && fabsf(nxt_x) <= FLT_MAX && fabsf(nxt_y) <= FLT_MAX)) {
         if (lane == 0) status[pt] = 0;
         return;
     }

@@ -57,10 +57,26 @@ def test_ba_window_vs_oracle(ctx, n_kf, n_lm):
                 assert np.abs(P - wP).max() < tol * 10 and rel_to_norm(L, wL).max() < tol
                 assert np.abs(chi2 - wchi2).max() < 1e-7 * max(1.0, wchi2.max())
             else:
-                # numeric Jacobians (g2o's default for this edge): only reproducible to ~1e-4 relative-to-norm
-                assert np.quantile(rel_to_norm(L, wL), 0.95) < 1e-3
-                assert np.abs(cen(P) - cen(wP)).max() < 2e-2
-                assert abs(st.chi2 - wst.chi2) < 1e-3 * wst.chi2
+                # numeric Jacobians (g2o's default for this edge, the reference's actual mode).  The delta = 1e-9 quotient
+                # makes the result reproducible only to ~1e-4 relative-to-norm: that IS the north_star
+                # contract, asserted here on the median and the 95 % quantile.  Measured over 6 seeds x 4 problem sizes
+                # (tests/tools/diag_numeric_ba.py on a B200): windows of 10-20 keyframes: landmark median <= 1.8e-5,
+                # q95 <= 7.5e-5, camera centres <= 1.1e-3 m over a 10-20 m window (<= 8e-5 of its extent), chi2 <= 9e-6.
+                rl = rel_to_norm(L, wL)
+                dc = np.linalg.norm(cen(P) - cen(wP), axis=1).max() / max(1.0, np.linalg.norm(cen(wP), axis=1).max())
+                if len(pr["poses"]) >= 10:
+                    assert np.median(rl) < 1e-4 and np.quantile(rl, 0.95) < 1e-4, (np.median(rl), np.quantile(rl, 0.95))
+                    assert dc < 1e-4, dc
+                    assert abs(st.chi2 - wst.chi2) < 1e-4 * wst.chi2
+                else:
+                    # 4-6 keyframes, 40-80 landmarks and no gauge fixed: the oracle's OWN numeric and analytic results
+                    # differ by up to 5e-4 here, i.e. the reference's output is not defined more finely than that — the
+                    # engine must sit within 3x that spread
+                    aP, aL, _, _ = geom.ba_optimize(pr["poses"], pr["lms"], pr["edge_kf"], pr["edge_lm"], pr["edge_cam"],
+                                                    pr["edge_uv"], K05, K05, EXT_L, EXT_R, jac_mode=0)
+                    spread = np.quantile(rel_to_norm(wL, aL), 0.95)
+                    assert np.quantile(rl, 0.95) < 3 * spread + 1e-4, (np.quantile(rl, 0.95), spread)
+                    assert abs(st.chi2 - wst.chi2) < 1e-3 * wst.chi2
     # inactive vertices stay untouched
     P, L, _, _ = res[2]
     assert np.array_equal(P[0], probs[2]["poses"][0]) and np.array_equal(L[-3:], probs[2]["lms"][-3:])

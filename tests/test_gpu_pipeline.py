@@ -109,6 +109,42 @@ def test_pipeline_window_eviction_lockstep(ctx, granule, clip):
         slam.close()
 
 
+def test_pipeline_window20_lockstep(ctx, granule, clip):
+    """BASELINE config 3 (num_active_keyframes = 20, an override of config/stereo_slam_configs/default.yaml:27): the
+    whole pipeline, teacher-forced.  num_features_needed_for_keyframe is raised so that EVERY frame is a keyframe: the
+    20-keyframe window is full after 20 frames and evicts on each of the remaining 16 (BA over ~10 k edges, a 120x120
+    reduced system)."""
+    cor, L, R, T = clip
+    kw = dict(num_active_keyframes=20, num_features_needed_for_keyframe=1000)
+    slam = ctx.slam(1, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, oracle_simd_granule=granule, **kw)
+    o = op.Pipeline(cor.K_half(), cor.baseline, op.Cfg(granule=granule, **kw), stages="oracle")
+    try:
+        worst = 0.0
+        for i in range(N_FRAMES):
+            est = slam.add_frames(L[i:i + 1], R[i:i + 1])[0].copy()
+            west = o.add_frame(L[i], R[i])
+            assert slam.status[0] == o.status and bool(slam.is_kf[0]) == o.is_kf and (i == 0 or slam.inliers[0] == o.tracking_inliers), i
+            assert np.abs(est - west).max() < 1e-5 * max(1.0, np.abs(west).max()), i
+            xy, ids, _ = slam.features(0)
+            wxy, wids = o.current_features()
+            assert len(xy) == len(wxy) and np.array_equal(ids, wids), i
+            akid, _, _ = slam.keyframes(0, active_only=True)
+            assert list(akid) == sorted(o.active_kfs) and len(akid) <= 20
+            alid, alxyz, aot = slam.landmarks(0, active_only=True)
+            assert list(alid) == sorted(o.active_lms)
+            assert list(aot) == [o.active_lms[k].observed_times for k in sorted(o.active_lms)]
+            wl = np.array([o.active_lms[k].pos for k in sorted(o.active_lms)]).reshape(-1, 3)
+            worst = max(worst, float(rel_to_norm(alxyz, wl).max()))
+            assert rel_to_norm(alxyz, wl).max() < 1e-4, i
+            _sync(slam, 0, o)
+        assert len(slam.keyframes(0)[0]) == N_FRAMES and len(slam.keyframes(0, active_only=True)[0]) == 20
+        ph, cn = slam.counters()
+        assert cn["ba_problems"] == N_FRAMES and cn["ba_kfs"] >= 20 * 16
+        print("window-20 lock-step: worst landmark rel-to-norm diff %.3g, BA edges per window at the end %d" % (worst, cn["ba_edges"] // N_FRAMES))
+    finally:
+        slam.close()
+
+
 def test_pipeline_free_running_accuracy(ctx, granule, clip):
     """Without teacher forcing the two implementations drift apart chaotically but must be equally accurate:
     ATE against the generator's ground truth and the keyframe rate agree."""
