@@ -230,6 +230,10 @@ SVS_API int svs_ba_shard_get(svs_ctx *ctx, svs_ba_shard *sh, double *poses_out, 
 SVS_API int svs_stereo_bm(svs_ctx *ctx, const uint8_t *left, const uint8_t *right, int w, int h, int stride,
                           int n_images, size_t img_stride_bytes, int ndisp, int block,
                           int16_t *disp_out /* n*h*w */);
+/* Same with the images and the disparity maps resident in device memory (a batch already in HBM, e.g. straight from a frame
+ * set or a decoder); synchronises the context stream before returning. */
+SVS_API int svs_stereo_bm_dev(svs_ctx *ctx, const uint8_t *left_dev, const uint8_t *right_dev, int w, int h, int stride,
+                              int n_images, size_t img_stride_bytes, int ndisp, int block, int16_t *disp_out_dev);
 SVS_API int svs_backproject(svs_ctx *ctx, const int16_t *disp, const uint8_t *bgr /* h*w*3 */, int w, int h,
                             const double K[4], double baseline, const double cam_pose_inv[7],
                             const double T_cw[7], float *xyz_out /* 3*h*w */, uint8_t *rgb_out /* 3*h*w */,
@@ -250,7 +254,12 @@ typedef struct {
     double max_triangulation_depth, chi2_th, gftt_quality, gftt_min_distance, lk_eps;
     /* 1 (default): right images are ingested only for the streams that insert a keyframe in this step (identical results,
      * ~half the image traffic); 0: both eyes of every frame are ingested, as Dataset::NextFrame resizes both */
-    int32_t lazy_right_ingest, reserved_;
+    int32_t lazy_right_ingest;
+    /* 1 (default): Frontend::Track()'s per-frame arithmetic (motion model, LK initial guesses, LK, feature hand-over, pose-only LM,
+     * status / keyframe test, relative motion) runs on device-resident per-stream state with no host round trip between the
+     * seams; the host classes see a stream only when it inserts a keyframe or initialises.  0: every seam is a host round trip
+     * (bit-identical results) */
+    int32_t device_tracking;
 } svs_slam_config;
 typedef struct svs_slam svs_slam;
 SVS_API void svs_slam_default_config(svs_slam_config *cfg);

@@ -105,7 +105,7 @@ const char *svs_kernel_name(int kid)
 {
     static const char *names[KID_COUNT] = {"k_half_nearest", "k_copy2d", "k_pyr_down", "k_mask_boxes", "k_corner_response",
                                            "k_corner_select", "k_corner_greedy", "k_lk_track", "k_triangulate", "k_pose_only_lm",
-                                           "k_ba_window", "k_bm_prefilter", "k_bm_sad", "k_backproject", "k_bgr2gray", "misc"};
+                                           "k_ba_window", "k_bm_prefilter", "k_bm_sad", "k_backproject", "k_bgr2gray", "misc", "k_trk_state"};
     return (kid >= 0 && kid < KID_COUNT) ? names[kid] : "";
 }
 const char *svs_create_error(void) { return g_create_err.c_str(); }

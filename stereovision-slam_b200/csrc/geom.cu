@@ -203,14 +203,15 @@ __device__ __forceinline__ void warp_allreduce32(double *v /* 32 per lane, in/ou
 __global__ void __launch_bounds__(PO_WARPS * 32)
 k_pose_only_lm(int n_prob, const int32_t *__restrict__ off, const double *__restrict__ pts_w, const double *__restrict__ uv,
                const double *__restrict__ Kall, const double *__restrict__ T0all, double chi2_th, int rounds, int iters,
-               double *__restrict__ T_out, uint8_t *__restrict__ outl, int32_t *__restrict__ n_inlier, svs_lm_stats *__restrict__ stats)
+               double *__restrict__ T_out, uint8_t *__restrict__ outl, int32_t *__restrict__ n_inlier, svs_lm_stats *__restrict__ stats,
+               const int32_t *__restrict__ end /* null: CSR (edges of problem b end at off[b + 1]) */)
 {
     __shared__ double s_red[PO_WARPS][32];
     int prob = blockIdx.x * PO_WARPS + (threadIdx.x >> 5);
     if (prob >= n_prob) return;
     int lane = threadIdx.x & 31;
     double *red = s_red[threadIdx.x >> 5];
-    int e0 = off[prob], e1 = off[prob + 1];
+    int e0 = off[prob], e1 = end ? end[prob] : off[prob + 1];
     double K[4], T0[7], T[7], Teval[7];
 #pragma unroll
     for (int i = 0; i < 4; i++) K[i] = Kall[4 * prob + i];
@@ -365,6 +366,17 @@ k_pose_only_lm(int n_prob, const int32_t *__restrict__ off, const double *__rest
     }
 }
 
+// Device-pointer entry for the device-resident tracker (track.cu): problem b owns edges [off[b], end[b]).
+int svs_i_pose_only_lm_dev(svs_ctx *c, int n_prob, const int32_t *off_dev, const int32_t *end_dev, const double *pts_w_dev,
+                           const double *uv_dev, const double *K_dev, const double *T0_dev, double chi2_th, int rounds, int iters,
+                           double *T_out_dev, uint8_t *outl_dev, int32_t *n_inlier_dev)
+{
+    if (n_prob <= 0) return SVS_OK;
+    SVS_KERNEL(c, KID_POSE_LM, k_pose_only_lm<<<(n_prob + PO_WARPS - 1) / PO_WARPS, PO_WARPS * 32, 0, c->stream>>>(
+        n_prob, off_dev, pts_w_dev, uv_dev, K_dev, T0_dev, chi2_th, rounds, iters, T_out_dev, outl_dev, n_inlier_dev, nullptr, end_dev));
+    return SVS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -423,7 +435,7 @@ int svs_pose_only_lm(svs_ctx *c, int n_prob, const int32_t *off, const double *p
         n_prob, reinterpret_cast<int32_t *>(db), reinterpret_cast<double *>(db + off_b), reinterpret_cast<double *>(db + off_b + p_b),
         reinterpret_cast<double *>(db + off_b + p_b + u_b), reinterpret_cast<double *>(db + off_b + p_b + u_b + k_b), chi2_th, rounds,
         iters, reinterpret_cast<double *>(dob), dob + t_b + st_b + ni_b, reinterpret_cast<int32_t *>(dob + t_b + st_b),
-        reinterpret_cast<svs_lm_stats *>(dob + t_b)));
+        reinterpret_cast<svs_lm_stats *>(dob + t_b), nullptr));
     SVS_CUDA(c, cudaMemcpyAsync(c->h_out.p, dob, out_b, cudaMemcpyDeviceToHost, c->stream));
     SVS_CUDA(c, cudaStreamSynchronize(c->stream));
     uint8_t *ho = c->h_out.as<uint8_t>();

@@ -258,6 +258,16 @@ int svs_stereo_bm(svs_ctx *c, const uint8_t *left, const uint8_t *right, int w, 
     return SVS_OK;
 }
 
+int svs_stereo_bm_dev(svs_ctx *c, const uint8_t *left_dev, const uint8_t *right_dev, int w, int h, int stride, int n, size_t img_stride,
+                      int ndisp, int block, int16_t *disp_out_dev)
+{
+    if (!c || !left_dev || !right_dev || !disp_out_dev || w < 3 || h < 3 || n < 1 || stride < w) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    SVS_TRY(svs_i_stereo_bm(c, left_dev, right_dev, w, h, stride, img_stride, n, ndisp, block, disp_out_dev));
+    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SVS_OK;
+}
+
 int svs_backproject(svs_ctx *c, const int16_t *disp, const uint8_t *bgr, int w, int h, const double K[4], double baseline,
                     const double cam_pose_inv[7], const double T_cw[7], float *xyz_out, uint8_t *rgb_out, int32_t *n_out)
 {

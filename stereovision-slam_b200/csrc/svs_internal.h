@@ -53,7 +53,7 @@ struct PinBuf {
 // Kernel classes for the optional per-kernel CUDA-event timing (svs_kernel_timing_*; bench.py's roofline).
 enum SvsKernelId { KID_HALF = 0, KID_COPY0, KID_PYRDOWN, KID_MASK, KID_CORNER_RESPONSE, KID_CORNER_SELECT, KID_CORNER_GREEDY,
                    KID_LK, KID_TRIANGULATE, KID_POSE_LM, KID_BA_WINDOW, KID_BM_PREFILTER, KID_BM_SAD, KID_BACKPROJECT,
-                   KID_BGR2GRAY, KID_MISC, KID_COUNT };
+                   KID_BGR2GRAY, KID_MISC, KID_TRACK_STATE, KID_COUNT };
 struct SvsPendingEv { int kid; cudaEvent_t a, b; };
 
 struct svs_ctx {
@@ -154,3 +154,7 @@ int svs_i_gftt(svs_ctx *c, const uint8_t *img_dev, int w, int h, int stride, siz
 int svs_i_lk(svs_ctx *c, const PyrDesc &prev, const PyrDesc &next, const int32_t *pt_img_dev /* per point */,
              const float *prev_xy_dev, float *next_xy_dev, int n_pts, int win, int max_iter, double eps,
              uint8_t *status_dev);
+// geom.cu
+int svs_i_pose_only_lm_dev(svs_ctx *c, int n_prob, const int32_t *off_dev, const int32_t *end_dev, const double *pts_w_dev,
+                           const double *uv_dev, const double *K_dev, const double *T0_dev, double chi2_th, int rounds, int iters,
+                           double *T_out_dev, uint8_t *outl_dev, int32_t *n_inlier_dev);

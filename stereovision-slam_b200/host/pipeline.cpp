@@ -10,6 +10,7 @@
 #include <vector>
 #include "../../include/svslam.h"
 #include "slam.h"
+#include "../csrc/track.h"
 
 namespace slam {
 
@@ -23,6 +24,8 @@ struct Stream {
     TriRequest tri;
     BaRequest ba;
     bool ran_track = false, ran_detect = false, ran_backend = false, is_kf = false;
+    bool on_host = true;          // the current frame exists in the host Frontend (always, without device tracking)
+    double out_pose[7] = {0, 0, 0, 1, 0, 0, 0};
 };
 
 class StreamBatch {
@@ -50,14 +53,30 @@ public:
                 s.frontend->SetBackend(s.backend);
             }
         }
+        if (cfg.device_tracking) {
+            TrkParams p;
+            p.B = n_streams; p.cap = (2 * cfg.num_features + 256 + 31) / 32 * 32; p.W = W_; p.H = H_;
+            p.num_features_tracking = cfg.num_features_tracking; p.num_features_tracking_bad = cfg.num_features_tracking_bad;
+            p.num_features_needed_for_keyframe = cfg.num_features_needed_for_keyframe;
+            p.lk_win = cfg.lk_win; p.lk_max_iter = cfg.lk_max_iter; p.lk_eps = cfg.lk_eps; p.chi2_th = 5.991;
+            p.cam_left = *cam_left_;
+            trk_ = svs_i_trk_create(ctx, p);
+            if (!trk_) { svs_frameset_destroy(ctx, fs_); fs_ = nullptr; }
+        }
     }
-    ~StreamBatch() { if (fs_) svs_frameset_destroy(ctx_, fs_); }
+    ~StreamBatch() { if (trk_) svs_i_trk_destroy(ctx_, trk_); if (fs_) svs_frameset_destroy(ctx_, fs_); }
     bool ok() const { return fs_ != nullptr; }
+    svs_tracker *tracker() { return trk_; }
+    svs_ctx *ctx() { return ctx_; }
     int n() const { return (int)streams_.size(); }
     Stream &stream(int i) { return streams_[i]; }
     svs_frameset *frameset() { return fs_; }
 
     int step(const uint8_t *const *left, const uint8_t *const *right, size_t row_stride, int on_device);
+    int track_host(double &t0);      // Track() up to the keyframe decision, every seam a host round trip
+    int track_device(double &t0);    // the same on the device-resident state (csrc/track.cu)
+    int upload_states();             // hand the streams the host touched in this step back to the device
+    int run_lk(int pair, bool (*sel)(const Stream &));
 
     void set_threads(int n) { threads_ = n > 0 ? n : 1; }
     void hint_next(const uint8_t *const *l, const uint8_t *const *r)
@@ -74,6 +93,9 @@ public:
 private:
     svs_ctx *ctx_;
     svs_frameset *fs_ = nullptr;
+    svs_tracker *trk_ = nullptr;
+    std::vector<TrkUpHdr> up_hdr_;
+    std::vector<TrkUpFeat> up_feat_;
     Config cfg_;
     int W_ = 0, H_ = 0;
     int threads_ = omp_get_max_threads();
@@ -96,19 +118,39 @@ static inline double now_s()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, size_t row_stride, int on_device)
+int StreamBatch::run_lk(int pair, bool (*sel)(const Stream &))
 {
     const int B = n();
-    double t0 = now_s(), t1;
-    const bool lazy = cfg_.lazy_right_ingest != 0;
-    int rc = svs_frameset_push_ptrs(ctx_, fs_, left, lazy ? nullptr : right, row_stride, on_device);
-    if (rc) return rc;
-    if (has_next_) {   // double buffering: the next pair's PCIe transfer / resize / pyramids overlap this step's kernels
-        has_next_ = false;
-        if ((rc = svs_frameset_prefetch_ptrs(ctx_, fs_, next_left_.data(), lazy ? nullptr : next_right_.data(), row_stride, on_device))) return rc;
+    off_.assign(B + 1, 0);
+    for (int b = 0; b < B; b++) off_[b + 1] = off_[b] + (sel(streams_[b]) ? (int)streams_[b].lk.status.size() : 0);
+    int tot = off_[B];
+    if (tot == 0) return 0;
+    lk_points += tot;
+    f0_.resize((size_t)2 * tot); f1_.resize((size_t)2 * tot); u0_.resize(tot);
+    for (int b = 0; b < B; b++) {
+        if (!sel(streams_[b])) continue;
+        const LkRequest &q = streams_[b].lk;
+        if (q.status.empty()) continue;
+        memcpy(&f0_[2 * (size_t)off_[b]], q.prev_xy.data(), q.prev_xy.size() * 4);
+        memcpy(&f1_[2 * (size_t)off_[b]], q.next_xy.data(), q.next_xy.size() * 4);
     }
-    t1 = now_s(); t_phase[0] += t1 - t0; t0 = t1;
+    int r = svs_lk_track_batch(ctx_, fs_, pair, off_.data(), f0_.data(), f1_.data(), cfg_.lk_max_iter, cfg_.lk_eps, u0_.data());
+    if (r) return r;
+    for (int b = 0; b < B; b++) {
+        if (!sel(streams_[b])) continue;
+        LkRequest &q = streams_[b].lk;
+        if (q.status.empty()) continue;
+        memcpy(q.next_xy.data(), &f1_[2 * (size_t)off_[b]], q.next_xy.size() * 4);
+        memcpy(q.status.data(), &u0_[off_[b]], q.status.size());
+    }
+    return 0;
+}
 
+int StreamBatch::track_host(double &t0)
+{
+    const int B = n();
+    double t1;
+    int rc;
 #pragma omp parallel for schedule(static) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
@@ -119,31 +161,6 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         if (s.frontend->wants_track()) { s.frontend->prepare_TrackLastFrame(s.lk); s.ran_track = true; }
     }
     // ---------------- TrackLastFrame: LK previous-left -> current-left (src/frontend.cpp:353-357)
-    auto run_lk = [&](int pair, bool (*sel)(const Stream &)) -> int {
-        off_.assign(B + 1, 0);
-        for (int b = 0; b < B; b++) off_[b + 1] = off_[b] + (sel(streams_[b]) ? (int)streams_[b].lk.status.size() : 0);
-        int tot = off_[B];
-        if (tot == 0) return 0;
-        lk_points += tot;
-        f0_.resize((size_t)2 * tot); f1_.resize((size_t)2 * tot); u0_.resize(tot);
-        for (int b = 0; b < B; b++) {
-            if (!sel(streams_[b])) continue;
-            const LkRequest &q = streams_[b].lk;
-            if (q.status.empty()) continue;
-            memcpy(&f0_[2 * (size_t)off_[b]], q.prev_xy.data(), q.prev_xy.size() * 4);
-            memcpy(&f1_[2 * (size_t)off_[b]], q.next_xy.data(), q.next_xy.size() * 4);
-        }
-        int r = svs_lk_track_batch(ctx_, fs_, pair, off_.data(), f0_.data(), f1_.data(), cfg_.lk_max_iter, cfg_.lk_eps, u0_.data());
-        if (r) return r;
-        for (int b = 0; b < B; b++) {
-            if (!sel(streams_[b])) continue;
-            LkRequest &q = streams_[b].lk;
-            if (q.status.empty()) continue;
-            memcpy(q.next_xy.data(), &f1_[2 * (size_t)off_[b]], q.next_xy.size() * 4);
-            memcpy(q.status.data(), &u0_[off_[b]], q.status.size());
-        }
-        return 0;
-    };
     t1 = now_s(); t_phase[7] += t1 - t0; t_host[0] += t1 - t0; t0 = t1;
     if ((rc = run_lk(0, [](const Stream &s) { return s.ran_track; }))) return rc;
     t1 = now_s(); t_phase[1] += t1 - t0; t0 = t1;
@@ -195,6 +212,100 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         if (s.ran_track) s.frontend->finish_EstimateCurrentPose(s.pose);
         if (s.frontend->wants_detect()) { s.frontend->prepare_DetectFeatures(s.det); s.ran_detect = true; }
     }
+    return 0;
+}
+
+int StreamBatch::track_device(double &t0)
+{
+    const int B = n();
+    double t1;
+    int rc = svs_i_trk_step(ctx_, trk_, fs_, &lk_points, &pose_edges);
+    if (rc) return rc;
+    t1 = now_s(); t_phase[1] += t1 - t0; t0 = t1;
+    const TrkOut *o = svs_i_trk_out(trk_);
+#pragma omp parallel for schedule(static) num_threads(threads_)
+    for (int b = 0; b < B; b++) {
+        Stream &s = streams_[b];
+        s.ran_track = s.ran_detect = s.ran_backend = s.is_kf = false;
+        s.on_host = false;
+        const FrontendStatus st = s.frontend->GetStatus();
+        if (st == FrontendStatus::INITING) {                       // StereoInit runs on the host classes
+            Frame::Ptr f = s.frontend->CreateFrame();
+            s.frontend->begin_AddFrame(f, W_, H_);
+            s.on_host = true;
+        } else if (st == FrontendStatus::TRACKING_GOOD || st == FrontendStatus::TRACKING_BAD) {
+            const TrkOut &r = o[b];
+            s.ran_track = true;
+            if (r.need_kf) {                                       // InsertKeyframe: the stream comes back to the host
+                s.frontend->adopt_tracked_keyframe(r.pose, r.last_pose, reinterpret_cast<const float *>(svs_i_trk_kf_feats(trk_, b)), r.nfeat,
+                                                   r.status, r.inliers, W_, H_);
+                s.on_host = true;
+            } else {
+                s.frontend->note_tracked_frame(r.status, r.inliers);
+                memcpy(s.out_pose, r.pose, 56);
+            }
+        } else {                                                    // LOST: Reset() is "not implemented" in the reference
+            s.frontend->skip_frame();
+            const double I[7] = {0, 0, 0, 1, 0, 0, 0};
+            memcpy(s.out_pose, I, 56);
+        }
+        if (s.on_host && s.frontend->wants_detect()) { s.frontend->prepare_DetectFeatures(s.det); s.ran_detect = true; }
+    }
+    return 0;
+}
+
+// Every stream the host classes touched in this step (keyframe inserted, initialisation tried) goes back to the device:
+// its current frame's left features with the landmark positions (refined by BA), its pose and the relative motion.
+int StreamBatch::upload_states()
+{
+    const int B = n();
+    ids_.clear();
+    for (int b = 0; b < B; b++) if (streams_[b].on_host) ids_.push_back(b);
+    const int ns = (int)ids_.size();
+    if (ns == 0) return 0;
+    up_hdr_.resize(ns);
+    long long tot = 0;
+    for (int k = 0; k < ns; k++) {
+        Stream &s = streams_[ids_[k]];
+        TrkUpHdr &h = up_hdr_[k];
+        const Frame &f = *s.frontend->current_frame_;
+        h.stream = ids_[k]; h.n = (int)f.feature_left_.size(); h.status = (int)s.frontend->GetStatus(); h.pad_ = 0; h.pad2_ = 0;
+        memcpy(h.pose, f.pose_.d, 56);
+        memcpy(h.rel, s.frontend->relative_motion().d, 56);
+        h.feat_off = tot;
+        tot += h.n;
+    }
+    up_feat_.resize((size_t)tot);
+#pragma omp parallel for schedule(static) num_threads(threads_)
+    for (int k = 0; k < ns; k++) {
+        Stream &s = streams_[ids_[k]];
+        const Frame &f = *s.frontend->current_frame_;
+        Map *map = s.frontend->map();
+        TrkUpFeat *o = up_feat_.data() + up_hdr_[k].feat_off;
+        for (size_t i = 0; i < f.feature_left_.size(); i++) {
+            const Feature &ft = f.feature_left_[i];
+            o[i].x = ft.x; o[i].y = ft.y; o[i].lm = ft.map_point_;
+            o[i].pw[0] = o[i].pw[1] = o[i].pw[2] = 0.0;
+            if (const MapPoint *mp = map->GetMapPoint(ft.map_point_)) { o[i].pw[0] = mp->pos_.x; o[i].pw[1] = mp->pos_.y; o[i].pw[2] = mp->pos_.z; }
+        }
+    }
+    return svs_i_trk_upload(ctx_, trk_, ns, up_hdr_.data(), up_feat_.data(), tot);
+}
+
+int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, size_t row_stride, int on_device)
+{
+    const int B = n();
+    double t0 = now_s(), t1;
+    const bool lazy = cfg_.lazy_right_ingest != 0;
+    int rc = svs_frameset_push_ptrs(ctx_, fs_, left, lazy ? nullptr : right, row_stride, on_device);
+    if (rc) return rc;
+    if (has_next_) {   // double buffering: the next pair's PCIe transfer / resize / pyramids overlap this step's kernels
+        has_next_ = false;
+        if ((rc = svs_frameset_prefetch_ptrs(ctx_, fs_, next_left_.data(), lazy ? nullptr : next_right_.data(), row_stride, on_device))) return rc;
+    }
+    t1 = now_s(); t_phase[0] += t1 - t0; t0 = t1;
+
+    if ((rc = trk_ ? track_device(t0) : track_host(t0))) return rc;
     // ---------------- DetectFeatures: GFTT with the tracked-feature mask (src/frontend.cpp:42-51)
     {
         ids_.clear();
@@ -331,12 +442,15 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
 #pragma omp parallel for schedule(static) reduction(+ : nkf) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
+        if (!s.on_host) continue;           // device-resident tracking: this stream's frame never left the GPU
         if (s.ran_backend) s.backend->finish_Optimize(s.ba);
         s.frontend->end_AddFrame();
+        memcpy(s.out_pose, s.frontend->current_frame_->pose_.d, 56);
         nkf += s.is_kf ? 1 : 0;
     }
     keyframes += nkf;
     frames += B;
+    if (trk_ && (rc = upload_states())) return rc;
     t1 = now_s(); t_phase[7] += t1 - t0; t_host[6] += t1 - t0;
     return 0;
 }
@@ -365,6 +479,7 @@ svs_slam *svs_slam_create(svs_ctx *ctx, int n_streams, int in_w, int in_h, int h
     cfg.lk_max_iter = c->lk_max_iter; cfg.lk_eps = c->lk_eps; cfg.ba_max_iter = c->ba_max_iter;
     cfg.ba_jacobian_mode = c->ba_jacobian_mode; cfg.oracle_simd_granule = c->oracle_simd_granule;
     cfg.lazy_right_ingest = c->lazy_right_ingest;
+    cfg.device_tracking = c->device_tracking;
     svs_slam *s = new (std::nothrow) svs_slam();
     if (!s) return nullptr;
     s->ctx = ctx;
@@ -391,7 +506,7 @@ void svs_slam_default_config(svs_slam_config *c)
     c->gftt_min_distance = d.gftt_min_distance; c->lk_win = d.lk_win; c->lk_max_level = d.lk_max_level;
     c->lk_max_iter = d.lk_max_iter; c->lk_eps = d.lk_eps; c->ba_max_iter = d.ba_max_iter;
     c->ba_jacobian_mode = d.ba_jacobian_mode; c->oracle_simd_granule = d.oracle_simd_granule;
-    c->lazy_right_ingest = d.lazy_right_ingest; c->reserved_ = 0;
+    c->lazy_right_ingest = d.lazy_right_ingest; c->device_tracking = d.device_tracking;
 }
 
 int svs_slam_add_frames(svs_slam *s, const uint8_t *const *left, const uint8_t *const *right, size_t row_stride, int on_device,
@@ -402,7 +517,7 @@ int svs_slam_add_frames(svs_slam *s, const uint8_t *const *left, const uint8_t *
     if (rc) return rc;
     for (int b = 0; b < s->batch->n(); b++) {
         slam::Stream &st = s->batch->stream(b);
-        if (poses_out) memcpy(poses_out + 7 * (size_t)b, st.frontend->current_frame_->pose_.d, 56);
+        if (poses_out) memcpy(poses_out + 7 * (size_t)b, st.out_pose, 56);
         if (status_out) status_out[b] = (int)st.frontend->GetStatus();
         if (keyframe_out) keyframe_out[b] = st.is_kf ? 1 : 0;
         if (inliers_out) inliers_out[b] = st.frontend->tracking_inliers_;
@@ -413,7 +528,22 @@ int svs_slam_add_frames(svs_slam *s, const uint8_t *const *left, const uint8_t *
 int svs_slam_get_features(svs_slam *s, int stream, int right, float *xy, int64_t *map_point_ids, uint8_t *valid, int cap, int *n)
 {
     if (!s || stream < 0 || stream >= s->batch->n() || !n) return SVS_ERR_ARG;
-    slam::Frame::Ptr f = s->batch->stream(stream).frontend->current_frame_;
+    slam::Stream &st = s->batch->stream(stream);
+    if (!st.on_host) {      // device-resident tracking: the frame lives on the GPU (left features only; no right features
+                            // exist outside keyframes)
+        *n = 0;
+        if (right || st.frontend->GetStatus() == slam::FrontendStatus::LOST) return SVS_OK;
+        const TrkFeat *ft = nullptr;
+        int rc = svs_i_trk_fetch(s->batch->ctx(), s->batch->tracker(), stream, &ft, n);
+        if (rc) return rc;
+        for (int i = 0; i < *n && i < cap; i++) {
+            if (xy) { xy[2 * i] = ft[i].x; xy[2 * i + 1] = ft[i].y; }
+            if (map_point_ids) map_point_ids[i] = ft[i].lm;
+            if (valid) valid[i] = 1;
+        }
+        return SVS_OK;
+    }
+    slam::Frame::Ptr f = st.frontend->current_frame_;
     if (!f) { *n = 0; return SVS_OK; }
     const std::vector<slam::Feature> &v = right ? f->feature_right_ : f->feature_left_;
     *n = (int)v.size();

@@ -8,28 +8,6 @@
 namespace slam {
 
 // ------------------------------------------------------------------ SE3 (Sophus::SE3d formulas)
-SE3 SE3::operator*(const SE3 &o) const
-{
-    const double *A = d, *B = o.d;
-    SE3 C;
-    C.d[0] = A[3] * B[0] + A[0] * B[3] + A[1] * B[2] - A[2] * B[1];
-    C.d[1] = A[3] * B[1] + A[1] * B[3] + A[2] * B[0] - A[0] * B[2];
-    C.d[2] = A[3] * B[2] + A[2] * B[3] + A[0] * B[1] - A[1] * B[0];
-    C.d[3] = A[3] * B[3] - A[0] * B[0] - A[1] * B[1] - A[2] * B[2];
-    double n2 = C.d[0] * C.d[0] + C.d[1] * C.d[1] + C.d[2] * C.d[2] + C.d[3] * C.d[3];
-    if (n2 != 1.0) { double s = 2.0 / (1.0 + n2); for (int i = 0; i < 4; i++) C.d[i] *= s; }
-    Vec3 t = rotate(o.translation());
-    C.d[4] = t.x + d[4]; C.d[5] = t.y + d[5]; C.d[6] = t.z + d[6];
-    return C;
-}
-SE3 SE3::inverse() const
-{
-    SE3 I;
-    I.d[0] = -d[0]; I.d[1] = -d[1]; I.d[2] = -d[2]; I.d[3] = d[3];
-    Vec3 t = I.rotate(translation());
-    I.d[4] = -t.x; I.d[5] = -t.y; I.d[6] = -t.z;
-    return I;
-}
 SE3 SE3::exp(const double *a)
 {
     const double *w = a + 3;
@@ -240,6 +218,31 @@ int Frontend::finish_EstimateCurrentPose(const PoseRequest &rq)
     // InsertKeyframe :576-643
     if (tracking_inliers_ < cfg_.num_features_needed_for_keyframe) InsertKeyframe_begin();
     return tracking_inliers_;
+}
+
+void Frontend::adopt_tracked_keyframe(const double pose[7], const double last_pose[7], const float *recs, int n, int status,
+                                      int inliers, int img_w, int img_h)
+{   // the state Track() would have reached on the host at the point where it calls InsertKeyframe() (frontend.cpp:681)
+    struct Rec { float x, y; int64_t lm; };
+    const Rec *r = reinterpret_cast<const Rec *>(recs);
+    img_w_ = img_w; img_h_ = img_h;
+    phase_track_ = true;
+    phase_detect_ = phase_backend_ = initing_ = init_ok_ = false;
+    if (!(last_frame_ && last_frame_->id_ + 1 == frame_factory_id_)) {
+        Frame::Ptr last = std::make_shared<Frame>();      // only its pose is read again (end_AddFrame, relative_motion_)
+        last->pose_ = SE3::fromArray(last_pose);
+        last_frame_ = last;
+    }   // else: the previous frame was handled here too (a keyframe): keep the shared object — this step's BA may refine its
+        // pose before relative_motion_ is taken, exactly as with the reference's shared Frame
+    current_frame_ = CreateFrame();
+    current_frame_->pose_ = SE3::fromArray(pose);
+    std::vector<Feature> &cf = current_frame_->feature_left_;
+    cf.resize((size_t)n);
+    for (int i = 0; i < n; i++) { Feature &f = cf[i]; f.x = r[i].x; f.y = r[i].y; f.size = 7; f.map_point_ = (long)r[i].lm; }
+    last_tracked = n;
+    status_ = (FrontendStatus)status;
+    tracking_inliers_ = inliers;
+    InsertKeyframe_begin();
 }
 
 void Frontend::InsertKeyframe_begin()

@@ -26,67 +26,101 @@
 #include <memory>
 #include <vector>
 
+// The small math types are shared with the device-resident tracker (csrc/track.cu): the SAME source text computes the
+// motion-model pose, the LK initial guesses and the relative motion on either side, and neither side contracts a*b+c into a
+// fused multiply-add (track.cu is built with --fmad=false, the host compiler targets baseline x86-64), so the two paths agree
+// bit for bit (tests/test_gpu_pipeline.py::test_device_tracking_is_bit_identical_to_host_tracking).
+#ifdef __CUDACC__
+#define SLAM_HD __host__ __device__
+#else
+#define SLAM_HD
+#endif
+
 namespace slam {
 
 // ------------------------------------------------------------------ math
 struct Vec2 { double x = 0, y = 0; };
 struct Vec3 {
     double x = 0, y = 0, z = 0;
-    Vec3() {}
-    Vec3(double a, double b, double c) : x(a), y(b), z(c) {}
-    Vec3 operator+(const Vec3 &o) const { return {x + o.x, y + o.y, z + o.z}; }
-    Vec3 operator-(const Vec3 &o) const { return {x - o.x, y - o.y, z - o.z}; }
+    SLAM_HD Vec3() {}
+    SLAM_HD Vec3(double a, double b, double c) : x(a), y(b), z(c) {}
+    SLAM_HD Vec3 operator+(const Vec3 &o) const { return {x + o.x, y + o.y, z + o.z}; }
+    SLAM_HD Vec3 operator-(const Vec3 &o) const { return {x - o.x, y - o.y, z - o.z}; }
     double norm() const { return std::sqrt(x * x + y * y + z * z); }
 };
 
 // Sophus::SE3d: unit quaternion (x,y,z,w) + translation; d = [qx qy qz qw tx ty tz] is the C-ABI layout.
 struct SE3 {
     double d[7] = {0, 0, 0, 1, 0, 0, 0};
-    SE3() {}
-    static SE3 fromArray(const double *p) { SE3 T; for (int i = 0; i < 7; i++) T.d[i] = p[i]; return T; }
-    static SE3 fromTranslation(const Vec3 &t) { SE3 T; T.d[4] = t.x; T.d[5] = t.y; T.d[6] = t.z; return T; }
+    SLAM_HD SE3() {}
+    SLAM_HD static SE3 fromArray(const double *p) { SE3 T; for (int i = 0; i < 7; i++) T.d[i] = p[i]; return T; }
+    SLAM_HD static SE3 fromTranslation(const Vec3 &t) { SE3 T; T.d[4] = t.x; T.d[5] = t.y; T.d[6] = t.z; return T; }
     // Eigen QuaternionBase::_transformVector; inline: called once or twice per feature per frame
-    Vec3 rotate(const Vec3 &p) const
+    SLAM_HD Vec3 rotate(const Vec3 &p) const
     {
         double ux = 2.0 * (d[1] * p.z - d[2] * p.y), uy = 2.0 * (d[2] * p.x - d[0] * p.z), uz = 2.0 * (d[0] * p.y - d[1] * p.x);
         return {p.x + d[3] * ux + (d[1] * uz - d[2] * uy), p.y + d[3] * uy + (d[2] * ux - d[0] * uz), p.z + d[3] * uz + (d[0] * uy - d[1] * ux)};
     }
-    Vec3 operator*(const Vec3 &p) const { Vec3 r = rotate(p); return {r.x + d[4], r.y + d[5], r.z + d[6]}; }   // point action
+    SLAM_HD Vec3 operator*(const Vec3 &p) const { Vec3 r = rotate(p); return {r.x + d[4], r.y + d[5], r.z + d[6]}; }   // point action
     // a pure translation (the rectified cameras' extrinsics): rotate() returns its argument bit for bit, so it can be skipped
-    bool rotation_is_identity() const { return d[0] == 0.0 && d[1] == 0.0 && d[2] == 0.0 && d[3] == 1.0; }
-    SE3 operator*(const SE3 &o) const;             // composition (Sophus renormalisation included)
-    SE3 inverse() const;
-    Vec3 translation() const { return {d[4], d[5], d[6]}; }
+    SLAM_HD bool rotation_is_identity() const { return d[0] == 0.0 && d[1] == 0.0 && d[2] == 0.0 && d[3] == 1.0; }
+    SLAM_HD SE3 operator*(const SE3 &o) const      // composition (Sophus renormalisation included)
+    {
+        const double *A = d, *B = o.d;
+        SE3 C;
+        C.d[0] = A[3] * B[0] + A[0] * B[3] + A[1] * B[2] - A[2] * B[1];
+        C.d[1] = A[3] * B[1] + A[1] * B[3] + A[2] * B[0] - A[0] * B[2];
+        C.d[2] = A[3] * B[2] + A[2] * B[3] + A[0] * B[1] - A[1] * B[0];
+        C.d[3] = A[3] * B[3] - A[0] * B[0] - A[1] * B[1] - A[2] * B[2];
+        double n2 = C.d[0] * C.d[0] + C.d[1] * C.d[1] + C.d[2] * C.d[2] + C.d[3] * C.d[3];
+        if (n2 != 1.0) { double s = 2.0 / (1.0 + n2); for (int i = 0; i < 4; i++) C.d[i] *= s; }
+        Vec3 t = rotate(o.translation());
+        C.d[4] = t.x + d[4]; C.d[5] = t.y + d[5]; C.d[6] = t.z + d[6];
+        return C;
+    }
+    SLAM_HD SE3 inverse() const
+    {
+        SE3 I;
+        I.d[0] = -d[0]; I.d[1] = -d[1]; I.d[2] = -d[2]; I.d[3] = d[3];
+        Vec3 t = I.rotate(translation());
+        I.d[4] = -t.x; I.d[5] = -t.y; I.d[6] = -t.z;
+        return I;
+    }
+    SLAM_HD Vec3 translation() const { return {d[4], d[5], d[6]}; }
     static SE3 exp(const double *tangent6);         // (upsilon, omega)
     void log(double *tangent6) const;
 };
 
 // ------------------------------------------------------------------ camera
-class Camera {
-public:
-    typedef std::shared_ptr<Camera> Ptr;
+// The plain-data part of Camera (usable as a kernel argument by the device-resident tracker).
+struct CameraModel {
     double fx_ = 0, fy_ = 0, cx_ = 0, cy_ = 0, baseline_ = 0;
     SE3 pose_, pose_inv_;   // extrinsic: stereo-system frame -> this camera
-    Camera() {}
     bool pure_translation_ = false;
-    Camera(double fx, double fy, double cx, double cy, double baseline, const SE3 &pose)
-        : fx_(fx), fy_(fy), cx_(cx), cy_(cy), baseline_(baseline), pose_(pose)
-    {
-        pose_inv_ = pose_.inverse();
-        pure_translation_ = pose_.rotation_is_identity();
-    }
-    SE3 pose() const { return pose_; }
-    void K(double k4[4]) const { k4[0] = fx_; k4[1] = fy_; k4[2] = cx_; k4[3] = cy_; }
-    Vec3 world2camera(const Vec3 &p_w, const SE3 &T_c_w) const
+    SLAM_HD Vec3 world2camera(const Vec3 &p_w, const SE3 &T_c_w) const
     {
         Vec3 v = T_c_w * p_w;
         if (pure_translation_) return {v.x + pose_.d[4], v.y + pose_.d[5], v.z + pose_.d[6]};   // == pose_ * v, bit for bit
         return pose_ * v;
     }
+    SLAM_HD Vec2 camera2pixel(const Vec3 &p_c) const { Vec2 r; r.x = fx_ * p_c.x / p_c.z + cx_; r.y = fy_ * p_c.y / p_c.z + cy_; return r; }
+    SLAM_HD Vec2 world2pixel(const Vec3 &p_w, const SE3 &T_c_w) const { return camera2pixel(world2camera(p_w, T_c_w)); }
+};
+
+class Camera : public CameraModel {
+public:
+    typedef std::shared_ptr<Camera> Ptr;
+    Camera() {}
+    Camera(double fx, double fy, double cx, double cy, double baseline, const SE3 &pose)
+    {
+        fx_ = fx; fy_ = fy; cx_ = cx; cy_ = cy; baseline_ = baseline; pose_ = pose;
+        pose_inv_ = pose_.inverse();
+        pure_translation_ = pose_.rotation_is_identity();
+    }
+    SE3 pose() const { return pose_; }
+    void K(double k4[4]) const { k4[0] = fx_; k4[1] = fy_; k4[2] = cx_; k4[3] = cy_; }
     Vec3 camera2world(const Vec3 &p_c, const SE3 &T_c_w) const { return T_c_w.inverse() * (pose_inv_ * p_c); }
-    Vec2 camera2pixel(const Vec3 &p_c) const { return {fx_ * p_c.x / p_c.z + cx_, fy_ * p_c.y / p_c.z + cy_}; }
     Vec3 pixel2camera(const Vec2 &p_p, double depth = 1) const { return {(p_p.x - cx_) * depth / fx_, (p_p.y - cy_) * depth / fy_, depth}; }
-    Vec2 world2pixel(const Vec3 &p_w, const SE3 &T_c_w) const { return camera2pixel(world2camera(p_w, T_c_w)); }
     Vec3 pixel2world(const Vec2 &p_p, const SE3 &T_c_w, double depth = 1) const { return camera2world(pixel2camera(p_p, depth), T_c_w); }
 };
 
@@ -252,6 +286,9 @@ struct Config {
     // The frontend reads the right image only in FindFeaturesInRight (keyframes / init): ingest it only then (identical
     // results, about half the image traffic).  0 = ingest both eyes of every frame like Dataset::NextFrame.
     int lazy_right_ingest = 1;
+    // Track()'s per-frame arithmetic on the device with device-resident feature / pose state (csrc/track.cu); 0 = every seam
+    // is a host round trip (the round-1 path, kept as the bit-identity reference of the device path)
+    int device_tracking = 1;
 };
 
 enum class FrontendStatus { INITING, TRACKING_GOOD, TRACKING_BAD, LOST };
@@ -313,6 +350,16 @@ public:
     int finish_Triangulate(const TriRequest &rq);        // :174-192 / :286-307 ; returns 1 when the backend must run
     bool wants_backend() const { return phase_backend_; }
     void end_AddFrame();                                 // relative_motion_ :685, last_frame_ :718
+
+    // ---- device-resident tracking (slam::StreamBatch with Config::device_tracking, csrc/track.cu): Track()'s per-frame
+    // arithmetic runs on the GPU and the host sees one record per stream per step; a stream comes back to these host
+    // classes only when it inserts a keyframe (or initialises), with the tracked frame the device hands over.
+    void note_tracked_frame(int status, int inliers) { frame_factory_id_++; status_ = (FrontendStatus)status; tracking_inliers_ = inliers; }
+    void skip_frame() { frame_factory_id_++; }
+    void adopt_tracked_keyframe(const double pose[7], const double last_pose[7], const float *xy_lm /* TrkFeat records */, int n,
+                                int status, int inliers, int img_w, int img_h);
+    const SE3 &relative_motion() const { return relative_motion_; }
+    Map *map() const { return map_.get(); }
 
     int tracking_inliers_ = 0;
     int last_detected = 0, last_right = 0, last_triangulated = 0, last_tracked = 0;

@@ -350,7 +350,7 @@ class SlamConfig(C.Structure):
         "num_features_needed_for_keyframe", "num_active_keyframes", "backend_on", "lk_win", "lk_max_level",
         "lk_max_iter", "ba_max_iter", "ba_jacobian_mode", "oracle_simd_granule")] + [(n, C.c_double) for n in (
         "max_triangulation_depth", "chi2_th", "gftt_quality", "gftt_min_distance", "lk_eps")] + [
-        ("lazy_right_ingest", C.c_int32), ("reserved_", C.c_int32)]
+        ("lazy_right_ingest", C.c_int32), ("device_tracking", C.c_int32)]
 
 
 class Slam:

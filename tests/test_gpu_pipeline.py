@@ -87,6 +87,41 @@ def test_pipeline_lockstep_matches_oracle(ctx, granule, clip, backend_on):
         slam.close()
 
 
+@pytest.mark.parametrize("backend_on,kw", [(1, {}), (0, {}), (1, dict(num_active_keyframes=3, num_features_needed_for_keyframe=110))])
+def test_device_tracking_is_bit_identical_to_host_tracking(ctx, granule, clip, backend_on, kw):
+    """device_tracking = 1 (Track()'s per-frame arithmetic on device-resident state, csrc/track.cu; the host classes see a
+    stream only at keyframes) against device_tracking = 0 (every seam a host round trip): free-running, three streams with
+    different keyframe phases, every output bit for bit."""
+    cor, L, R, T = clip
+    B, delay = 3, [0, 2, 5]
+    a = ctx.slam(B, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, backend_on=backend_on, oracle_simd_granule=granule, device_tracking=1, **kw)
+    b = ctx.slam(B, cor.W, cor.H, cor.K_half(), cor.baseline, half=True, backend_on=backend_on, oracle_simd_granule=granule, device_tracking=0, **kw)
+    try:
+        nk = 0
+        for i in range(N_FRAMES - 5):
+            idx = [i + d for d in delay]
+            pa = a.add_frames(L[idx], R[idx]).copy()
+            pb = b.add_frames(L[idx], R[idx]).copy()
+            assert np.array_equal(pa.view(np.uint64), pb.view(np.uint64)), i
+            assert np.array_equal(a.status, b.status) and np.array_equal(a.is_kf, b.is_kf) and np.array_equal(a.inliers, b.inliers), i
+            nk += int(a.is_kf.sum())
+            for s in range(B):
+                for right in (False, True):
+                    fa, fb = a.features(s, right=right), b.features(s, right=right)
+                    assert np.array_equal(fa[0].view(np.uint32), fb[0].view(np.uint32)) and np.array_equal(fa[1], fb[1]) and np.array_equal(fa[2], fb[2]), (i, s, right)
+        assert nk >= 9
+        for s in range(B):
+            for x, y in zip(a.landmarks(s), b.landmarks(s)):
+                assert np.array_equal(x, y)
+            for x, y in zip(a.keyframes(s), b.keyframes(s)):
+                assert np.array_equal(x, y)
+        ca, cb = a.counters()[1], b.counters()[1]
+        for k in ("frames", "keyframes", "ba_problems", "ba_iterations", "ba_trials", "ba_edges", "lk_points", "pose_edges"):
+            assert ca[k] == cb[k], k
+    finally:
+        a.close(); b.close()
+
+
 def test_pipeline_window_eviction_lockstep(ctx, granule, clip):
     """A small window (num_active_keyframes = 3) forces Map::RemoveOldKeyframe / CleanMap on every keyframe."""
     cor, L, R, T = clip
