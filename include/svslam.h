@@ -195,15 +195,19 @@ SVS_API int svs_ba_optimize(svs_ctx *ctx, int n_prob, const int32_t *kf_off, dou
 SVS_API int svs_ba_host_seconds(svs_ctx *ctx, double out[3]);
 
 /* ---------------------------------------------------------------- a7, sharded : large / multi-GPU bundle adjustment
- * Same problem and solver as svs_ba_optimize, for windows too large for one CTA (config 4: N = 50, L = 1e5) and for
- * landmark sharding across GPUs: every shard holds ALL n_kf poses and a disjoint subset of the landmarks
- * with their edges (edge_lm indexes the shard's own landmarks).  The caller runs g2o's LM control loop and SUMS three
- * device buffers over the shards between the calls (NCCL all-reduce, nothing for one shard) — see
- * stereovision-slam_b200/svslam/ba_shard.py:
- *   svs_ba_shard_linearize -> lin_dev[42 n_kf + 2] = [Hpp | bp | robust chi2 | 0]   (sum), maxdiag_dev[1] (max)
- *   svs_ba_shard_schur     -> red_dev[(6 n_kf)^2 + 6 n_kf]                          (sum), flag_dev[1] (min)
- *   svs_ba_shard_try       -> tri_dev[4] = [trial chi2 | landmark scale | pose scale (replicated) | solve ok]  (sum of [0..1])
- *   svs_ba_shard_accept    commits the trial state. */
+ * Same problem and solver as svs_ba_optimize — the g2o block of Backend::Optimize, src/backend.cpp:22-164, ending in
+ * optimizer.optimize(max_iter) at :163-164 — for windows too large for one CTA (config 4: N = 50, L = 1e5) and for landmark
+ * sharding across GPUs: every shard holds ALL n_kf poses and a disjoint subset of the landmarks with their
+ * edges (edge_lm indexes the shard's own landmarks).
+ *
+ * svs_ba_shard_optimize runs the WHOLE Levenberg-Marquardt loop in one persistent cooperative kernel: accept / reject,
+ * lambda schedule and stopping tests are on the device, no host round trip.  With several shards the kernels of all ranks
+ * exchange their partial reduced camera systems THEMSELVES through peer memory (no NCCL): every shard owns an exchange
+ * window in device memory (svs_ba_shard_window); the caller maps every peer's window into this process (svs_ipc_export /
+ * svs_ipc_import over any bootstrap: MPI, sockets, torch.distributed; plain pointers inside one process) and hands the
+ * list to svs_ba_shard_set_peers.  Then ALL ranks call svs_ba_shard_optimize (or _launch + _finish) concurrently; each
+ * returns the same statistics, poses (replicated) and its own landmarks.  A rank whose peer never arrives fails with
+ * SVS_ERR_CUDA after a timeout instead of hanging. */
 typedef struct svs_ba_shard svs_ba_shard;
 SVS_API svs_ba_shard *svs_ba_shard_create(svs_ctx *ctx, int n_kf, const double *poses, int n_lm, const double *lms, int n_edge,
                                           const int32_t *edge_kf, const int32_t *edge_lm, const uint8_t *edge_cam,
@@ -211,14 +215,19 @@ SVS_API svs_ba_shard *svs_ba_shard_create(svs_ctx *ctx, int n_kf, const double *
                                           const double ext_left[7], const double ext_right[7], double huber_delta,
                                           int jacobian_mode);
 SVS_API void svs_ba_shard_destroy(svs_ctx *ctx, svs_ba_shard *sh);
-SVS_API int svs_ba_shard_lin_size(const svs_ba_shard *sh);
-SVS_API int svs_ba_shard_red_size(const svs_ba_shard *sh);
-SVS_API int svs_ba_shard_linearize(svs_ctx *ctx, svs_ba_shard *sh, double *lin_dev, double *maxdiag_dev);
-SVS_API int svs_ba_shard_schur(svs_ctx *ctx, svs_ba_shard *sh, double lambda, double *red_dev, int *flag_dev);
-SVS_API int svs_ba_shard_try(svs_ctx *ctx, svs_ba_shard *sh, const double *lin_dev, const double *red_dev, double lambda,
-                             int flag_ok, double *tri_dev);
-SVS_API int svs_ba_shard_accept(svs_ctx *ctx, svs_ba_shard *sh);
+SVS_API int svs_ba_shard_window(const svs_ba_shard *sh, void **window_dev, size_t *bytes);
+/* peer_window_dev[r] = rank r's window as a device pointer valid in THIS process; peer_window_dev[rank] must be the own one */
+SVS_API int svs_ba_shard_set_peers(svs_ctx *ctx, svs_ba_shard *sh, int n_ranks, int rank, void *const *peer_window_dev);
+/* several shards on ONE GPU (tests): bound each kernel's grid so that all of them are resident at the same time */
+SVS_API int svs_ba_shard_set_grid_limit(svs_ba_shard *sh, int max_ctas);
+SVS_API int svs_ba_shard_optimize(svs_ctx *ctx, svs_ba_shard *sh, int max_iter, svs_ba_stats *stats);
+SVS_API int svs_ba_shard_launch(svs_ctx *ctx, svs_ba_shard *sh, int max_iter);        /* asynchronous half of _optimize */
+SVS_API int svs_ba_shard_finish(svs_ctx *ctx, svs_ba_shard *sh, svs_ba_stats *stats); /* waits, returns the statistics */
 SVS_API int svs_ba_shard_get(svs_ctx *ctx, svs_ba_shard *sh, double *poses_out, double *lms_out, double *edge_chi2_out);
+/* CUDA IPC plumbing for the windows (cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle): 64-byte handles */
+SVS_API int svs_ipc_export(svs_ctx *ctx, const void *dev_ptr, unsigned char handle_out[64]);
+SVS_API int svs_ipc_import(svs_ctx *ctx, const unsigned char handle[64], void **dev_ptr_out);
+SVS_API int svs_ipc_release(svs_ctx *ctx, void *dev_ptr);
 
 /* ---------------------------------------------------------------- a10 : dense stereo
  * svs_stereo_bm replaces stereo_depth_est_->compute(l, r, disp) (src/dense_reconstruction.cpp:114) for

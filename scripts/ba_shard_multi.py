@@ -1,12 +1,14 @@
-"""torchrun script: landmark-sharded BA across GPUs with NCCL all-reduce, config-4 shape.
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/ba_shard_nccl.py [n_lm]"""
+"""torchrun script: landmark-sharded BA across GPUs, config-4 shape.  One cooperative solver kernel per GPU;
+the kernels exchange their partial reduced systems through each other's device memory over NVLink (no NCCL in the loop;
+torch.distributed only carries the 64-byte CUDA IPC handles of the exchange windows once).
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/ba_shard_multi.py [n_lm]"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "stereovision-slam_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "stereovision-slam_b200"))
 import numpy as np, torch, torch.distributed as dist
 import svslam
 from svslam import ba_shard
-from util import K05, EXT_L, EXT_R, ba_problem_big
+from svslam.problems import K05, EXT_L, EXT_R, ba_problem_big
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -20,13 +22,16 @@ res = {}
 for rep in range(3):
     sh = ba_shard.Shard(ctx, p["poses"], p["lms"], p["edge_kf"], p["edge_lm"], p["edge_cam"], p["edge_uv"], K05, K05, EXT_L, EXT_R)
     if world > 1:
+        ba_shard.wire_distributed(sh, dist)
         dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    st = ba_shard.lm_optimize([sh], 10, dist if world > 1 else None)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    st = sh.optimize(10)
+    dt = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
     P, L, c2 = sh.get()
+    if world > 1:
+        dist.barrier()          # nobody unmaps a window a peer may still read
     sh.close()
     res = dict(n_gpus=world, n_kf=50, n_lm=n_lm, n_edges=int(len(prob["edge_kf"])), local_edges=int(len(p["edge_kf"])), seconds=dt,
                lm_iterations=st["iterations"], trials=st["trials"], iters_per_sec=st["iterations"] / dt, chi2_init=st["chi2_init"],

@@ -21,6 +21,7 @@
 // to an L2-resident global buffer through the same code path.
 #include "svs_internal.h"
 #include "geom_dev.cuh"
+#include <omp.h>
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -473,37 +474,40 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now_s();
 
-    // ---- host-side structure: active poses, CSR by landmark / pose, per-block pair lists
+    // ---- host-side structure: active poses, CSR by landmark / pose, per-block pair lists.  The problems are independent:
+    // each is built into its own vectors by an OpenMP team (the windows of one step come from different streams), then the
+    // per-problem pieces are laid out back to back with prefix offsets.
+    struct Built {
+        std::vector<int32_t> act_pose, l_off, p_off, blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off, lg_off, g_lm, g_pose, pg_off, pg_groups;
+        int bad = 0;
+    };
     std::vector<BaProb> probs(n_prob);
-    std::vector<int32_t> act_pose, edge_p(sumE), l_off, l_edges(sumE), p_off, p_edges(sumE), blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off, lg_off, g_lm, g_pose, pg_off, pg_groups;
-    long long pairs_total = 0;
-    l_off.reserve((size_t)sumL + n_prob); lg_off.reserve((size_t)sumL + n_prob); g_lm.reserve(sumE); g_pose.reserve(sumE);
-    pg_groups.reserve(sumE); pr_e1.reserve(2 * (size_t)sumE); pr_e2.reserve(2 * (size_t)sumE);
-    ch_blk.reserve((size_t)sumE / 4 + 64 * (size_t)n_prob); ch_off.reserve((size_t)sumE / 4 + 65 * (size_t)n_prob);
+    std::vector<Built> built(n_prob);
+    std::vector<int32_t> edge_p(sumE), l_edges(sumE), p_edges(sumE);
     const size_t smem_cap = 200 * 1024;
-    size_t max_smem = 0;
-    long long S_tot = 0;
+    const int omp_team = c->host_threads > 0 ? c->host_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(omp_team)
     for (int b = 0; b < n_prob; b++) {
         int N = kf_off[b + 1] - kf_off[b], L = lm_off[b + 1] - lm_off[b], E = e_off[b + 1] - e_off[b], e0 = e_off[b];
         BaProb &P = probs[b];
+        Built &B = built[b];
         std::vector<int> pidx(N, -1);
         for (int e = 0; e < E; e++) {
             int k = edge_kf[e0 + e], l = edge_lm[e0 + e];
-            if (k < 0 || k >= N || l < 0 || l >= L) SVS_FAIL(c, SVS_ERR_ARG, "ba: edge index out of range");
+            if (k < 0 || k >= N || l < 0 || l >= L) { B.bad = 1; break; }
             pidx[k] = 0;
         }
-        P.act0 = (int)act_pose.size();
+        if (B.bad) continue;
         int NA = 0;
-        for (int k = 0; k < N; k++) if (pidx[k] == 0) { pidx[k] = NA++; act_pose.push_back(k); }
+        for (int k = 0; k < N; k++) if (pidx[k] == 0) { pidx[k] = NA++; B.act_pose.push_back(k); }
         P.NA = NA; P.L = L; P.E = E; P.pose0 = kf_off[b]; P.lm0 = lm_off[b]; P.e0 = e0;
         for (int e = 0; e < E; e++) edge_p[e0 + e] = pidx[edge_kf[e0 + e]];
         // CSR by landmark; inside a landmark the edges are listed pose-ascending (stable: creation order inside a pose),
         // so that the edges of one GROUP = (landmark, pose) form a run
-        P.loff0 = (int)l_off.size();
         std::vector<int> cnt(L + 1, 0);
         for (int e = 0; e < E; e++) cnt[edge_lm[e0 + e] + 1]++;
         for (int l = 0; l < L; l++) cnt[l + 1] += cnt[l];
-        for (int l = 0; l <= L; l++) l_off.push_back(cnt[l]);
+        B.l_off.assign(cnt.begin(), cnt.end());
         { std::vector<int> fill(cnt.begin(), cnt.end() - 1);
           for (int e = 0; e < E; e++) l_edges[e0 + fill[edge_lm[e0 + e]]++] = e; }
         for (int l = 0; l < L; l++) {      // stable insertion sort: a landmark has a handful of edges
@@ -517,39 +521,36 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
             }
         }
         // CSR by active pose
-        P.poff0 = (int)p_off.size();
         std::vector<int> pc(NA + 1, 0);
         for (int e = 0; e < E; e++) pc[edge_p[e0 + e] + 1]++;
         for (int a = 0; a < NA; a++) pc[a + 1] += pc[a];
-        for (int a = 0; a <= NA; a++) p_off.push_back(pc[a]);
+        B.p_off.assign(pc.begin(), pc.end());
         { std::vector<int> fill(pc.begin(), pc.end() - 1);
           for (int e = 0; e < E; e++) p_edges[e0 + fill[edge_p[e0 + e]]++] = e; }
         // groups, landmark-major / pose-ascending; CSR by landmark and by pose
-        P.grp0 = (int)g_lm.size(); P.lgoff0 = (int)lg_off.size(); P.pgoff0 = (int)pg_off.size();
         int G = 0;
         std::vector<int> pgc(NA + 1, 0);
+        B.lg_off.reserve(L + 1); B.g_lm.reserve(E); B.g_pose.reserve(E);
         for (int l = 0; l < L; l++) {
-            lg_off.push_back(G);
+            B.lg_off.push_back(G);
             int cur = -1;
             for (int s1 = cnt[l]; s1 < cnt[l + 1]; s1++) {
                 int pp = edge_p[e0 + l_edges[e0 + s1]];
-                if (pp != cur) { cur = pp; g_lm.push_back(l); g_pose.push_back(pp); pgc[pp + 1]++; G++; }
+                if (pp != cur) { cur = pp; B.g_lm.push_back(l); B.g_pose.push_back(pp); pgc[pp + 1]++; G++; }
             }
         }
-        lg_off.push_back(G);
+        B.lg_off.push_back(G);
         P.G = G;
         for (int a = 0; a < NA; a++) pgc[a + 1] += pgc[a];
-        for (int a = 0; a <= NA; a++) pg_off.push_back(pgc[a]);
+        B.pg_off.assign(pgc.begin(), pgc.end());
         { std::vector<int> fill(pgc.begin(), pgc.end() - 1);
-          pg_groups.resize((size_t)P.grp0 + G);
-          for (int g = 0; g < G; g++) pg_groups[P.grp0 + fill[g_pose[P.grp0 + g]]++] = g; }
+          B.pg_groups.resize(G);
+          for (int g = 0; g < G; g++) B.pg_groups[fill[B.g_pose[g]]++] = g; }
         // (group, group) pairs per upper block (i <= j): the groups of a landmark have distinct, ascending poses, so the
         // pairs are (a, b) with a <= b in list order.  Sorted by block id i*NA + j (counting sort; inside a block in
         // landmark order), then cut into chunks of <= BA_CH pairs that never span two blocks
-        P.blk0 = (int)blk_i.size(); P.bch0 = (int)blk_ch.size(); P.pair0 = (int)pr_e1.size();
-        P.ch0 = (int)ch_blk.size(); P.choff0 = (int)ch_off.size(); P.part0 = (long long)ch_blk.size();
         std::vector<int> bcount((size_t)NA * NA + 1, 0);
-        const int32_t *lgo = lg_off.data() + P.lgoff0, *gp = g_pose.data() + P.grp0;
+        const int32_t *lgo = B.lg_off.data(), *gp = B.g_pose.data();
         for (int l = 0; l < L; l++)
             for (int g1 = lgo[l]; g1 < lgo[l + 1]; g1++)
                 for (int g2 = g1; g2 < lgo[l + 1]; g2++) bcount[(size_t)gp[g1] * NA + gp[g2] + 1]++;
@@ -559,27 +560,56 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
             int cn = bcount[k + 1];
             if (cn > 0) {
                 nblk++; bstart[k] = run;
-                blk_i.push_back((int)(k / NA)); blk_j.push_back((int)(k % NA));
-                blk_ch.push_back(nch);
-                for (int c0 = 0; c0 < cn; c0 += BA_CH) { ch_blk.push_back(nblk - 1); ch_off.push_back(run + c0); nch++; }
+                B.blk_i.push_back((int)(k / NA)); B.blk_j.push_back((int)(k % NA));
+                B.blk_ch.push_back(nch);
+                for (int c0 = 0; c0 < cn; c0 += BA_CH) { B.ch_blk.push_back(nblk - 1); B.ch_off.push_back(run + c0); nch++; }
                 run += cn;
             }
         }
-        blk_ch.push_back(nch);
-        ch_off.push_back(run);
+        B.blk_ch.push_back(nch);
+        B.ch_off.push_back(run);
         P.nblk = nblk; P.nch = nch;
-        size_t pbase = pr_e1.size();
-        pr_e1.resize(pbase + run); pr_e2.resize(pbase + run);
+        B.pr_e1.resize(run); B.pr_e2.resize(run);
         for (int l = 0; l < L; l++)
             for (int g1 = lgo[l]; g1 < lgo[l + 1]; g1++)
                 for (int g2 = g1; g2 < lgo[l + 1]; g2++) {
                     int q = bstart[(size_t)gp[g1] * NA + gp[g2]]++;
-                    pr_e1[pbase + q] = g1; pr_e2[pbase + q] = g2;
+                    B.pr_e1[q] = g1; B.pr_e2[q] = g2;
                 }
-        pairs_total += run;
-        if (ba_smem_need(NA, 2) <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, ba_smem_need(NA, 2)); }
-        else if (ba_smem_need(NA, 1) <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, ba_smem_need(NA, 1)); }
-        else { P.S_off = S_tot; size_t np = 6 * (size_t)NA; S_tot += (long long)(np * (np | 1)); max_smem = std::max(max_smem, ba_smem_need(NA, 0)); }
+    }
+    // ---- lay the pieces out back to back
+    std::vector<int32_t> act_pose, l_off, p_off, blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off, lg_off, g_lm, g_pose, pg_off, pg_groups;
+    size_t max_smem = 0;
+    long long S_tot = 0;
+    {
+        size_t n_act = 0, n_lo = 0, n_po = 0, n_blk = 0, n_bch = 0, n_pr = 0, n_ch = 0, n_co = 0, n_lg = 0, n_g = 0, n_pgo = 0;
+        for (int b = 0; b < n_prob; b++) {
+            if (built[b].bad) SVS_FAIL(c, SVS_ERR_ARG, "ba: edge index out of range");
+            BaProb &P = probs[b];
+            const Built &B = built[b];
+            P.act0 = (int)n_act; P.loff0 = (int)n_lo; P.poff0 = (int)n_po; P.blk0 = (int)n_blk; P.bch0 = (int)n_bch; P.pair0 = (int)n_pr;
+            P.ch0 = (int)n_ch; P.choff0 = (int)n_co; P.part0 = (long long)n_ch; P.grp0 = (int)n_g; P.lgoff0 = (int)n_lg; P.pgoff0 = (int)n_pgo;
+            n_act += B.act_pose.size(); n_lo += B.l_off.size(); n_po += B.p_off.size(); n_blk += B.blk_i.size(); n_bch += B.blk_ch.size();
+            n_pr += B.pr_e1.size(); n_ch += B.ch_blk.size(); n_co += B.ch_off.size(); n_lg += B.lg_off.size(); n_g += B.g_lm.size();
+            n_pgo += B.pg_off.size();
+            const int NA = P.NA;
+            if (ba_smem_need(NA, 2) <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, ba_smem_need(NA, 2)); }
+            else if (ba_smem_need(NA, 1) <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, ba_smem_need(NA, 1)); }
+            else { P.S_off = S_tot; size_t np = 6 * (size_t)NA; S_tot += (long long)(np * (np | 1)); max_smem = std::max(max_smem, ba_smem_need(NA, 0)); }
+        }
+        act_pose.resize(n_act); l_off.resize(n_lo); p_off.resize(n_po); blk_i.resize(n_blk); blk_j.resize(n_blk); blk_ch.resize(n_bch);
+        pr_e1.resize(n_pr); pr_e2.resize(n_pr); ch_blk.resize(n_ch); ch_off.resize(n_co); lg_off.resize(n_lg); g_lm.resize(n_g);
+        g_pose.resize(n_g); pg_off.resize(n_pgo); pg_groups.resize(n_g);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(omp_team)
+        for (int b = 0; b < n_prob; b++) {
+            const BaProb &P = probs[b];
+            const Built &B = built[b];
+            auto put = [](std::vector<int32_t> &dst, size_t at, const std::vector<int32_t> &src) { if (!src.empty()) memcpy(dst.data() + at, src.data(), src.size() * 4); };
+            put(act_pose, P.act0, B.act_pose); put(l_off, P.loff0, B.l_off); put(p_off, P.poff0, B.p_off); put(blk_i, P.blk0, B.blk_i);
+            put(blk_j, P.blk0, B.blk_j); put(blk_ch, P.bch0, B.blk_ch); put(pr_e1, P.pair0, B.pr_e1); put(pr_e2, P.pair0, B.pr_e2);
+            put(ch_blk, P.ch0, B.ch_blk); put(ch_off, P.choff0, B.ch_off); put(lg_off, P.lgoff0, B.lg_off); put(g_lm, P.grp0, B.g_lm);
+            put(g_pose, P.grp0, B.g_pose); put(pg_off, P.pgoff0, B.pg_off); put(pg_groups, P.grp0, B.pg_groups);
+        }
     }
     if (max_smem > 220 * 1024) SVS_FAIL(c, SVS_ERR_CAPACITY, "ba: window too large for the single-CTA solver");
 
@@ -617,7 +647,14 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     SVS_CUDA(c, c->h_in.reserve(tot + 16));
     SVS_CUDA(c, c->d_in2.reserve(tot + 16));
     uint8_t *hb = c->h_in.as<uint8_t>(), *db = c->d_in2.as<uint8_t>();
-    for (const Seg &s : segs) if (s.bytes) memcpy(hb + s.off, s.src, s.bytes);
+    {   // parallel pack: the big segments (pair lists, edge arrays) are cut into 256 KB pieces
+        struct Piece { const uint8_t *src; uint8_t *dst; size_t n; };
+        std::vector<Piece> pieces;
+        for (const Seg &s : segs)
+            for (size_t o = 0; o < s.bytes; o += 262144) pieces.push_back({(const uint8_t *)s.src + o, hb + s.off + o, std::min<size_t>(262144, s.bytes - o)});
+#pragma omp parallel for schedule(static) num_threads(omp_team)
+        for (int i = 0; i < (int)pieces.size(); i++) memcpy(pieces[i].dst, pieces[i].src, pieces[i].n);
+    }
     SVS_CUDA(c, cudaMemcpyAsync(db, hb, tot, cudaMemcpyHostToDevice, c->stream));
     // scratch
     size_t sc_b = (sumG * 36 + (size_t)sumL * 27 + (size_t)S_tot + ch_blk.size() * 36) * 8 + 64;

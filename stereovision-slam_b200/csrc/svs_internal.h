@@ -64,6 +64,7 @@ struct svs_ctx {
     long long prof_n[KID_COUNT] = {0};
     int device = 0;
     int sm_count = 0;
+    int host_threads = 0;   // OpenMP team size for host-side problem construction in this context's calls (0 = OpenMP's default)
     int zc_ctas = 0;    // persistent grid of the zero-copy (PCIe) ingest kernel: 0 = automatic (svs_i_zc_grid), env SVS_ZC_CTAS overrides
     cudaStream_t stream = nullptr;
     cudaStream_t stream_in = nullptr;   // ingest stream: prefetch of the NEXT frame pair overlaps this step's compute

@@ -78,7 +78,7 @@ public:
     int upload_states();             // hand the streams the host touched in this step back to the device
     int run_lk(int pair, bool (*sel)(const Stream &));
 
-    void set_threads(int n) { threads_ = n > 0 ? n : 1; }
+    void set_threads(int n) { threads_ = n > 0 ? n : 1; ctx_->host_threads = threads_; }
     void hint_next(const uint8_t *const *l, const uint8_t *const *r)
     {
         next_left_.assign(l, l + n()); next_right_.assign(r, r + n());
@@ -410,6 +410,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
             int sN = off_[np], sL = off2_[np], sE = off3_[np];
             d0_.resize((size_t)7 * sN); d1_.resize((size_t)3 * sL + 1); d2_.resize((size_t)2 * sE); d3_.resize(sE);
             i0_.resize(sE); i1_.resize(sE); u0_.resize(sE); bast_.resize(np);
+#pragma omp parallel for schedule(static) num_threads(threads_)
             for (int k = 0; k < np; k++) {
                 const BaRequest &q = streams_[ids_[k]].ba;
                 memcpy(&d0_[7 * (size_t)off_[k]], q.poses.data(), q.poses.size() * 8);
@@ -426,11 +427,15 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
                                  u0_.data(), d2_.data(), Kl, Kr, el.d, er.d, cfg_.chi2_th, cfg_.ba_max_iter, cfg_.ba_jacobian_mode,
                                  d3_.data(), bast_.data());
             if (rc) return rc;
+#pragma omp parallel for schedule(static) num_threads(threads_)
             for (int k = 0; k < np; k++) {
                 BaRequest &q = streams_[ids_[k]].ba;
                 memcpy(q.poses.data(), &d0_[7 * (size_t)off_[k]], q.poses.size() * 8);
                 if (!q.lms.empty()) memcpy(q.lms.data(), &d1_[3 * (size_t)off2_[k]], q.lms.size() * 8);
                 memcpy(q.chi2.data(), &d3_[off3_[k]], q.chi2.size() * 8);
+            }
+            for (int k = 0; k < np; k++) {
+                const BaRequest &q = streams_[ids_[k]].ba;
                 ba_iterations += bast_[k].iterations; ba_trials += bast_[k].trials; ba_edges += (long long)q.edge_kf.size();
                 ba_lms += (long long)q.lm_ids.size(); ba_kfs += (long long)q.kf_ids.size();
             }

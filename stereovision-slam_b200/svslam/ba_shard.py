@@ -1,13 +1,13 @@
-"""Driver of the landmark-sharded bundle adjustment (svs_ba_shard_*): g2o's Levenberg-Marquardt control loop
- in the caller, with the three per-trial reductions done by `allreduce` — NCCL through
-torch.distributed for one shard per GPU, a plain sum for several shards on one GPU (tests), identity for one shard.
-The buffers that are reduced live in torch CUDA tensors; the kernels write into them through their data_ptr."""
+"""Landmark-sharded bundle adjustment (svs_ba_shard_*): thin wrappers around the C entry points.  The Levenberg-Marquardt
+loop — g2o's control flow, SURVEY.md Appendix B.2 — runs entirely inside one cooperative kernel per GPU
+(svs_ba_shard_optimize), and the kernels of the ranks exchange their partial reduced systems themselves through peer
+memory.  What is left here is plumbing: splitting a problem by landmarks, and handing every rank the other ranks' exchange
+windows (CUDA IPC handles carried by torch.distributed, or plain pointers for several shards inside one process)."""
 import ctypes as C
 
 import numpy as np
-import torch
 
-from . import _p, _f64, _i32, _u8, SvsError
+from . import _p, _f64, _i32, _u8, SvsError, BaStats
 
 
 class Shard:
@@ -24,31 +24,43 @@ class Shard:
                                          C.c_double(huber_delta), jac_mode)
         if not self.h:
             raise SvsError("svs_ba_shard_create failed: " + ctx.last_error())
-        dev = torch.device("cuda", torch.cuda.current_device())
-        self.lin = torch.zeros(42 * self.N + 2, dtype=torch.float64, device=dev)
-        self.maxdiag = torch.zeros(1, dtype=torch.float64, device=dev)
-        self.red = torch.zeros(36 * self.N * self.N + 6 * self.N, dtype=torch.float64, device=dev)
-        self.flag = torch.ones(1, dtype=torch.int32, device=dev)
-        self.tri = torch.zeros(4, dtype=torch.float64, device=dev)
-        # the fills above run on torch's current stream, the svs_ba_shard_* kernels on the context's own non-blocking stream:
-        # nothing else orders the two, so the fills must have landed before the first kernel writes these buffers
-        torch.cuda.synchronize(dev)
+        self._imported = []
 
-    def _v(self, t):
-        return C.c_void_p(t.data_ptr())
+    def window(self):
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self.ctx._chk(self.ctx.lib.svs_ba_shard_window(C.c_void_p(self.h), C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
 
-    def linearize(self):
-        self.ctx._chk(self.ctx.lib.svs_ba_shard_linearize(C.c_void_p(self.ctx.h), C.c_void_p(self.h), self._v(self.lin), self._v(self.maxdiag)))
+    def set_peers(self, rank, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+        self.ctx._chk(self.ctx.lib.svs_ba_shard_set_peers(C.c_void_p(self.ctx.h), C.c_void_p(self.h), len(ptrs), rank, arr))
 
-    def schur(self, lam):
-        self.ctx._chk(self.ctx.lib.svs_ba_shard_schur(C.c_void_p(self.ctx.h), C.c_void_p(self.h), C.c_double(lam), self._v(self.red), self._v(self.flag)))
+    def set_grid_limit(self, n):
+        self.ctx._chk(self.ctx.lib.svs_ba_shard_set_grid_limit(C.c_void_p(self.h), int(n)))
 
-    def try_step(self, lin, red, lam, flag_ok):
-        self.ctx._chk(self.ctx.lib.svs_ba_shard_try(C.c_void_p(self.ctx.h), C.c_void_p(self.h), self._v(lin), self._v(red), C.c_double(lam),
-                                                    int(flag_ok), self._v(self.tri)))
+    def launch(self, max_iter=10):
+        self.ctx._chk(self.ctx.lib.svs_ba_shard_launch(C.c_void_p(self.ctx.h), C.c_void_p(self.h), int(max_iter)))
 
-    def accept(self):
-        self.ctx._chk(self.ctx.lib.svs_ba_shard_accept(C.c_void_p(self.ctx.h), C.c_void_p(self.h)))
+    def finish(self):
+        st = BaStats()
+        self.ctx._chk(self.ctx.lib.svs_ba_shard_finish(C.c_void_p(self.ctx.h), C.c_void_p(self.h), C.byref(st)))
+        return stats_dict(st)
+
+    def optimize(self, max_iter=10):
+        self.launch(max_iter)
+        return self.finish()
+
+    def export_handle(self):
+        h = (C.c_ubyte * 64)()
+        self.ctx._chk(self.ctx.lib.svs_ipc_export(C.c_void_p(self.ctx.h), C.c_void_p(self.window()[0]), h))
+        return bytes(h)
+
+    def import_handle(self, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        ptr = C.c_void_p()
+        self.ctx._chk(self.ctx.lib.svs_ipc_import(C.c_void_p(self.ctx.h), buf, C.byref(ptr)))
+        self._imported.append(ptr.value)
+        return ptr.value
 
     def get(self):
         poses = np.zeros((self.N, 7)); lms = np.zeros((self.L, 3)); chi2 = np.zeros(max(self.E, 1))
@@ -57,8 +69,17 @@ class Shard:
 
     def close(self):
         if self.h:
+            self.ctx.sync()
+            for p in self._imported:
+                self.ctx.lib.svs_ipc_release(C.c_void_p(self.ctx.h), C.c_void_p(p))
+            self._imported = []
             self.ctx.lib.svs_ba_shard_destroy(C.c_void_p(self.ctx.h), C.c_void_p(self.h))
             self.h = None
+
+
+def stats_dict(st):
+    return dict(iterations=int(st.iterations), trials=int(st.trials), linearizations=int(st.linearizations), chi2=float(st.chi2),
+                chi2_init=float(st.chi2_init), lam=float(st.lambda_))
 
 
 def split_problem(prob, world):
@@ -80,76 +101,43 @@ def split_problem(prob, world):
     return out
 
 
-def lm_optimize(shards, max_iter=10, dist=None):
-    """Levenberg-Marquardt over one or more shards.  `shards` = the Shard objects THIS process owns (several on one
-    GPU in tests, exactly one per rank under torch.distributed).  Returns stats dict; state stays in the shards."""
-    def allsum(tensors):
-        t = tensors[0] if len(tensors) == 1 else torch.stack(tensors).sum(0)
-        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return t
+def exchange_handles(my_handle, rank, world, all_gather):
+    """Every rank's 64-byte window handle, in rank order.  all_gather(bytes) -> list of bytes is the only thing asked of the
+    bootstrap (torch.distributed over gloo or NCCL, MPI, ...)."""
+    handles = all_gather(my_handle)
+    if len(handles) != world or handles[rank] != my_handle or any(len(h) != 64 for h in handles):
+        raise SvsError("window handle exchange failed")
+    return handles
 
-    def allmax(tensors):
-        t = tensors[0] if len(tensors) == 1 else torch.stack(tensors).max(0).values
-        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t
 
-    def allmin(tensors):
-        t = tensors[0] if len(tensors) == 1 else torch.stack(tensors).min(0).values
-        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        return t
+def wire_distributed(shard, dist):
+    """One shard per rank of a torch.distributed process group (one process per GPU): map the peers' windows (CUDA IPC)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        return
 
-    ctx = shards[0].ctx
-    N = shards[0].N
-    lam, ni = 0.0, 2.0
-    st = dict(iterations=0, trials=0, chi2=0.0, chi2_init=0.0, lam=0.0)
-    for it in range(max_iter):
-        for s in shards:
-            s.linearize()
-        ctx.sync()
-        lin = allsum([s.lin for s in shards])
-        cur = float(lin[42 * N].item())
-        if it == 0:
-            st["chi2_init"] = cur
-            # the pose diagonal must be taken from the SUMMED Hpp, the landmark diagonals are local
-            md_l = float(allmax([s.maxdiag for s in shards]).item())
-            hpp = lin[:36 * N].view(N, 6, 6)
-            md_p = float(torch.diagonal(hpp, dim1=1, dim2=2).abs().max().item())
-            lam, ni = 1e-5 * max(md_l, md_p), 2.0
-        rho, q = 0.0, 0
-        while True:
-            for s in shards:
-                s.schur(lam)
-            ctx.sync()
-            red = allsum([s.red for s in shards])
-            ok = int(allmin([s.flag for s in shards]).item())
-            for s in shards:
-                s.try_step(lin, red, lam, ok)
-            ctx.sync()
-            loc = allsum([s.tri[:2] for s in shards]).cpu().numpy()
-            pose_scale, solved = float(shards[0].tri[2].item()), float(shards[0].tri[3].item()) != 0.0
-            tmp = float(loc[0]) if solved else np.finfo(np.float64).max
-            scale = pose_scale + float(loc[1]) + 1e-3
-            rho = (cur - tmp) / scale
-            q += 1
-            st["trials"] += 1
-            if rho > 0 and np.isfinite(tmp):
-                alpha = min(1.0 - (2 * rho - 1) ** 3, 2.0 / 3.0)
-                lam *= max(1.0 / 3.0, alpha)
-                ni = 2.0
-                cur = tmp
-                for s in shards:
-                    s.accept()
-            else:
-                lam *= ni
-                ni *= 2
-            if not (rho < 0 and q < 10):
-                break
-        st["iterations"] += 1
-        st["chi2"], st["lam"] = cur, lam
-        if q == 10 or rho == 0:
-            break
-    ctx.sync()
-    return st
+    def all_gather(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+    handles = exchange_handles(shard.export_handle(), rank, world, all_gather)
+    own = shard.window()[0]
+    shard.set_peers(rank, [own if r == rank else shard.import_handle(handles[r]) for r in range(world)])
+    dist.barrier()
+
+
+def wire_local(shards, sm_count=148):
+    """Several shards inside ONE process on ONE GPU (tests): plain device pointers; every shard must sit on its own context
+    (its own stream) and all kernels must be resident together, so each gets an equal slice of the SMs."""
+    ptrs = [s.window()[0] for s in shards]
+    for r, s in enumerate(shards):
+        s.set_peers(r, ptrs)
+        s.set_grid_limit(max(1, sm_count // len(shards)))
+
+
+def optimize_all(shards, max_iter=10):
+    """Launch the cooperative solvers of all local shards, then wait for all of them; returns the (identical) statistics."""
+    for s in shards:
+        s.launch(max_iter)
+    sts = [s.finish() for s in shards]
+    return sts[0], sts

@@ -55,35 +55,43 @@ def test_reference_arm_prints_the_contract_line():
 def test_gpu_arm_report_block_dry_run():
     """The part of bench.py's GPU arm that turns the measured regions into the JSON line (roofline, traffic, per-kernel view,
     e2e bytes) executed on fabricated measurements: it must produce every key of the bench contract."""
-    import textwrap
     import types
-    src = open(os.path.join(ROOT, "bench.py")).read()
-    a = src.index("    # ---- roofline of the dominant kernel")
-    b = src.index("    print(json.dumps(out))\n    if dist is not None:")
-    block = textwrap.dedent(src[a:b])
+    b = _bench()
     names = ("push", "track_lk", "pose_lm", "detect", "right_lk", "triangulate", "ba", "host")
     cn = ("frames", "keyframes", "ba_problems", "ba_iterations", "ba_trials", "ba_edges", "ba_lms", "ba_kfs", "lk_points", "pose_edges",
           "h2d_image_bytes", "right_images")
     kernels = ["k_half_nearest", "k_pyr_down", "k_mask_boxes", "k_corner_response", "k_corner_select", "k_corner_greedy", "k_lk_track",
-               "k_triangulate", "k_pose_only_lm", "k_ba_window"]
+               "k_triangulate", "k_pose_only_lm", "k_ba_window", "k_trk_state"]
     p = dict(ms=1200.0, wall=1.2, launches=12000, phases={k: 1.0 for k in names}, counts={k: 1000 + i for i, k in enumerate(cn)},
              kern={k: (100.0 + i, 50 + i) for i, k in enumerate(kernels)}, lost=0)
-    ns = {}
-    exec("import os, sys, json, subprocess, time\nimport numpy as np\n", ns)
-    ns.update(ROOT=ROOT, METRIC="stereo_frames_per_sec", UNIT="frames/s", WORKLOAD="w", C=None, log=print, save_clip=None, L=None, R=None,
-              args=types.SimpleNamespace(no_cpu_baseline=True, steps=60, warmup=5, eager_right=False, no_prefetch=False, stagger=40,
-                                         priming=150, h2d_mode=2, cpu_frames=0),
-              kern_pass=p, dev_pass=dict(p, kern={}), e2e_pass=p, cor=types.SimpleNamespace(W=1226, H=370), B=4096, G=16, world=1,
-              clocks={"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": []}, ba4=None, ate=None, diag=None, nclip=48, cores=16,
-              host_threads=1, value=2e5, e2e=1.5e5, img_bytes=1226 * 370)
-    exec(block, ns)
-    out = json.loads(json.dumps(ns["out"]))
+    args = types.SimpleNamespace(no_cpu_baseline=True, steps=60, warmup=5, eager_right=False, no_prefetch=False, priming=-1, h2d_mode=2,
+                                 cpu_frames=0, host_tracking=False)
+    traffic = {"k_ba_window": dict(traffic=4.2e6, dur_us=900.0, dram_pct=0.1, issue_active_pct=30.0, fp64_pipe_pct=20.0, registers=128.0, grid="110"),
+               "k_lk_track": dict(traffic=1.6e7, dur_us=5000.0, dram_pct=0.7, issue_active_pct=70.0, fp64_pipe_pct=0.0, registers=80.0, grid="300000")}
+    out = b.build_report(args, 1, 4096, 2, types.SimpleNamespace(W=1226, H=370), b.CONFIGS[2], dict(p, kern={}), p, p,
+                         {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": []}, 6533.2, "measured", traffic, None, None, None, None,
+                         {"config_1": {"value": 1.0}}, 2256, 24, 16, 16, 8, 48)
+    out = json.loads(json.dumps(out))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
               "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in out, k
-    assert out["config"]["workload"] == "w" and "model" not in out["config"]
+    assert out["config"]["workload"] == b.CONFIGS[2]["workload"] and "model" not in out["config"]
+    assert out["value"] == 4096 * 60 / 1.2 and out["config"]["distinct_sequences_per_gpu"] == 2256
+    assert "larger than" in out["config"]["l2"] and "NOT" not in out["config"]["l2"]
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(out["e2e"])
     r = out["roofline"]
     assert r["kernel"] == "k_ba_window" and r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    assert r["traffic"] is not None and r["traffic"] > 0
+    assert r["traffic"] == 4.2e6
     assert "k_lk_track" in out["detail"]["kernel_roofline"] and "ncu_standalone" in out["detail"]["kernel_roofline"]["k_lk_track"]
+    assert out["detail"]["config_1"] == {"value": 1.0}
+
+
+def test_variants_are_distinct_bytes():
+    import numpy as np
+    b = _bench()
+    img = np.random.RandomState(0).randint(0, 256, (4, 30, 40)).astype(np.uint8)
+    assert b.variant(img, 0) is img
+    v1, v2 = b.variant(img, 1), b.variant(img, 2)
+    assert v1.dtype == np.uint8 and v1.shape == img.shape and (v1 != img).mean() > 0.5 and (v1 != v2).mean() > 0.5
+    assert np.array_equal(v1, b.variant(img, 1))          # deterministic
+    assert abs(v1.astype(float).mean() - img.astype(float).mean()) < 20
