@@ -76,10 +76,16 @@ def pingpong(i, n):
     return p if p < n else 2 * n - 2 - p
 
 
+_COR = {}
+
+
 def _render_one(a):
     from svslam import synth
     calib, seed, n_frames, i, eye = a
-    return synth.Corridor(calib, seed=seed, n_frames=n_frames).render(i, eye)
+    key = (calib, seed, n_frames)
+    if key not in _COR:          # building the textured corridor costs seconds: once per worker process
+        _COR[key] = synth.Corridor(calib, seed=seed, n_frames=n_frames)
+    return _COR[key].render(i, eye)
 
 
 def make_clip(calib, n_frames, seed=5):
@@ -90,7 +96,7 @@ def make_clip(calib, n_frames, seed=5):
     jobs = [(calib, seed, n_frames, i, eye) for eye in (0, 1) for i in range(n_frames)]
     procs = max(1, min(len(jobs), (os.cpu_count() or 1)))
     with mp.get_context("spawn").Pool(procs) as pool:
-        imgs = pool.map(_render_one, jobs, chunksize=max(1, len(jobs) // (4 * procs)))
+        imgs = pool.map(_render_one, jobs, chunksize=max(1, (len(jobs) + procs - 1) // procs))
     L, R = np.stack(imgs[:n_frames]), np.stack(imgs[n_frames:])
     T = np.stack([cor.T_cw(i) for i in range(n_frames)])
     return cor, L, R, T

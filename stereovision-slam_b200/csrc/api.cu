@@ -153,7 +153,7 @@ void svs_destroy(svs_ctx *c)
     cudaStreamSynchronize(c->stream);
     prof_harvest(c);
     for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
-    DevBuf *d[] = {&c->d_in, &c->d_in2, &c->d_out, &c->d_out2, &c->d_tmp, &c->d_tmp2, &c->d_tmp3, &c->d_tmp4, &c->d_tmp5, &c->d_tmp6};
+    DevBuf *d[] = {&c->d_in, &c->d_in2, &c->d_out, &c->d_out2, &c->d_tmp, &c->d_tmp2, &c->d_tmp3, &c->d_tmp4, &c->d_tmp5, &c->d_tmp6, &c->d_tmp7};
     for (DevBuf *b : d) b->release();
     c->h_in.release(); c->h_out.release();
     cudaStreamDestroy(c->stream);
@@ -194,6 +194,18 @@ svs_frameset *svs_frameset_create(svs_ctx *c, int n_streams, int in_w, int in_h,
     }
     for (int i = 0; i < 3; i++) { fs->L[i] = d; fs->L[i].base = fs->pyr[i].as<uint8_t>(); }
     for (int i = 0; i < 2; i++) { fs->R[i] = d; fs->R[i].base = fs->pyr[3 + i].as<uint8_t>(); }
+    // TMA tensor maps (u8 [stream][H_l][W_l], out-of-image bytes read as zero) for the bulk-async staged kernels
+    fs->has_tmaps = true;
+    for (int i = 0; i < 5 && fs->has_tmaps; i++) {
+        const PyrDesc &pd = i < 3 ? fs->L[i] : fs->R[i - 3];
+        for (int l = 0; l < pd.nlev; l++)
+            if (svs_i_tmap_u8_3d(&fs->tm_pyr[i][l], pd.base + pd.off[l], pd.w[l], pd.h[l], n_streams, (size_t)pd.stride[l], pd.img_pitch,
+                                 SVS_PD_BOX_W, SVS_PD_BOX_H) != 0) { fs->has_tmaps = false; break; }
+        if (i < 3 && fs->has_tmaps &&
+            svs_i_tmap_u8_3d(&fs->tm_gftt[i], pd.base + pd.off[0], pd.w[0], pd.h[0], n_streams, (size_t)pd.stride[0], pd.img_pitch,
+                             SVS_CR_BOX_W, SVS_CR_BOX_H) != 0) fs->has_tmaps = false;
+    }
+    if (!fs->has_tmaps) { c->err = "frameset: cuTensorMapEncodeTiled failed"; svs_frameset_destroy(c, fs); return nullptr; }
     if (cudaEventCreateWithFlags(&fs->pf_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fs->pf_order, cudaEventDisableTiming) != cudaSuccess) {
         c->err = "frameset: cudaEventCreate failed";
@@ -272,8 +284,8 @@ static int frameset_fill(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc, const 
         SVS_TRY(svs_i_copy_level0(c, dl, fs->in_w, fs->in_h, rs, is, n_img, Lc, pl, ids_dev));
         if (Rc) SVS_TRY(svs_i_copy_level0(c, dr, fs->in_w, fs->in_h, rs, is, n_img, *Rc, pr, ids_dev));
     }
-    SVS_TRY(svs_i_build_pyramid(c, Lc, n_img, ids_dev));
-    if (Rc) SVS_TRY(svs_i_build_pyramid(c, *Rc, n_img, ids_dev));
+    SVS_TRY(svs_i_build_pyramid(c, Lc, n_img, ids_dev, fs->maps_of(Lc)));
+    if (Rc) SVS_TRY(svs_i_build_pyramid(c, *Rc, n_img, ids_dev, fs->maps_of(*Rc)));
     return SVS_OK;
 }
 
@@ -441,7 +453,7 @@ int svs_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, int stride, i
 static int gftt_common(svs_ctx *c, const uint8_t *img_dev, int w, int h, int stride, size_t img_pitch, int n_img,
                        const int32_t *ids_host, const uint8_t *mask_host, int mask_stride,
                        const int32_t *occ_off_host, const float *occ_xy_host, int max_corners, double quality,
-                       double min_distance, int granule, float *out_xy, float *out_resp, int32_t *out_n)
+                       double min_distance, int granule, float *out_xy, float *out_resp, int32_t *out_n, const CUtensorMap *tm = nullptr)
 {
     if (max_corners <= 0) SVS_FAIL(c, SVS_ERR_ARG, "gftt: max_corners must be > 0");
     int n_occ = occ_off_host ? occ_off_host[n_img] : 0;
@@ -472,7 +484,7 @@ static int gftt_common(svs_ctx *c, const uint8_t *img_dev, int w, int h, int str
     uint8_t *dob = c->d_out.as<uint8_t>();
     SVS_TRY(svs_i_gftt(c, img_dev, w, h, stride, img_pitch, n_img, ids_dev, mask_dev, off_dev, xy_dev, n_occ, max_corners,
                        quality, min_distance, granule, reinterpret_cast<float *>(dob), reinterpret_cast<float *>(dob + oxy_b),
-                       reinterpret_cast<int32_t *>(dob + oxy_b + orp_b), nullptr));
+                       reinterpret_cast<int32_t *>(dob + oxy_b + orp_b), nullptr, tm));
     uint8_t *hob = c->h_out.as<uint8_t>();
     SVS_CUDA(c, cudaMemcpyAsync(hob, dob, oxy_b + orp_b + on_b, cudaMemcpyDeviceToHost, c->stream));
     int *ovf = reinterpret_cast<int *>(hob + align_up(oxy_b + orp_b + on_b, 4));
@@ -528,7 +540,8 @@ int svs_gftt_detect_batch(svs_ctx *c, svs_frameset *fs, const int32_t *stream_id
     SVS_CUDA(c, cudaSetDevice(c->device));
     const PyrDesc &L = fs->Lcur();
     return gftt_common(c, L.base + L.off[0], fs->W, fs->H, L.stride[0], L.img_pitch, n_sel, stream_ids, nullptr, 0, occ_off,
-                       occupied_xy, max_corners, quality, min_distance, granule, out_xy, out_response, out_n);
+                       occupied_xy, max_corners, quality, min_distance, granule, out_xy, out_response, out_n,
+                       fs->has_tmaps ? &fs->tm_gftt[fs->il_cur] : nullptr);
 }
 
 // ------------------------------------------------------------------ a2 / a3

@@ -12,6 +12,8 @@
 // Compile this file with --fmad=false: every float operation below must round exactly once where
 // OpenCV rounds; the fused operations are spelled __fmaf_rn explicitly.
 #include "svs_internal.h"
+#include "tma.cuh"
+#include <algorithm>
 #include <climits>
 
 __device__ __forceinline__ int g_refl101(int i, int n)
@@ -57,7 +59,7 @@ struct RowF { float rx, ry; };
 __global__ void __launch_bounds__(128)
 k_corner_response(const uint8_t *__restrict__ img_base, size_t img_pitch, const int32_t *__restrict__ img_ids,
                   int w, int h, int stride, const uint8_t *__restrict__ mask, float *__restrict__ eig,
-                  unsigned *__restrict__ maxbits, float ks, float k2, int body)
+                  unsigned *__restrict__ maxbits, float ks, float k2, int body, const int *__restrict__ only_if)
 {
     const unsigned FULL = 0xffffffffu;
     int lane = threadIdx.x & 31;
@@ -65,6 +67,7 @@ k_corner_response(const uint8_t *__restrict__ img_base, size_t img_pitch, const 
     int n_strips = (w + CR_OUT - 1) / CR_OUT;
     if (strip >= n_strips) return;
     int slot = blockIdx.y;
+    if (only_if && !only_if[slot]) return;      // fallback pass of the tiled kernel: only images it flagged as inexact
     int img = img_ids ? img_ids[slot] : slot;
     const uint8_t *src = img_base + (size_t)img * img_pitch;
     float *out = eig + (size_t)slot * w * h;
@@ -146,6 +149,156 @@ k_corner_response(const uint8_t *__restrict__ img_base, size_t img_pitch, const 
     unsigned mb = any ? f2ord(vmax) : 0u;
     for (int o = 16; o > 0; o >>= 1) mb = max(mb, __shfl_xor_sync(FULL, mb, o));
     if (lane == 0 && mb) atomicMax(maxbits + slot, mb);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tiled, TMA-staged corner response (the batched path).  The sequential march above exists because OpenCV's box filter keeps
+// a RUNNING f64 column sum (SUM += new row; out = SUM; SUM -= old row), whose rounding depends on the history of the column.
+// But its intermediate values are only ever T_y = rs(y) + rs(y+1) and O_y = T_(y-1) + rs(y+1) (rs = f64 row sums of three f32
+// products): if every one of those sums is EXACTLY representable, every add / subtract of the running scheme is exact and the
+// result is the exact sum, whatever the order.  For 8-bit images that is always the case (the products span < 2^-1 .. 2^-47,
+// 46 bits < 53).  So: tiles compute out = (rs(y-1) + rs(y)) + rs(y+1) fully in parallel and CHECK exactness with TwoSum; a
+// tile that sees one inexact sum flags its image, and the flagged images (never seen so far) are recomputed by the
+// sequential kernel — bit-exactness is kept unconditionally, and the grid grows from 66 CTAs to one tile per 64x16 outputs.
+// Staging: the 96 x 20 source box (16 bytes left of the tile, see SVS_CR_BOX_W) arrives by cp.async.bulk.tensor (UTMALDG) into one of two buffers while the
+// previous tile is computed; zero-filled out-of-image bytes are patched to reflect-101 in shared memory.
+#define CT_W 64
+#define CT_H 16
+#define CT_BYTES (SVS_CR_BOX_W * SVS_CR_BOX_H)
+__device__ __forceinline__ bool twosum_exact(double a, double b, double s)
+{   // s = fl(a + b); exact iff the TwoSum error term is zero (no contraction: this file is built with --fmad=false)
+    const double bb = s - a;
+    return ((a - (s - bb)) + (b - bb)) == 0.0;
+}
+__global__ void __launch_bounds__(256)
+k_corner_response_tma(const __grid_constant__ CUtensorMap tm, const int32_t *__restrict__ img_ids, int n_slots, int w, int h,
+                      const uint8_t *__restrict__ mask, float *__restrict__ eig, unsigned *__restrict__ tile_max, int *__restrict__ inexact,
+                      float ks, float k2, int body, int tiles_x, int tiles_y)
+{
+    __shared__ __align__(128) uint8_t tile_s[2][1920];
+    __shared__ float rxs[SVS_CR_BOX_H][CT_W + 3], rys[SVS_CR_BOX_H][CT_W + 3];
+    __shared__ float cxx[CT_H + 2][CT_W + 3], cxy[CT_H + 2][CT_W + 3], cyy[CT_H + 2][CT_W + 3];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ unsigned s_max[8];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int per_img = tiles_x * tiles_y, total = n_slots * per_img;
+    if (tid == 0) { tma::mbar_init(&bar[0], 1); tma::mbar_init(&bar[1], 1); tma::fence_init(); }
+    __syncthreads();
+    auto issue = [&](int t, int buf) {
+        const int n = t / per_img, r = t - n * per_img, ty = r / tiles_x, tx = r - ty * tiles_x;
+        tma::mbar_expect_tx(&bar[buf], CT_BYTES);
+        tma::load_3d(tile_s[buf], &tm, &bar[buf], tx * CT_W - 16, ty * CT_H - 2, img_ids ? img_ids[n] : n);
+    };
+    int t = blockIdx.x;
+    if (tid == 0 && t < total) issue(t, 0);
+    for (int it = 0; t < total; t += gridDim.x, it++) {
+        const int buf = it & 1, tn = t + gridDim.x;
+        if (tid == 0 && tn < total) { tma::fence_proxy_async(); issue(tn, buf ^ 1); }
+        const int slot = t / per_img, r0 = t - slot * per_img, ty0 = r0 / tiles_x, tx0 = r0 - ty0 * tiles_x;
+        const int ox0 = tx0 * CT_W, oy0 = ty0 * CT_H, bx0 = ox0 - 16, by0 = oy0 - 2;
+        uint8_t *tb = tile_s[buf];
+        if (tid == 0) s_bad = 0;
+        tma::mbar_wait(&bar[buf], (it >> 1) & 1);
+        // image reflect-101 of the one row / column outside the image a Sobel window can touch (rows first, then columns)
+        if (by0 < 0 || by0 + SVS_CR_BOX_H > h) {
+            for (int i = tid; i < 2 * (SVS_CR_BOX_W / 4); i += 256) {
+                const int k = i / (SVS_CR_BOX_W / 4), q = i - k * (SVS_CR_BOX_W / 4);
+                const int y = k ? h : -1, ys = k ? h - 2 : 1, rd = y - by0, rs = ys - by0;
+                if (rd >= 0 && rd < SVS_CR_BOX_H && rs >= 0 && rs < SVS_CR_BOX_H)
+                    reinterpret_cast<uint32_t *>(tb + rd * SVS_CR_BOX_W)[q] = reinterpret_cast<const uint32_t *>(tb + rs * SVS_CR_BOX_W)[q];
+            }
+            __syncthreads();
+        }
+        if (bx0 < 0 || bx0 + SVS_CR_BOX_W > w) {
+            for (int i = tid; i < 2 * SVS_CR_BOX_H; i += 256) {
+                const int k = i / SVS_CR_BOX_H, r = i - k * SVS_CR_BOX_H;
+                const int x = k ? w : -1, xs = k ? w - 2 : 1, cd = x - bx0, cs = xs - bx0;
+                if (cd >= 0 && cd < SVS_CR_BOX_W && cs >= 0 && cs < SVS_CR_BOX_W) tb[r * SVS_CR_BOX_W + cd] = tb[r * SVS_CR_BOX_W + cs];
+            }
+        }
+        __syncthreads();
+        // stage 1: Sobel row pass at tile rows 0..19 (image y = by0 + ty), columns image x = ox0 - 1 + tc, tc = 0..65
+        for (int i = tid; i < SVS_CR_BOX_H * (CT_W + 2); i += 256) {
+            const int ty = i / (CT_W + 2), tc = i - ty * (CT_W + 2);
+            const int x = ox0 - 1 + tc;
+            const uint8_t *p = tb + ty * SVS_CR_BOX_W + tc + 15;      // tile column of image x is x - bx0 = tc + 15
+            const float fl = (float)p[-1], fc = (float)p[0], fr = (float)p[1];
+            float tt = __fmul_rn(fl, ks);
+            if (x < body) { tt = __fmaf_rn(fc, k2, tt); tt = __fmaf_rn(fr, ks, tt); }
+            else { tt = __fadd_rn(tt, __fmul_rn(fc, k2)); tt = __fadd_rn(tt, __fmul_rn(fr, ks)); }
+            rxs[ty][tc] = __fsub_rn(fr, fl);
+            rys[ty][tc] = tt;
+        }
+        __syncthreads();
+        // stage 2: covariances at image rows oy0 - 1 + cy (cy = 0..17), same columns
+        for (int i = tid; i < (CT_H + 2) * (CT_W + 2); i += 256) {
+            const int cy = i / (CT_W + 2), tc = i - cy * (CT_W + 2);
+            const float dx = __fmaf_rn(__fadd_rn(rxs[cy][tc], rxs[cy + 2][tc]), ks, __fmul_rn(rxs[cy + 1][tc], k2));
+            const float dy = __fsub_rn(rys[cy + 2][tc], rys[cy][tc]);
+            cxx[cy][tc] = __fmul_rn(dx, dx); cxy[cy][tc] = __fmul_rn(dx, dy); cyy[cy][tc] = __fmul_rn(dy, dy);
+        }
+        __syncthreads();
+        // stage 3: 3x3 box sums with reflect-101 of the COVARIANCE image, min eigenvalue, masked maximum
+        float vmax = -INFINITY;
+        bool any = false, bad = false;
+        {
+            const int xo = tid & 63, seg = tid >> 6, ox = ox0 + xo;
+            if (ox < w) {
+                const int xl = (ox - 1 >= 0) ? ox - 1 : 1, xr = (ox + 1 <= w - 1) ? ox + 1 : w - 2;
+                const int cl = xl - ox0 + 1, cc = xo + 1, cr = xr - ox0 + 1;
+                auto rowsum = [&](int yy, double &sxx, double &sxy, double &syy) {
+                    const int yr = yy < 0 ? -yy : (yy > h - 1 ? 2 * (h - 1) - yy : yy);
+                    const int cy = yr - oy0 + 1;
+                    sxx = ((double)cxx[cy][cl] + (double)cxx[cy][cc]) + (double)cxx[cy][cr];
+                    sxy = ((double)cxy[cy][cl] + (double)cxy[cy][cc]) + (double)cxy[cy][cr];
+                    syy = ((double)cyy[cy][cl] + (double)cyy[cy][cc]) + (double)cyy[cy][cr];
+                };
+                const int y0 = oy0 + 4 * seg;
+                double axx, axy, ayy, bxx, bxy, byy, nxx, nxy, nyy;
+                if (y0 < h) { rowsum(y0 - 1, axx, axy, ayy); rowsum(y0, bxx, bxy, byy); }
+                for (int j = 0; j < 4; j++) {
+                    const int y = y0 + j;
+                    if (y >= h) break;
+                    rowsum(y + 1, nxx, nxy, nyy);
+                    const double txx = axx + bxx, txy = axy + bxy, tyy = ayy + byy;
+                    const double sxx = txx + nxx, sxy = txy + nxy, syy = tyy + nyy;
+                    bad |= !(twosum_exact(axx, bxx, txx) && twosum_exact(txx, nxx, sxx) && twosum_exact(axy, bxy, txy) &&
+                             twosum_exact(txy, nxy, sxy) && twosum_exact(ayy, byy, tyy) && twosum_exact(tyy, nyy, syy));
+                    const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c2 = __fmul_rn((float)syy, 0.5f);
+                    const float tt = __fsub_rn(a, c2);
+                    const float rad = __fadd_rn(__fmul_rn(tt, tt), __fmul_rn(b, b));
+                    const float lam = __fsub_rn(__fadd_rn(a, c2), __fsqrt_rn(rad));
+                    const size_t o = (size_t)slot * w * h + (size_t)y * w + ox;
+                    eig[o] = lam;
+                    if (!mask || mask[o]) { vmax = fmaxf(vmax, lam); any = true; }
+                    axx = bxx; axy = bxy; ayy = byy; bxx = nxx; bxy = nxy; byy = nyy;
+                }
+            }
+        }
+        unsigned mb = any ? f2ord(vmax) : 0u;
+        for (int o = 16; o > 0; o >>= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+        if (lane == 0) s_max[tid >> 5] = mb;
+        if (bad) s_bad = 1;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned m = 0;
+            for (int i = 0; i < 8; i++) m = max(m, s_max[i]);
+            tile_max[t] = m;
+            if (s_bad) inexact[slot] = 1;
+        }
+        __syncthreads();      // all reads of this buffer / the stage arrays are done before the next iteration reuses them
+    }
+}
+// per image: maximum over its tiles, unless the image was flagged (then the sequential fallback computes it)
+__global__ void k_corner_tile_max(const unsigned *__restrict__ tile_max, int per_img, const int *__restrict__ inexact, unsigned *__restrict__ maxbits)
+{
+    const int slot = blockIdx.x;
+    if (inexact[slot]) return;
+    unsigned m = 0;
+    for (int i = threadIdx.x; i < per_img; i += 32) m = max(m, tile_max[(size_t)slot * per_img + i]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) maxbits[slot] = m;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -273,7 +426,7 @@ static size_t next_pow2(size_t v) { size_t p = 1; while (p < v) p <<= 1; return 
 int svs_i_gftt(svs_ctx *c, const uint8_t *img, int w, int h, int stride, size_t img_pitch, int n_img,
                const int32_t *img_ids, const uint8_t *mask, const int32_t *occ_off, const float *occ_xy,
                int n_occ_total, int max_corners, double quality, double min_distance, int granule,
-               float *out_xy, float *out_resp, int32_t *out_n, float *eig_out)
+               float *out_xy, float *out_resp, int32_t *out_n, float *eig_out, const CUtensorMap *tm)
 {
     if (n_img <= 0) return SVS_OK;
     if (w < 3 || h < 3) SVS_FAIL(c, SVS_ERR_ARG, "gftt: image must be at least 3x3");
@@ -299,8 +452,29 @@ int svs_i_gftt(svs_ctx *c, const uint8_t *img, int w, int h, int stride, size_t 
     int body = granule > 0 ? (w / granule) * granule : 0;
     int n_strips = (w + CR_OUT - 1) / CR_OUT;
     dim3 grd((n_strips + 3) / 4, n_img);
-    SVS_KERNEL(c, KID_CORNER_RESPONSE, k_corner_response<<<grd, 128, 0, c->stream>>>(img, img_pitch, img_ids, w, h, stride, mask_dev, eig, maxbits, ks,
-                                                  k2, body));
+    CUtensorMap tm_local;
+    const CUtensorMap *tmap = tm;
+    if (!tmap && w >= 8 && h >= 8 && (stride & 15) == 0 && (img_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 && !img_ids &&
+        svs_i_tmap_u8_3d(&tm_local, img, w, h, n_img, (size_t)stride, n_img > 1 ? img_pitch : align_up((size_t)stride * h, 16), SVS_CR_BOX_W, SVS_CR_BOX_H) == 0)
+        tmap = &tm_local;
+    if (tmap && w >= 8 && h >= 8) {
+        // tiled + TMA-staged kernel with the exactness check; the sequential kernel re-does the images it flags (none so far)
+        const int tx = (w + CT_W - 1) / CT_W, ty = (h + CT_H - 1) / CT_H;
+        const long long total = (long long)tx * ty * n_img;
+        SVS_CUDA(c, c->d_tmp7.reserve((size_t)total * 4 + (size_t)n_img * 4 + 16));
+        unsigned *tile_max = c->d_tmp7.as<unsigned>();
+        int *inexact = reinterpret_cast<int *>(tile_max + total);
+        SVS_CUDA(c, cudaMemsetAsync(inexact, 0, (size_t)n_img * 4, c->stream));
+        const int grid = (int)std::min<long long>(total, (long long)c->sm_count * 4);
+        SVS_KERNEL(c, KID_CORNER_RESPONSE, k_corner_response_tma<<<grid, 256, 0, c->stream>>>(*tmap, img_ids, n_img, w, h, mask_dev, eig, tile_max, inexact,
+                                                                                               ks, k2, body, tx, ty));
+        SVS_KERNEL(c, KID_CORNER_RESPONSE, k_corner_response<<<grd, 128, 0, c->stream>>>(img, img_pitch, img_ids, w, h, stride, mask_dev, eig, maxbits, ks,
+                                                                                         k2, body, inexact));
+        SVS_KERNEL(c, KID_MISC, k_corner_tile_max<<<n_img, 32, 0, c->stream>>>(tile_max, tx * ty, inexact, maxbits));
+    } else {
+        SVS_KERNEL(c, KID_CORNER_RESPONSE, k_corner_response<<<grd, 128, 0, c->stream>>>(img, img_pitch, img_ids, w, h, stride, mask_dev, eig, maxbits, ks,
+                                                                                         k2, body, nullptr));
+    }
     if (max_corners <= 0) return SVS_OK;
     size_t cap = next_pow2(P / 4 + 1);
     SVS_CUDA(c, c->d_tmp4.reserve(cap * n_img * sizeof(unsigned long long)));

@@ -6,6 +6,7 @@
 //
 // Both are HBM-streaming stencils over a batch of images (blockIdx.z = image).
 #include "svs_internal.h"
+#include "tma.cuh"
 #include <algorithm>
 
 int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t *bytes_per_image)
@@ -242,10 +243,126 @@ k_pyr_down(const uint8_t *__restrict__ src_base, int sw, int sh, int sstride, ui
     }
 }
 
-int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images, const int32_t *img_ids_dev)
+// ---------------------------------------------------------------------------------------------
+// pyrDown with TMA staging (frame sets): a PERSISTENT grid walks the (image, tile) list of one level; the 160-byte x 35-row
+// source box of the NEXT tile is in flight (cp.async.bulk.tensor.3d -> UTMALDG, completion on an mbarrier) while the current
+// one is filtered — the staging loop, its address arithmetic and its per-word border tests are gone from the instruction
+// stream.  TMA fills out-of-image bytes with zeros; the few border tiles patch their reflect-101 rows / columns in shared
+// memory (the reflected source pixel is always inside the same tile).  Arithmetic identical to k_pyr_down (bit-exact).
+#define PD_TP SVS_PD_BOX_W                       // tile row pitch in bytes = TMA box width; tile byte c is image x = 2*ox0 - 16 + c
+#define PD_TBYTES (PD_ROWS * PD_TP)              // 5600
+__global__ void __launch_bounds__(256)
+k_pyr_down_tma(const __grid_constant__ CUtensorMap tm, int sw, int sh, uint8_t *__restrict__ dst_base, int dw, int dh, int dstride,
+               size_t img_pitch, const int32_t *__restrict__ img_ids, int n_img, int tiles_x, int tiles_y)
+{
+    __shared__ __align__(128) uint8_t tile_s[2][5632];
+    __shared__ __align__(8) uint32_t hrow[PD_ROWS][PD_TX / 2];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int tid = threadIdx.x;
+    const int per_img = tiles_x * tiles_y, total = n_img * per_img;
+    if (tid == 0) { tma::mbar_init(&bar[0], 1); tma::mbar_init(&bar[1], 1); tma::fence_init(); }
+    __syncthreads();
+    auto issue = [&](int t, int buf) {
+        const int n = t / per_img, r = t - n * per_img, ty = r / tiles_x, tx = r - ty * tiles_x;
+        const int z = img_ids ? img_ids[n] : n;
+        tma::mbar_expect_tx(&bar[buf], PD_TBYTES);
+        tma::load_3d(tile_s[buf], &tm, &bar[buf], 2 * tx * PD_TX - 16, 2 * ty * PD_TY - 2, z);
+    };
+    int t = blockIdx.x;
+    if (tid == 0 && t < total) issue(t, 0);
+    for (int it = 0; t < total; t += gridDim.x, it++) {
+        const int buf = it & 1, tn = t + gridDim.x;
+        if (tid == 0 && tn < total) { tma::fence_proxy_async(); issue(tn, buf ^ 1); }
+        const int n = t / per_img, r0 = t - n * per_img, ty0 = r0 / tiles_x, tx0 = r0 - ty0 * tiles_x;
+        const int img = img_ids ? img_ids[n] : n;
+        uint8_t *dst = dst_base + (size_t)img * img_pitch;
+        const int ox0 = tx0 * PD_TX, oy0 = ty0 * PD_TY, bx0 = 2 * ox0 - 16, iy0 = 2 * oy0 - 2;
+        uint8_t *tb = tile_s[buf];
+        tma::mbar_wait(&bar[buf], (it >> 1) & 1);
+        // reflect-101 patch-up of the zero-filled out-of-image bytes this tile actually reads (rows first, then columns)
+        if (iy0 < 0 || iy0 + PD_ROWS > sh) {
+            for (int i = tid; i < PD_ROWS * (PD_TP / 4); i += 256) {
+                const int r = i / (PD_TP / 4), q = i - r * (PD_TP / 4), iy = iy0 + r;
+                if (iy < 0 || iy >= sh) {
+                    const int ry = refl101(iy, sh) - iy0;
+                    if (ry >= 0 && ry < PD_ROWS) reinterpret_cast<uint32_t *>(tb + r * PD_TP)[q] = reinterpret_cast<const uint32_t *>(tb + ry * PD_TP)[q];
+                }
+            }
+            __syncthreads();
+        }
+        if (bx0 < 0 || bx0 + PD_TP > sw) {
+            for (int i = tid; i < PD_ROWS * 8; i += 256) {
+                const int r = i >> 3, k = i & 7;
+                const int x = (k < 4) ? k - 4 : sw + (k - 4);          // the columns a 5-tap window can reach outside the image
+                const int cdst = x - bx0, csrc = refl101(x, sw) - bx0;
+                if (cdst >= 0 && cdst < PD_TP && csrc >= 0 && csrc < PD_TP) tb[r * PD_TP + cdst] = tb[r * PD_TP + csrc];
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < PD_ROWS * (PD_TX / 2); i += 256) {
+            const int r = i / (PD_TX / 2), j = i - r * (PD_TX / 2);
+            const uint32_t *tw = reinterpret_cast<const uint32_t *>(tb + r * PD_TP);
+            uint32_t w0 = tw[j + 3], w1 = tw[j + 4], w2 = tw[j + 5];      // image bytes 2*ox0 + 4j - 4 .. + 7 sit 12 bytes into the box
+            uint32_t b2 = (w0 >> 16) & 0xFF, b3 = w0 >> 24, b4 = w1 & 0xFF, b5 = (w1 >> 8) & 0xFF, b6 = (w1 >> 16) & 0xFF, b7 = w1 >> 24,
+                     b8 = w2 & 0xFF;
+            uint32_t A = b2 + 4 * b3 + 6 * b4 + 4 * b5 + b6;
+            uint32_t B = b4 + 4 * b5 + 6 * b6 + 4 * b7 + b8;
+            hrow[r][j] = A | (B << 16);
+        }
+        __syncthreads();
+        {
+            int ty = tid >> 4, jq = tid & 15;
+            int oy = oy0 + ty, ox = ox0 + 4 * jq;
+            if (oy < dh && ox < dw) {
+                const uint2 *h = reinterpret_cast<const uint2 *>(&hrow[2 * ty][2 * jq]);
+                const int rp = (PD_TX / 2) / 2;
+                uint2 h0 = h[0], h1 = h[rp], h2 = h[2 * rp], h3 = h[3 * rp], h4 = h[4 * rp];
+                uint32_t s0 = h0.x + 4 * h1.x + 6 * h2.x + 4 * h3.x + h4.x;
+                uint32_t s1 = h0.y + 4 * h1.y + 6 * h2.y + 4 * h3.y + h4.y;
+                uint32_t r0 = ((s0 + 0x00800080u) >> 8) & 0x00FF00FFu, r1 = ((s1 + 0x00800080u) >> 8) & 0x00FF00FFu;
+                uint32_t out = (r0 & 0xFF) | ((r0 >> 16) << 8) | ((r1 & 0xFF) << 16) | ((r1 >> 16) << 24);
+                uint8_t *d = dst + (size_t)oy * dstride + ox;
+                if (ox + 4 <= dw) *reinterpret_cast<uint32_t *>(d) = out;
+                else for (int k = 0; k < 4 && ox + k < dw; k++) d[k] = (uint8_t)(out >> (8 * k));
+            }
+        }
+        __syncthreads();      // every read of tile_s[buf] and hrow is done before the copy issued in the NEXT iteration lands
+    }
+}
+
+int svs_i_tmap_u8_3d(CUtensorMap *m, const void *base, int w, int h, int n, size_t row_stride, size_t img_pitch, int box_w, int box_h)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return -1;
+        fn = reinterpret_cast<EncodeFn>(p);
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride & 15) || (img_pitch & 15) || (box_w & 15) || box_w > 256 || box_h > 256) return -2;
+    cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t gstr[2] = {(cuuint64_t)row_stride, (cuuint64_t)img_pitch};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1}, estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images, const int32_t *img_ids_dev, const CUtensorMap *level_maps)
 {
     if (n_images <= 0) return SVS_OK;
     for (int l = 1; l < d.nlev; l++) {
+        if (level_maps && d.w[l - 1] >= 16 && d.h[l - 1] >= 16) {     // TMA-staged persistent kernel (frame sets)
+            const int tx = (d.w[l] + PD_TX - 1) / PD_TX, ty = (d.h[l] + PD_TY - 1) / PD_TY;
+            const long long total = (long long)tx * ty * n_images;
+            const int grid = (int)std::min<long long>(total, (long long)c->sm_count * 6);
+            SVS_KERNEL(c, KID_PYRDOWN, k_pyr_down_tma<<<grid, 256, 0, c->stream>>>(level_maps[l - 1], d.w[l - 1], d.h[l - 1], d.base + d.off[l], d.w[l],
+                                                                                     d.h[l], d.stride[l], d.img_pitch, img_ids_dev, n_images, tx, ty));
+            continue;
+        }
         dim3 blk(256);
         dim3 grd((d.w[l] + PD_TX - 1) / PD_TX, (d.h[l] + PD_TY - 1) / PD_TY, n_images);
         SVS_KERNEL(c, KID_PYRDOWN, k_pyr_down<<<grd, blk, 0, c->stream>>>(d.base + d.off[l - 1], d.w[l - 1], d.h[l - 1], d.stride[l - 1],

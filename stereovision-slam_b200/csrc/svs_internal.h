@@ -1,5 +1,6 @@
 // Internal declarations shared by the CUDA translation units behind include/svslam.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -8,6 +9,13 @@
 #include "../../include/svslam.h"
 
 #define SVS_MAX_LEVELS 8
+// TMA boxes.  The innermost (byte) coordinate of a bulk tensor copy must be a multiple of 16 (measured: any other start traps
+// with "illegal instruction", tests/tools/tma_probe.cu), so a tile's box starts 16 bytes left of its first output column:
+// k_pyr_down_tma reads image bytes [2*ox0 - 16, 2*ox0 + 144) x 35 rows, the corner response [ox0 - 16, ox0 + 80) x 20 rows.
+#define SVS_PD_BOX_W 160
+#define SVS_PD_BOX_H 35
+#define SVS_CR_BOX_W 96
+#define SVS_CR_BOX_H 20
 
 // Device image pyramid batch: image b, level l, row y at base + b*img_pitch + off[l] + y*stride[l].
 struct PyrDesc {
@@ -72,7 +80,7 @@ struct svs_ctx {
     long long launches = 0;
     double ba_host_s[3] = {0, 0, 0};   // svs_ba_optimize wall time: structure build | pack + enqueue | wait for the device + unpack
     // scratch (named by user)
-    DevBuf d_in, d_in2, d_out, d_out2, d_tmp, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_tmp6;
+    DevBuf d_in, d_in2, d_out, d_out2, d_tmp, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_tmp6, d_tmp7;
     PinBuf h_in, h_out;
 };
 
@@ -82,6 +90,17 @@ struct svs_frameset {
     // "next" is the target of svs_frameset_prefetch_ptrs, filled on the context's ingest stream while the current
     // step's kernels run; a push rotates the roles.
     PyrDesc L[3], R[2];
+    // TMA tensor maps over [stream][H_l][W_l] of every level of the five pyramid buffers (box = k_pyr_down_tma's source tile)
+    // and over level 0 with the corner-response tile box
+    CUtensorMap tm_pyr[5][SVS_MAX_LEVELS];
+    CUtensorMap tm_gftt[3];
+    bool has_tmaps = false;
+    const CUtensorMap *maps_of(const PyrDesc &d) const {
+        if (!has_tmaps) return nullptr;
+        for (int i = 0; i < 3; i++) if (d.base == L[i].base) return tm_pyr[i];
+        for (int i = 0; i < 2; i++) if (d.base == R[i].base) return tm_pyr[3 + i];
+        return nullptr;
+    }
     int il_prev = 1, il_cur = 0, il_next = 2, ir_cur = 0, ir_next = 1;
     const PyrDesc &Lcur() const { return L[il_cur]; }
     const PyrDesc &Lprev() const { return L[il_prev]; }
@@ -130,6 +149,9 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // stepped from several host threads, and the attribute is per device.
 cudaError_t svs_i_opt_in_smem(svs_ctx *c, const void *func);
 
+// images.cu: u8 tensor map [n][h][w], byte strides (1, row_stride, img_pitch), box (box_w, box_h, 1); 0 on success
+int svs_i_tmap_u8_3d(CUtensorMap *m, const void *base, int w, int h, int n, size_t row_stride, size_t img_pitch, int box_w, int box_h);
+
 // ---- internal device-level entry points (all asynchronous on ctx->stream) ----
 // images.cu
 int svs_i_make_pyr_desc(PyrDesc *d, int w, int h, int win, int max_level, size_t *bytes_per_image);
@@ -143,14 +165,16 @@ int svs_i_half_nearest_zc(svs_ctx *c, const uint8_t *const *src_ptrs_dev, int n_
                           int ptrs_aligned4, const int32_t *dst_ids_dev = nullptr);
 int svs_i_copy_level0(svs_ctx *c, const uint8_t *src_dev, int w, int h, size_t row_stride, size_t img_stride,
                       int n, const PyrDesc &d, const uint8_t *const *src_ptrs_dev = nullptr, const int32_t *dst_ids_dev = nullptr);
-int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images, const int32_t *img_ids_dev = nullptr);
+int svs_i_build_pyramid(svs_ctx *c, const PyrDesc &d, int n_images, const int32_t *img_ids_dev = nullptr,
+                        const CUtensorMap *level_maps = nullptr /* one per level: TMA-staged kernel */);
 // gftt.cu
 int svs_i_gftt(svs_ctx *c, const uint8_t *img_dev, int w, int h, int stride, size_t img_pitch, int n_img,
                const int32_t *img_ids_dev /* may be null: identity */,
                const uint8_t *mask_dev /* n_img*h*w or null */,
                const int32_t *occ_off_dev, const float *occ_xy_dev /* or null */, int n_occ_total,
                int max_corners, double quality, double min_distance, int granule,
-               float *out_xy_dev, float *out_resp_dev, int32_t *out_n_dev, float *eig_out_dev /* optional */);
+               float *out_xy_dev, float *out_resp_dev, int32_t *out_n_dev, float *eig_out_dev /* optional */,
+               const CUtensorMap *tm = nullptr /* u8 [slot][h][w] map with the SVS_CR box: TMA-staged tiled corner response */);
 // lk.cu
 int svs_i_lk(svs_ctx *c, const PyrDesc &prev, const PyrDesc &next, const int32_t *pt_img_dev /* per point */,
              const float *prev_xy_dev, float *next_xy_dev, int n_pts, int win, int max_iter, double eps,

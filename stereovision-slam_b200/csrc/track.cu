@@ -295,7 +295,7 @@ int svs_i_trk_upload(svs_ctx *c, svs_tracker *t, int n_sel, const TrkUpHdr *hdrs
     SVS_CUDA(c, cudaSetDevice(c->device));
     for (int k = 0; k < n_sel; k++) {
         if (hdrs[k].stream < 0 || hdrs[k].stream >= t->p.B) SVS_FAIL(c, SVS_ERR_ARG, "tracker upload: stream out of range");
-        if (hdrs[k].n > t->p.cap) SVS_FAIL(c, SVS_ERR_CAPACITY, "tracker: more features in a frame than the device feature table holds (2 * num_features + 256)");
+        if (hdrs[k].n > t->p.cap) SVS_FAIL(c, SVS_ERR_CAPACITY, "tracker: more features in a frame than the device feature table holds (4 * num_features + 512)");
     }
     const size_t hb = align_up((size_t)n_sel * sizeof(TrkUpHdr), 256), fb = (size_t)n_feats * sizeof(TrkUpFeat);
     SVS_CUDA(c, cudaEventSynchronize(t->up_done));      // the previous upload has left the pinned staging buffer

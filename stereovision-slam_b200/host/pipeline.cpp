@@ -55,7 +55,8 @@ public:
         }
         if (cfg.device_tracking) {
             TrkParams p;
-            p.B = n_streams; p.cap = (2 * cfg.num_features + 256 + 31) / 32 * 32; p.W = W_; p.H = H_;
+            p.B = n_streams; p.W = W_; p.H = H_;
+            p.cap = (4 * cfg.num_features + 512 + 31) / 32 * 32;      // tracked + newly detected left features of one frame
             p.num_features_tracking = cfg.num_features_tracking; p.num_features_tracking_bad = cfg.num_features_tracking_bad;
             p.num_features_needed_for_keyframe = cfg.num_features_needed_for_keyframe;
             p.lk_win = cfg.lk_win; p.lk_max_iter = cfg.lk_max_iter; p.lk_eps = cfg.lk_eps; p.chi2_th = 5.991;

@@ -98,6 +98,39 @@ def test_frameset_pyramids_and_batched_gftt(ctx, granule):
         fs.close()
 
 
+def test_tma_staged_kernels_over_many_tiles(ctx, granule):
+    """The TMA-staged persistent kernels (k_pyr_down_tma, k_corner_response_tma) with more tiles than resident CTAs, so
+    that every CTA walks several tiles through its two shared-memory buffers (mbarrier phase flips, buffer reuse), on
+    full-resolution frames (processed at 1241x376: 20 x 24 corner tiles and 10 x 12 pyramid tiles per image) — every pyramid
+    level and the GFTT result of every stream against the oracle."""
+    B, H, W = 24, 376, 1241
+    base = [texture(H, W, 70 + s) for s in range(4)]
+    rng = np.random.RandomState(9)
+    left = np.stack([np.roll(base[s % 4], (3 * s, 17 * s), (0, 1)) for s in range(B)])        # 24 distinct images, cheaply
+    right = np.stack([np.roll(base[(s + 1) % 4], (5 * s, 11 * s), (0, 1)) for s in range(B)])
+    fs = ctx.frameset(B, W, H, half=False)
+    try:
+        fs.push(left, right)
+        fs.push(right, left)                                   # second push: the other buffers and tensor maps
+        for b in range(B):
+            for which, src in ((0, right), (1, left), (2, left)):
+                if b % 5 and which:
+                    continue
+                pyr = o.build_pyramid(src[b])
+                for lvl in range(fs.n_levels):
+                    assert np.array_equal(fs.download(b, which, lvl), pyr[lvl]), (b, which, lvl)
+        sel = list(range(B))
+        occ = [np.stack([rng.rand(k) * W, rng.rand(k) * H], 1).astype(np.float32) for k in [0, 30, 80, 5] * (B // 4)]
+        res = ctx.gftt_detect_batch(fs, sel, occ, max_corners=400, min_distance=12.0, granule=granule)
+        for (xy, r), s_, oc in zip(res, sel, occ):
+            if s_ % 3:
+                continue
+            wxy, wr = o.gftt_detect(right[s_], o.feature_mask((H, W), oc) if len(oc) else None, 400, 0.01, 12.0, granule)
+            assert len(wxy) > 100 and np.array_equal(xy, wxy) and np.array_equal(r, wr), s_
+    finally:
+        fs.close()
+
+
 @pytest.mark.parametrize("H,W,pad", [(370, 1226, 0), (376, 1241, 3), (47, 101, 1)])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_frameset_ingest_modes(ctx, H, W, pad, mode):
