@@ -229,6 +229,22 @@ SVS_API int svs_ipc_export(svs_ctx *ctx, const void *dev_ptr, unsigned char hand
 SVS_API int svs_ipc_import(svs_ctx *ctx, const unsigned char handle[64], void **dev_ptr_out);
 SVS_API int svs_ipc_release(svs_ctx *ctx, void *dev_ptr);
 
+/* ---------------------------------------------------------------- f4 : pose-graph optimisation
+ * Replaces the g2o block of LoopClosure::PoseGraphOptimization (src/loopclosure.cpp:641-746): one VertexPose per keyframe,
+ * EdgePoseGraph (include/StereoVisionSLAM/g2o_types.h:231-267, error = log(measurement^-1 * pose_a * pose_b^-1), information
+ * I6) for every consecutive-keyframe pair (measurement = Frame::relative_pose_pkf_) and every closed loop
+ * (Frame::loop_relative_pose_), fixed[k] != 0 for the vertices held constant (keyframe 0 at :693-696), Levenberg-Marquardt
+ * over a dense pivoted LDLT of the whole system, optimizer.optimize(max_iter = 22).  Edge e connects vertex edge_a[e]
+ * (the later keyframe) to edge_b[e].  jacobian_mode: 1 = g2o's numeric central differences with delta 1e-9 (what the
+ * reference does: the edge has no linearizeOplus), 0 = closed form.  The whole loop runs in one cooperative kernel.
+ * svs_pose_graph_move_landmarks is the landmark update that follows (:749-777): pos <- new_pose[k]^-1 * (old_pose[k] * pos)
+ * with k = lm_kf[i] the keyframe of the landmark's first valid observation (< 0: landmark untouched). */
+SVS_API int svs_pose_graph_optimize(svs_ctx *ctx, int n_kf, double *poses_inout /* 7*n_kf */, const uint8_t *fixed /* n_kf */,
+                                    int n_edge, const int32_t *edge_a, const int32_t *edge_b, const double *measurement /* 7*n_edge */,
+                                    int max_iter, int jacobian_mode, svs_ba_stats *stats);
+SVS_API int svs_pose_graph_move_landmarks(svs_ctx *ctx, int n_lm, double *lms_inout /* 3*n_lm */, const int32_t *lm_kf,
+                                          int n_kf, const double *old_poses, const double *new_poses);
+
 /* ---------------------------------------------------------------- a10 : dense stereo
  * svs_stereo_bm replaces stereo_depth_est_->compute(l, r, disp) (src/dense_reconstruction.cpp:114) for
  * cv::StereoBM::create(ndisp, block) with OpenCV's defaults (XSOBEL prefilter cap 31, texture 10,

@@ -600,6 +600,181 @@ int orc_ba_optimize(int n_kf, double *poses, int n_lm, double *lms, int n_edge,
 }
 
 /* ------------------------------------------------------------------------- */
+/* Pose-graph optimisation: LoopClosure::PoseGraphOptimization, src/loopclosure.cpp:641-799          */
+/* VertexPose per keyframe (left-multiplicative update, g2o_types.h:40-60), the vertex of keyframe 0 fixed (:693-696),          */
+/* EdgePoseGraph (g2o_types.h:231-267): error = log(M^-1 * v0 * v1^-1) (6-vector, translation first), information I6, no robust */
+/* kernel, no linearizeOplus -> g2o numeric central differences (delta 1e-9) for the NON-fixed vertices;                         */
+/* BlockSolver<6,6> + LinearSolverDense -> dense pivoted LDLT of the whole 6K x 6K system; optimize(22) (:745-746).              */
+/* jac_mode 1 = numeric (the reference), 0 = closed-form Jacobians (SE3 left-Jacobian inverse) for a noise-free comparison.     */
+/* ------------------------------------------------------------------------- */
+static void pg_error(const double *M, const double *A, const double *B, double *e)
+{
+    double Mi[7], Bi[7], t1[7], t2[7];
+    orc_se3_inv(M, Mi); orc_se3_inv(B, Bi);
+    orc_se3_mul(Mi, A, t1); orc_se3_mul(t1, Bi, t2);
+    orc_se3_log(t2, e);
+}
+static void mat3_mul(const double *A, const double *B, double *C)
+{ for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += A[i * 3 + k] * B[k * 3 + j]; C[i * 3 + j] = s; } }
+static void hat3(const double *v, double *M) { M[0] = 0; M[1] = -v[2]; M[2] = v[1]; M[3] = v[2]; M[4] = 0; M[5] = -v[0]; M[6] = -v[1]; M[7] = v[0]; M[8] = 0; }
+/* inverse of the SE3 left Jacobian at xi = (rho, phi) (Barfoot, State Estimation for Robotics, eqs. 7.85-7.95), 6x6 row-major */
+void orc_se3_left_jac_inv(const double *xi, double *Ji)
+{
+    const double *rho = xi, *phi = xi + 3;
+    double th2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2], th = sqrt(th2);
+    double P[9], R[9], PP[9], PR[9], RP[9], PRP[9], PPR[9], RPP[9], PRPP[9], PPRP[9];
+    hat3(phi, P); hat3(rho, R);
+    mat3_mul(P, P, PP); mat3_mul(P, R, PR); mat3_mul(R, P, RP); mat3_mul(PR, P, PRP); mat3_mul(PP, R, PPR); mat3_mul(RP, P, RPP);
+    mat3_mul(PRP, P, PRPP); mat3_mul(PP, RP, PPRP);
+    double Jinv[9], Q[9];
+    double c1, c2, c3, a;    /* Q coefficients; a = coefficient of phi^ phi^ in J^-1 */
+    if (th < 1e-5) {
+        c1 = 1.0 / 6.0 - th2 / 120.0; c2 = 1.0 / 24.0 - th2 / 720.0; c3 = 1.0 / 120.0 - th2 / 2520.0;
+        a = 1.0 / 12.0 + th2 / 720.0;
+    } else {
+        double s = sin(th), c = cos(th), th3 = th2 * th, th4 = th2 * th2, th5 = th4 * th;
+        c1 = (th - s) / th3; c2 = (1.0 - 0.5 * th2 - c) / th4; c3 = 0.5 * ((1.0 - 0.5 * th2 - c) / th4 - 3.0 * (th - s - th3 / 6.0) / th5);
+        a = (1.0 - 0.5 * th * s / (1.0 - c)) / th2;      /* 1/th^2 (1 - th/2 cot(th/2)) */
+    }
+    for (int i = 0; i < 9; i++) {
+        double I = (i % 4 == 0) ? 1.0 : 0.0;
+        Jinv[i] = I - 0.5 * P[i] + a * PP[i];
+        Q[i] = 0.5 * R[i] + c1 * (PR[i] + RP[i] + PRP[i]) - c2 * (PPR[i] + RPP[i] - 3.0 * PRP[i]) - c3 * (PRPP[i] + PPRP[i]);
+    }
+    double JQ[9], JQJ[9];
+    mat3_mul(Jinv, Q, JQ); mat3_mul(JQ, Jinv, JQJ);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        Ji[i * 6 + j] = Jinv[i * 3 + j]; Ji[i * 6 + 3 + j] = -JQJ[i * 3 + j];
+        Ji[(3 + i) * 6 + j] = 0.0; Ji[(3 + i) * 6 + 3 + j] = Jinv[i * 3 + j];
+    }
+}
+/* Ja = d e / d delta_a, Jb = d e / d delta_b for the left-multiplicative vertex updates, 6x6 row-major each */
+static void pg_jac(const double *M, const double *A, const double *B, int mode, double *Ja, double *Jb)
+{
+    if (mode == 1) {
+        const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+        for (int v = 0; v < 2; v++)
+            for (int d = 0; d < 6; d++) {
+                double add[6] = {0, 0, 0, 0, 0, 0}, Tp[7], e1[6], e2[6];
+                const double *T = v ? B : A;
+                add[d] = delta; memcpy(Tp, T, sizeof(Tp)); se3_oplus(Tp, add); pg_error(M, v ? A : Tp, v ? Tp : B, e1);
+                add[d] = -delta; memcpy(Tp, T, sizeof(Tp)); se3_oplus(Tp, add); pg_error(M, v ? A : Tp, v ? Tp : B, e2);
+                for (int r = 0; r < 6; r++) (v ? Jb : Ja)[r * 6 + d] = scalar * (e1[r] - e2[r]);
+            }
+        return;
+    }
+    /* e(da) = log(M^-1 exp(da) A B^-1) = log(exp(Ad(M^-1) da) E) ~ e0 + Jl^-1(e0) Ad(M^-1) da
+       e(db) = log(M^-1 A B^-1 exp(-db)) = log(E exp(-db))         ~ e0 - Jr^-1(e0) db,  Jr^-1(e) = Jl^-1(-e) */
+    double e0[6], me0[6], Jl[36], Jr[36], Mi[7], Rm[9], tx[9], tR[9], Ad[36];
+    pg_error(M, A, B, e0);
+    for (int i = 0; i < 6; i++) me0[i] = -e0[i];
+    orc_se3_left_jac_inv(e0, Jl); orc_se3_left_jac_inv(me0, Jr);
+    orc_se3_inv(M, Mi); quat_to_R(Mi, Rm); hat3(Mi + 4, tx); mat3_mul(tx, Rm, tR);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        Ad[i * 6 + j] = Rm[i * 3 + j]; Ad[i * 6 + 3 + j] = tR[i * 3 + j]; Ad[(3 + i) * 6 + j] = 0.0; Ad[(3 + i) * 6 + 3 + j] = Rm[i * 3 + j];
+    }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) {
+        double s = 0;
+        for (int k = 0; k < 6; k++) s += Jl[i * 6 + k] * Ad[k * 6 + j];
+        Ja[i * 6 + j] = s; Jb[i * 6 + j] = -Jr[i * 6 + j];
+    }
+}
+void orc_pg_edge_jac(const double *M, const double *A, const double *B, int mode, double *Ja, double *Jb) { pg_jac(M, A, B, mode, Ja, Jb); }
+
+int orc_pose_graph_optimize(int n_kf, double *poses /* 7*n in/out */, const uint8_t *fixed /* n */, int n_edge, const int32_t *edge_a,
+                            const int32_t *edge_b, const double *meas /* 7*n_edge */, int max_iter, int jac_mode, orc_ba_stats *st)
+{
+    orc_ba_stats local; if (!st) st = &local;
+    memset(st, 0, sizeof(*st));
+    int N = n_kf, E = n_edge;
+    if (E == 0) return 0;
+    /* active = non-fixed vertices with >= 1 edge, ascending id */
+    int *idx = (int *)malloc(sizeof(int) * N);
+    for (int i = 0; i < N; i++) idx[i] = -1;
+    for (int e = 0; e < E; e++) { if (!fixed[edge_a[e]]) idx[edge_a[e]] = 0; if (!fixed[edge_b[e]]) idx[edge_b[e]] = 0; }
+    int NA = 0;
+    for (int i = 0; i < N; i++) if (idx[i] == 0) idx[i] = NA++;
+    int n = 6 * NA;
+    if (n == 0) { free(idx); return 0; }
+    double *H = (double *)malloc(sizeof(double) * n * n), *b = (double *)malloc(sizeof(double) * n), *S = (double *)malloc(sizeof(double) * n * n);
+    double *x = (double *)malloc(sizeof(double) * n), *pb = (double *)malloc(sizeof(double) * 7 * N), *err = (double *)malloc(sizeof(double) * 6 * E);
+    double lambda = 0, ni = 2, cur = 0;
+    for (int it = 0; it < max_iter; it++) {
+        cur = 0;
+        for (int e = 0; e < E; e++) {
+            pg_error(meas + 7 * e, poses + 7 * edge_a[e], poses + 7 * edge_b[e], err + 6 * e);
+            for (int r = 0; r < 6; r++) cur += err[6 * e + r] * err[6 * e + r];
+        }
+        if (it == 0) st->chi2_init = cur;
+        memset(H, 0, sizeof(double) * n * n); memset(b, 0, sizeof(double) * n);
+        for (int e = 0; e < E; e++) {
+            double Ja[36], Jb[36];
+            pg_jac(meas + 7 * e, poses + 7 * edge_a[e], poses + 7 * edge_b[e], jac_mode, Ja, Jb);
+            int ia = idx[edge_a[e]], ib = idx[edge_b[e]];
+            const double *J[2] = {Ja, Jb};
+            int id[2] = {ia, ib};
+            for (int u = 0; u < 2; u++) {
+                if (id[u] < 0) continue;
+                for (int r = 0; r < 6; r++) {
+                    double s = 0;
+                    for (int k = 0; k < 6; k++) s += J[u][k * 6 + r] * err[6 * e + k];
+                    b[6 * id[u] + r] -= s;
+                }
+                for (int v = 0; v < 2; v++) {
+                    if (id[v] < 0) continue;
+                    for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) {
+                        double s = 0;
+                        for (int k = 0; k < 6; k++) s += J[u][k * 6 + r] * J[v][k * 6 + c];
+                        H[(size_t)(6 * id[u] + r) * n + 6 * id[v] + c] += s;
+                    }
+                }
+            }
+        }
+        st->linearizations++;
+        if (it == 0) {
+            double md = 0;
+            for (int i = 0; i < n; i++) md = fmax(md, fabs(H[(size_t)i * n + i]));
+            lambda = 1e-5 * md; ni = 2;
+        }
+        double rho = 0;
+        int q = 0;
+        do {
+            memcpy(pb, poses, sizeof(double) * 7 * N);
+            memcpy(S, H, sizeof(double) * n * n);
+            for (int i = 0; i < n; i++) S[(size_t)i * n + i] += lambda;
+            int ok = orc_ldlt_solve(n, S, b, x);
+            st->solves++;
+            if (!ok) memset(x, 0, sizeof(double) * n);
+            for (int i = 0; i < N; i++) if (idx[i] >= 0) se3_oplus(poses + 7 * i, x + 6 * idx[i]);
+            double tmp = 0;
+            for (int e = 0; e < E; e++) {
+                pg_error(meas + 7 * e, poses + 7 * edge_a[e], poses + 7 * edge_b[e], err + 6 * e);
+                for (int r = 0; r < 6; r++) tmp += err[6 * e + r] * err[6 * e + r];
+            }
+            if (!ok) tmp = DBL_MAX;
+            rho = cur - tmp;
+            double scale = 1e-3;
+            for (int a = 0; a < n; a++) scale += x[a] * (lambda * x[a] + b[a]);
+            rho /= scale;
+            if (rho > 0 && isfinite(tmp)) {
+                double alpha = 1.0 - pow(2 * rho - 1, 3);
+                alpha = fmin(alpha, 2.0 / 3.0);
+                lambda *= fmax(1.0 / 3.0, alpha); ni = 2; cur = tmp;
+            } else {
+                lambda *= ni; ni *= 2;
+                memcpy(poses, pb, sizeof(double) * 7 * N);
+            }
+            q++; st->trials++;
+        } while (rho < 0 && q < 10);
+        st->iterations++;
+        st->lambda = lambda; st->chi2 = cur;
+        if (q == 10 || rho == 0) break;
+    }
+    free(idx); free(H); free(b); free(S); free(x); free(pb); free(err);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Pyramidal LK (cv::calcOpticalFlowPyrLK as called at frontend.cpp:105,353) */
 /* ------------------------------------------------------------------------- */
 static inline int refl101(int i, int n)

@@ -169,3 +169,31 @@ def triangulate(left_xy, right_xy, K_left, K_right, baseline):
     xyz = v[:, :3] / v[:, 3:4]
     ok = (s[:, 3] / s[:, 2] < 1e-2).astype(np.uint8)
     return xyz, ok
+
+
+def pose_graph_optimize(poses, fixed, edge_a, edge_b, meas, max_iter=22, jac_mode=1):
+    """LoopClosure::PoseGraphOptimization's g2o block (src/loopclosure.cpp:641-746): returns (poses, stats)."""
+    P = np.array(poses, np.float64).reshape(-1, 7).copy()
+    fx = np.ascontiguousarray(fixed, np.uint8)
+    ea, eb = np.ascontiguousarray(edge_a, np.int32), np.ascontiguousarray(edge_b, np.int32)
+    M = np.ascontiguousarray(meas, np.float64).reshape(-1, 7)
+    st = BaStats()
+    lib().orc_pose_graph_optimize(len(P), _p(P), _p(fx), len(ea), _p(ea), _p(eb), _p(M), int(max_iter), int(jac_mode), C.byref(st))
+    return P, st
+
+
+def pg_edge_jac(M, A, B, mode):
+    Ja, Jb = np.zeros((6, 6)), np.zeros((6, 6))
+    lib().orc_pg_edge_jac(_p(np.ascontiguousarray(M, np.float64)), _p(np.ascontiguousarray(A, np.float64)),
+                          _p(np.ascontiguousarray(B, np.float64)), int(mode), _p(Ja), _p(Jb))
+    return Ja, Jb
+
+
+def move_landmarks(lms, lm_kf, old_poses, new_poses):
+    """src/loopclosure.cpp:749-777: pos_w = new_pose(kf)^-1 * (old_pose(kf) * pos) with kf = keyframe of the landmark's first
+    valid observation; lm_kf < 0: untouched."""
+    out = np.array(lms, np.float64).reshape(-1, 3).copy()
+    for i, k in enumerate(lm_kf):
+        if k >= 0:
+            out[i] = se3_act(se3_inv(new_poses[k]), se3_act(old_poses[k], out[i]))
+    return out

@@ -16,6 +16,9 @@ COLS = OrderedDict([
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+    ("sm__inst_executed.sum", "warp_inst"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
     ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
     ("launch__registers_per_thread", "regs"),

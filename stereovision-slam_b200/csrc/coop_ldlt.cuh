@@ -1,0 +1,152 @@
+// Grid-cooperative dense LDL^T solve with Eigen::LDLT's pivot order, for systems too large for one CTA's shared memory
+// (the pose graph's 6K x 6K system, g2o::LinearSolverDense in LoopClosure::PoseGraphOptimization, src/loopclosure.cpp:664-672).
+// Eigen's unblocked LDLT picks at step k the largest |diagonal| of the NOT yet updated trailing part (left-looking), i.e. the
+// pivot order is the original diagonal sorted by decreasing magnitude: the caller writes the symmetrically permuted lower
+// triangle into A once and this routine factorises it WITHOUT pivoting, right-looking, in 32-column panels:
+//   (a) warp 0 of CTA 0 factorises the 32 x 32 diagonal block in shared memory (32 dependent steps, warp-synchronous)
+//   (b) every CTA forward-substitutes a share of the rows below it (one row per thread)
+//   (c) every CTA updates 64 x 64 tiles of the trailing matrix from shared-memory copies of the panel rows
+// The right-hand side rides along as row n (so z = D^-1 L^-1 g falls out of the factorisation); CTA 0 finishes with the
+// blocked back-substitution x = L^-T z.  Three grid barriers per panel.
+#pragma once
+#include <cooperative_groups.h>
+#include <cfloat>
+
+#define CL_PW 32
+#define CL_TILE 64
+// shared scratch in doubles: panel block + its pivots + two tile operand panels
+#define CL_SMEM_DOUBLES (CL_PW * (CL_PW + 1) + CL_PW + 2 * CL_TILE * (CL_PW + 1))
+
+// A: (n + 1) x pitch, lower triangle of the PERMUTED matrix in rows 0..n-1, right-hand side (permuted) in row n.
+// dvec: n pivots (out).  xs: n, solution in permuted order (out, valid in CTA 0's view after the final barrier).
+// sign_io: one double in global memory, 0 on entry; Eigen's sign tracking (1 / -1 / 2 mixed / 3 zero first pivot) on exit.
+template <int T>
+__device__ void coop_ldlt_solve(cooperative_groups::grid_group &grid, double *A, int n, int pitch, double *dvec, double *xs,
+                                double *sign_io, double *sm)
+{
+    double *Ds = sm;                              // [CL_PW][CL_PW + 1]
+    double *ds = Ds + CL_PW * (CL_PW + 1);        // [CL_PW]
+    double *Li = ds + CL_PW;                      // [CL_TILE][CL_PW + 1]
+    double *Lj = Li + CL_TILE * (CL_PW + 1);      // [CL_TILE][CL_PW + 1]  (rows of L times the pivots)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gtid = blockIdx.x * T + tid, gsz = gridDim.x * T;
+    for (int k0 = 0; k0 < n; k0 += CL_PW) {
+        const int w = min(CL_PW, n - k0), k1 = k0 + w;
+        if (blockIdx.x == 0) {
+            for (int t = tid; t < w * w; t += T) { const int i = t / w, c = t - i * w; Ds[i * (CL_PW + 1) + c] = A[(size_t)(k0 + i) * pitch + k0 + c]; }
+            __syncthreads();
+            if (warp == 0) {
+                int sign = (int)sign_io[0];
+                for (int kk = 0; kk < w; kk++) {
+                    const double akk = Ds[kk * (CL_PW + 1) + kk];
+                    if (k0 + kk == 0 && !(fabs(akk) > 0.0)) sign = 3;
+                    if (sign == 1) { if (akk < 0) sign = 2; }
+                    else if (sign == -1) { if (akk > 0) sign = 2; }
+                    else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = -1; }
+                    if (fabs(akk) > 0.0 && lane > kk && lane < w) {
+                        const double u = Ds[lane * (CL_PW + 1) + kk], inv = 1.0 / akk;
+                        for (int c = kk + 1; c <= lane; c++) Ds[lane * (CL_PW + 1) + c] -= u * (Ds[c * (CL_PW + 1) + kk] * inv);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) sign_io[0] = (double)sign;
+                // pivots, and the unit-lower block (unscaled entries divided by their pivot)
+                if (lane < w) {
+                    dvec[k0 + lane] = Ds[lane * (CL_PW + 1) + lane];
+                    for (int c = 0; c < lane; c++) {
+                        const double dk = Ds[c * (CL_PW + 1) + c], u = Ds[lane * (CL_PW + 1) + c];
+                        A[(size_t)(k0 + lane) * pitch + k0 + c] = (fabs(dk) > 0.0) ? u / dk : u;
+                    }
+                }
+            }
+        }
+        grid.sync();
+        // (b) rows k1..n: u_c = a_ic - sum_{j<c} u_j L11[c][j], l_ic = u_c / d_c
+        {
+            for (int t = tid; t < w * w; t += T) { const int i = t / w, c = t - i * w; Ds[i * (CL_PW + 1) + c] = (c < i) ? A[(size_t)(k0 + i) * pitch + k0 + c] : 0.0; }
+            for (int t = tid; t < w; t += T) ds[t] = dvec[k0 + t];
+            __syncthreads();
+            for (int i = k1 + gtid; i <= n; i += gsz) {
+                double *row = A + (size_t)i * pitch + k0;
+                double u[CL_PW];
+#pragma unroll
+                for (int c = 0; c < CL_PW; c++) {
+                    if (c < w) {
+                        double s = row[c];
+#pragma unroll
+                        for (int j = 0; j < c; j++) s -= u[j] * Ds[c * (CL_PW + 1) + j];
+                        u[c] = s;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CL_PW; c++)
+                    if (c < w) { const double dk = ds[c]; row[c] = (fabs(dk) > 0.0) ? u[c] / dk : u[c]; }
+            }
+        }
+        grid.sync();
+        // (c) trailing update, 64 x 64 tiles of the lower triangle (rows up to n = the right-hand side row)
+        {
+            const int m = n + 1 - k1;                       // rows / columns k1 .. n (column n is never touched)
+            if (m > 0 && k1 < n) {
+                const int nt = (m + CL_TILE - 1) / CL_TILE;
+                const int n_tiles = nt * (nt + 1) / 2;
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                    int ti = 0, rem = tile;                 // tile -> (ti >= tj) of the lower triangle
+                    while (rem > ti) { rem -= ti + 1; ti++; }
+                    const int tj = rem;
+                    const int i0 = k1 + ti * CL_TILE, j0 = k1 + tj * CL_TILE;
+                    __syncthreads();
+                    for (int t = tid; t < CL_TILE * CL_PW; t += T) {
+                        const int r = t / CL_PW, c = t - r * CL_PW;
+                        const int i = i0 + r, j = j0 + r;
+                        Li[r * (CL_PW + 1) + c] = (i <= n && c < w) ? A[(size_t)i * pitch + k0 + c] : 0.0;
+                        Lj[r * (CL_PW + 1) + c] = (j < n && c < w) ? A[(size_t)j * pitch + k0 + c] * ds[c] : 0.0;
+                    }
+                    __syncthreads();
+                    const int tr = (tid >> 5) * 4, tc = tid & 31;          // rows tr..tr+3, columns tc and tc + 32
+                    double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+#pragma unroll 8
+                    for (int c = 0; c < CL_PW; c++) {
+                        const double b0 = Lj[tc * (CL_PW + 1) + c], b1 = Lj[(tc + 32) * (CL_PW + 1) + c];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { const double a = Li[(tr + q) * (CL_PW + 1) + c]; acc[q][0] += a * b0; acc[q][1] += a * b1; }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int i = i0 + tr + q, j = j0 + tc + 32 * h;
+                            if (i <= n && j < n && j <= i) A[(size_t)i * pitch + j] -= acc[q][h];
+                        }
+                }
+            }
+        }
+        grid.sync();
+    }
+    if (blockIdx.x == 0) {      // z = row n where the pivot is usable; x = L^-T z, blocks of 32 from the end
+        for (int i = tid; i < n; i += T) { const double dk = dvec[i]; xs[i] = (fabs(dk) > DBL_MIN) ? A[(size_t)n * pitch + i] : 0.0; }
+        __syncthreads();
+        for (int b1 = n; b1 > 0; b1 -= CL_PW) {
+            const int b0 = max(0, b1 - CL_PW), w = b1 - b0;
+            for (int t = tid; t < w * w; t += T) { const int i = t / w, c = t - i * w; Ds[i * (CL_PW + 1) + c] = A[(size_t)(b0 + i) * pitch + b0 + c]; }
+            for (int t = tid; t < w; t += T) ds[t] = xs[b0 + t];
+            __syncthreads();
+            if (warp == 0) {
+                for (int i = w - 1; i >= 0; i--) {
+                    const double xi = ds[i];
+                    if (lane < i) ds[lane] -= Ds[i * (CL_PW + 1) + lane] * xi;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            for (int t = tid; t < w; t += T) xs[b0 + t] = ds[t];
+            for (int j = tid; j < b0; j += T) {
+                double s = 0;
+                for (int i = 0; i < w; i++) s += A[(size_t)(b0 + i) * pitch + j] * ds[i];
+                xs[j] -= s;
+            }
+            __syncthreads();
+        }
+    }
+    grid.sync();
+}

@@ -60,6 +60,28 @@ __device__ __forceinline__ void se3_exp(const double *a, double *T)
     double d0 = w[1] * c2 - w[2] * c1, d1 = w[2] * c0 - w[0] * c2, d2 = w[0] * c1 - w[1] * c0;
     T[4] = u[0] + A * c0 + B * d0; T[5] = u[1] + A * c1 + B * d1; T[6] = u[2] + A * c2 + B * d2;
 }
+__device__ __forceinline__ void se3_inv(const double *T, double *O)
+{   // Sophus::SE3d::inverse: conjugate quaternion, -R^T t
+    double q[4] = {-T[0], -T[1], -T[2], T[3]}, r[3];
+    quat_rot(q, T + 4, r);
+    O[0] = q[0]; O[1] = q[1]; O[2] = q[2]; O[3] = q[3]; O[4] = -r[0]; O[5] = -r[1]; O[6] = -r[2];
+}
+__device__ __forceinline__ void se3_log(const double *T, double *a)
+{   // Sophus::SE3d::log -> (upsilon, omega); same branches as the host mirror (host/slam.cpp SE3::log)
+    const double n2 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2], w = T[3];
+    double f, th;
+    if (n2 < 1e-10 * 1e-10) { f = 2.0 / w - (2.0 / 3.0) * n2 / (w * w * w); th = f * sqrt(n2); }
+    else { const double n = sqrt(n2); const double at = (w < 0) ? atan2(-n, -w) : atan2(n, w); f = 2.0 * at / n; th = f * n; }
+    const double om[3] = {f * T[0], f * T[1], f * T[2]};
+    double c;
+    if (fabs(th) < 1e-10) c = 1.0 / 12.0;
+    else { const double h = 0.5 * th; c = (1.0 - th * cos(h) / (2.0 * sin(h))) / (th * th); }
+    const double *t = T + 4;
+    const double x0 = om[1] * t[2] - om[2] * t[1], x1 = om[2] * t[0] - om[0] * t[2], x2 = om[0] * t[1] - om[1] * t[0];
+    const double y0 = om[1] * x2 - om[2] * x1, y1 = om[2] * x0 - om[0] * x2, y2 = om[0] * x1 - om[1] * x0;
+    a[0] = t[0] - 0.5 * x0 + c * y0; a[1] = t[1] - 0.5 * x1 + c * y1; a[2] = t[2] - 0.5 * x2 + c * y2;
+    a[3] = om[0]; a[4] = om[1]; a[5] = om[2];
+}
 __device__ __forceinline__ void se3_oplus(const double *T, const double *upd, double *O)
 {   // VertexPose::oplusImpl (g2o_types.h:40-60): O = exp(upd) * T
     double E[7];

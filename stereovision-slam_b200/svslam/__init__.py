@@ -336,6 +336,24 @@ def _backproject(self, disp, bgr, K, baseline, cam_pose_inv, T_cw):
 
 
 Context.triangulate = _triangulate
+def _pose_graph_optimize(self, poses, fixed, edge_a, edge_b, meas, max_iter=22, jac_mode=1):
+    P = _f64(poses).reshape(-1, 7).copy()
+    fx, ea, eb, M = _u8(fixed), _i32(edge_a), _i32(edge_b), _f64(meas).reshape(-1, 7)
+    st = BaStats()
+    self._chk(self.lib.svs_pose_graph_optimize(C.c_void_p(self.h), len(P), _p(P), _p(fx), len(ea), _p(ea), _p(eb), _p(M), int(max_iter),
+                                               int(jac_mode), C.byref(st)))
+    return P, st
+
+
+def _pose_graph_move_landmarks(self, lms, lm_kf, old_poses, new_poses):
+    L = _f64(lms).reshape(-1, 3).copy()
+    k, po, pn = _i32(lm_kf), _f64(old_poses).reshape(-1, 7), _f64(new_poses).reshape(-1, 7)
+    self._chk(self.lib.svs_pose_graph_move_landmarks(C.c_void_p(self.h), len(L), _p(L), _p(k), len(po), _p(po), _p(pn)))
+    return L
+
+
+Context.pose_graph_optimize = _pose_graph_optimize
+Context.pose_graph_move_landmarks = _pose_graph_move_landmarks
 Context.pose_only_lm = _pose_only_lm
 Context.ba_optimize = _ba_optimize
 Context.stereo_bm = _stereo_bm

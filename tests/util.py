@@ -139,3 +139,29 @@ def rel_to_norm(a, b):
     return np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(b, axis=-1), 1e-12)
 
 
+
+
+def pose_graph_problem(seed, n=40, drift=(0.02, 0.004), loops=((-1, 2),), step=0.15):
+    """A keyframe chain with odometry drift and loop edges, like LoopClosure::PoseGraphOptimization sees
+    (src/loopclosure.cpp:641-746): returns dict(poses (drifted initial estimate), fixed, edge_a, edge_b, meas, gt)."""
+    from oracle import geom
+    rng = np.random.RandomState(seed)
+
+    def rnd(st, sr):
+        return geom.se3_exp(np.concatenate([rng.randn(3) * st, rng.randn(3) * sr]))
+    gt = [geom.se3_inv(geom.se3_exp(np.array([3 * np.sin(step * i), 0.1 * np.sin(2 * step * i), 3 * (1 - np.cos(step * i)), 0, step * i, 0])))
+          for i in range(n)]
+    ea, eb, meas = [], [], []
+    for i in range(1, n):
+        ea.append(i); eb.append(i - 1)
+        meas.append(geom.se3_mul(geom.se3_mul(gt[i], geom.se3_inv(gt[i - 1])), rnd(*drift)))
+    for (a, b) in loops:
+        a, b = a % n, b % n
+        ea.append(a); eb.append(b)
+        meas.append(geom.se3_mul(geom.se3_mul(gt[a], geom.se3_inv(gt[b])), rnd(drift[0] * 0.2, drift[1] * 0.2)))
+    init = [gt[0]]
+    for i in range(1, n):
+        init.append(geom.se3_mul(meas[i - 1], init[-1]))
+    fixed = np.zeros(n, np.uint8)
+    fixed[0] = 1
+    return dict(poses=np.array(init), fixed=fixed, edge_a=np.array(ea, np.int32), edge_b=np.array(eb, np.int32), meas=np.array(meas), gt=np.array(gt))
