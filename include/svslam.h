@@ -265,6 +265,18 @@ SVS_API int svs_backproject(svs_ctx *ctx, const int16_t *disp, const uint8_t *bg
                             int32_t *n_out);
 SVS_API int svs_bgr2gray(svs_ctx *ctx, const uint8_t *bgr, int w, int h, int n_images, uint8_t *gray);
 
+/* ---------------------------------------------------------------- f3 : dense-map post-processing
+ * svs_pointcloud_sor replaces pcl::StatisticalOutlierRemoval with setMeanK(mean_k = 50), setStddevMulThresh(stddev_mul = 1.0) as
+ * used per keyframe and on the merged map (src/dense_reconstruction.cpp:179-184, :194-200): the mean distance of every point to
+ * its mean_k nearest neighbours (exact k-NN, float distances), keep[i] = mean_i <= mu + stddev_mul * sigma over all points.
+ * svs_voxel_grid replaces pcl::VoxelGrid with setLeafSize(leaf = 0.02) (:203-209): one centroid per occupied voxel (xyz and
+ * colour averaged), in ascending voxel index; like PCL, a cloud whose voxel index would overflow 32 bits is returned
+ * unchanged (n_out = n).  PCL is un-vendored: semantics restated from PCL 1.12, parity unpinned. */
+SVS_API int svs_pointcloud_sor(svs_ctx *ctx, const float *xyz /* 3n */, int n, int mean_k, double stddev_mul, uint8_t *keep_out /* n */,
+                               float *mean_dist_out /* n or NULL */, int *n_kept);
+SVS_API int svs_voxel_grid(svs_ctx *ctx, const float *xyz /* 3n */, const uint8_t *rgb /* 3n or NULL */, int n, double leaf,
+                           float *xyz_out /* 3n */, uint8_t *rgb_out /* 3n or NULL */, int *n_out);
+
 /* ---------------------------------------------------------------- a6 / a8 / a9 : the pipeline
  * svs_slam steps n_streams independent stereo streams in lock-step through the host-side mirror of the reference's
  * Frontend / Backend / Map classes (stereovision-slam_b200/host/slam.h), i.e. it is Frontend::AddFrame

@@ -24,6 +24,7 @@
 #include <omp.h>
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -82,12 +83,13 @@ __host__ __device__ inline size_t ba_smem_need(int NA, int n_S)
 }
 #include "ba_ldlt.cuh"
 
+template <int BT>
 __device__ __forceinline__ double block_sum(double v, double *red)
 {   // deterministic tree reduction; result broadcast to all threads
     int tid = threadIdx.x;
     red[tid] = v;
     __syncthreads();
-    for (int s = BA_T / 2; s > 0; s >>= 1) {
+    for (int s = BT / 2; s > 0; s >>= 1) {
         if (tid < s) red[tid] += red[tid + s];
         __syncthreads();
     }
@@ -95,12 +97,13 @@ __device__ __forceinline__ double block_sum(double v, double *red)
     __syncthreads();
     return r;
 }
+template <int BT>
 __device__ __forceinline__ double block_max(double v, double *red)
 {
     int tid = threadIdx.x;
     red[tid] = v;
     __syncthreads();
-    for (int s = BA_T / 2; s > 0; s >>= 1) {
+    for (int s = BT / 2; s > 0; s >>= 1) {
         if (tid < s) red[tid] = fmax(red[tid], red[tid + s]);
         __syncthreads();
     }
@@ -109,7 +112,10 @@ __device__ __forceinline__ double block_max(double v, double *red)
     return r;
 }
 
-__global__ void __launch_bounds__(BA_T, 1)
+// BT = 512: one CTA per SM (fastest single window).  BT = 256: two CTAs per SM — a window takes longer but a launch with more
+// windows than SMs runs in ONE wave instead of two (the kernel is latency-bound: 20 % issue-active at 512 threads).
+template <int BT>
+__global__ void __launch_bounds__(BT, BT == 512 ? 1 : 2)
 k_ba_window(BaArgs A)
 {
     extern __shared__ double smd[];
@@ -117,8 +123,8 @@ k_ba_window(BaArgs A)
     int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NA = P.NA, L = P.L, E = P.E, np = 6 * NA, pitch = np | 1;
     // ---- shared memory carve-up
-    double *red = smd;                       // BA_T
-    double *poseA = red + BA_T;              // 7*NA accepted
+    double *red = smd;                       // BT
+    double *poseA = red + BT;              // 7*NA accepted
     double *poseT = poseA + 7 * NA;          // 7*NA trial
     double *Hpp = poseT + 7 * NA;            // 36*NA
     double *bp = Hpp + 36 * NA;              // np
@@ -147,18 +153,18 @@ k_ba_window(BaArgs A)
     const int G = P.G;
     const double hd = A.huber_delta;
 
-    for (int i = tid; i < 7 * NA; i += BA_T) {
+    for (int i = tid; i < 7 * NA; i += BT) {
         int a = i / 7;
         double v = A.poses[7 * (size_t)(P.pose0 + A.act_pose[P.act0 + a]) + (i - 7 * a)];
         poseA[i] = v; poseT[i] = v;
     }
-    for (int i = tid; i < 3 * L; i += BA_T) lmT[i] = lms[i];
+    for (int i = tid; i < 3 * L; i += BT) lmT[i] = lms[i];
     __syncthreads();
 
     // robust chi2 of a state (poses in shared memory, landmarks in global)
     auto chi2_of = [&](const double *pz, const double *lz) -> double {
         double acc = 0;
-        for (int l = tid; l < L; l += BA_T) {
+        for (int l = tid; l < L; l += BT) {
             for (int s = l_off[l]; s < l_off[l + 1]; s++) {
                 int e = l_edges[s], cam = edge_cam[e];
                 double er[2], a[3], c[3];
@@ -168,7 +174,7 @@ k_ba_window(BaArgs A)
                 acc += r0;
             }
         }
-        return block_sum(acc, red);
+        return block_sum<BT>(acc, red);
     };
 
     int st_it = 0, st_tr = 0, st_lin = 0, st_sol = 0;
@@ -178,7 +184,7 @@ k_ba_window(BaArgs A)
     for (int it = 0; it < A.max_iter && !stop; it++) {
         // ================= linearise at the accepted state =================
         double acc = 0;
-        for (int l = tid; l < L; l += BA_T) {
+        for (int l = tid; l < L; l += BT) {
             int s0 = l_off[l], s1 = l_off[l + 1];
             if (s0 == s1) continue;
             double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b3[3] = {0, 0, 0};
@@ -222,9 +228,9 @@ k_ba_window(BaArgs A)
 #pragma unroll
             for (int x = 0; x < 3; x++) bl[3 * (size_t)l + x] = b3[x];
         }
-        double cur = block_sum(acc, red);
+        double cur = block_sum<BT>(acc, red);
         if (it == 0) chi_init = cur;
-        for (int a = warp; a < NA; a += BA_T / 32) {
+        for (int a = warp; a < NA; a += BT / 32) {
             double H[21], b6[6];
 #pragma unroll
             for (int x = 0; x < 21; x++) H[x] = 0;
@@ -266,10 +272,10 @@ k_ba_window(BaArgs A)
         st_lin++;
         if (it == 0) {   // lambda_init = tau * max diagonal over all active vertices
             double md = 0;
-            for (int i = tid; i < np; i += BA_T) md = fmax(md, fabs(Hpp[36 * (i / 6) + 7 * (i % 6)]));
-            for (int l = tid; l < L; l += BA_T)
+            for (int i = tid; i < np; i += BT) md = fmax(md, fabs(Hpp[36 * (i / 6) + 7 * (i % 6)]));
+            for (int l = tid; l < L; l += BT)
                 if (l_off[l] != l_off[l + 1]) md = fmax(md, fmax(fabs(Hll[9 * (size_t)l]), fmax(fabs(Hll[9 * (size_t)l + 4]), fabs(Hll[9 * (size_t)l + 8]))));
-            md = block_max(md, red);
+            md = block_max<BT>(md, red);
             if (tid == 0) { s_lambda = 1e-5 * md; s_ni = 2; }
             __syncthreads();
         }
@@ -279,15 +285,15 @@ k_ba_window(BaArgs A)
         do {
             double lambda = s_lambda;
             // ---- reduced system: S = Hpp + lambda I (block diagonal), g = bp
-            for (int i = tid; i < np * pitch; i += BA_T) S[i] = 0.0;
+            for (int i = tid; i < np * pitch; i += BT) S[i] = 0.0;
             if (tid == 0) s_flag = 1;
             __syncthreads();
-            for (int i = tid; i < 36 * NA; i += BA_T) {
+            for (int i = tid; i < 36 * NA; i += BT) {
                 int a = i / 36, r = (i % 36) / 6, c2 = i % 6;
                 S[(6 * a + r) * pitch + 6 * a + c2] = Hpp[i] + (r == c2 ? lambda : 0.0);
             }
             // ---- V^-1 per landmark
-            for (int l = tid; l < L; l += BA_T) {
+            for (int l = tid; l < L; l += BT) {
                 int s0 = l_off[l], s1 = l_off[l + 1];
                 if (s0 == s1) continue;
                 double D[9], Di[9];
@@ -300,7 +306,7 @@ k_ba_window(BaArgs A)
             }
             __syncthreads();
             // ---- per GROUP: W V^-1
-            for (int e = tid; e < G; e += BA_T) {
+            for (int e = tid; e < G; e += BT) {
                 const double *Di = Dinv + 9 * (size_t)g_lm[e], *W = Hpl + 18 * (size_t)e;
                 double X[18];
 #pragma unroll
@@ -318,7 +324,7 @@ k_ba_window(BaArgs A)
                 const int32_t *pr_e1 = A.pr_e1 + P.pair0, *pr_e2 = A.pr_e2 + P.pair0;
                 const int32_t *ch_off = A.ch_off + P.choff0;
                 double *part = A.part + 36 * (size_t)P.part0;
-                for (int t = tid; t < 4 * P.nch; t += BA_T) {
+                for (int t = tid; t < 4 * P.nch; t += BT) {
                     int ch = t >> 2, qr = (t >> 1) & 1, qc = t & 1;
                     double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
                     // software pipeline: the indices of pair p+2 and the 2 x 9 operands of pair p+1 are in flight while pair p
@@ -352,7 +358,7 @@ k_ba_window(BaArgs A)
             {
                 const int32_t *blk_i = A.blk_i + P.blk0, *blk_j = A.blk_j + P.blk0, *blk_ch = A.blk_ch + P.bch0;
                 const double *part = A.part + 36 * (size_t)P.part0;
-                for (int t = tid; t < P.nblk * 36; t += BA_T) {
+                for (int t = tid; t < P.nblk * 36; t += BT) {
                     int bk = t / 36, ent = t - 36 * bk, r = ent / 6, c2 = ent - 6 * r;
                     double sum = 0;
                     const double *C = part + ent;
@@ -364,7 +370,7 @@ k_ba_window(BaArgs A)
                 }
             }
             // ---- g_i = bp_i - sum_e (W V^-1)_e bl
-            for (int a = warp; a < NA; a += BA_T / 32) {
+            for (int a = warp; a < NA; a += BT / 32) {
                 double s6[6] = {0, 0, 0, 0, 0, 0};
                 for (int s = pg_off[a] + lane; s < pg_off[a + 1]; s += 32) {
                     int e = pg_groups[s];
@@ -380,12 +386,12 @@ k_ba_window(BaArgs A)
             }
             __syncthreads();
             bool ok = s_flag != 0;
-            if (ok) ok = S2 ? block_ldlt_solve_pp(S, S2, pitch, np, g, xp, tr, tmp) : block_ldlt_solve(S, pitch, np, g, xp, tr, tmp, &s_piv);
+            if (ok) ok = S2 ? block_ldlt_solve_pp<BT>(S, S2, pitch, np, g, xp, tr, tmp) : block_ldlt_solve<BT>(S, pitch, np, g, xp, tr, tmp, &s_piv);
             st_sol++;
-            if (!ok) { for (int i = tid; i < np; i += BA_T) xp[i] = 0.0; __syncthreads(); }
+            if (!ok) { for (int i = tid; i < np; i += BT) xp[i] = 0.0; __syncthreads(); }
             // ---- back-substitution, trial state, scale term
             double sc = 0;
-            for (int l = tid; l < L; l += BA_T) {
+            for (int l = tid; l < L; l += BT) {
                 int s0 = l_off[l], s1 = l_off[l + 1];
                 if (s0 == s1) continue;
                 double c3[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
@@ -412,8 +418,8 @@ k_ba_window(BaArgs A)
                     sc += x3[x] * (lambda * x3[x] + bl[3 * (size_t)l + x]);
                 }
             }
-            for (int a = tid; a < NA; a += BA_T) gd::se3_oplus(poseA + 7 * a, xp + 6 * a, poseT + 7 * a);
-            double scl = block_sum(sc, red);     // also orders the trial-state writes before chi2_of reads them
+            for (int a = tid; a < NA; a += BT) gd::se3_oplus(poseA + 7 * a, xp + 6 * a, poseT + 7 * a);
+            double scl = block_sum<BT>(sc, red);     // also orders the trial-state writes before chi2_of reads them
             double tmpchi = chi2_of(poseT, lmT);
             if (tid == 0) {
                 double scp = 0;
@@ -430,8 +436,8 @@ k_ba_window(BaArgs A)
             rho = s_rho;
             if (s_q) {
                 cur = s_cur;
-                for (int i = tid; i < 7 * NA; i += BA_T) poseA[i] = poseT[i];
-                for (int i = tid; i < 3 * L; i += BA_T) lms[i] = lmT[i];
+                for (int i = tid; i < 7 * NA; i += BT) poseA[i] = poseT[i];
+                for (int i = tid; i < 3 * L; i += BT) lms[i] = lmT[i];
             }
             __syncthreads();
             q++; st_tr++;
@@ -442,13 +448,13 @@ k_ba_window(BaArgs A)
         __syncthreads();
     }
     // ---- outputs: per-edge chi2 as g2o leaves it (errors of the LAST evaluated state, possibly a rejected trial)
-    for (int e = tid; e < E; e += BA_T) {
+    for (int e = tid; e < E; e += BT) {
         int cam = edge_cam[e];
         double er[2], a[3], c[3];
         gd::ba_error(poseT + 7 * edge_p[e], A.ext[cam], A.K[cam], lmT + 3 * (size_t)edge_l[e], edge_uv + 2 * e, er, a, c);
         A.edge_chi2[P.e0 + e] = er[0] * er[0] + er[1] * er[1];
     }
-    for (int i = tid; i < 7 * NA; i += BA_T) {
+    for (int i = tid; i < 7 * NA; i += BT) {
         int a = i / 7;
         A.poses[7 * (size_t)(P.pose0 + A.act_pose[P.act0 + a]) + (i - 7 * a)] = poseA[i];
     }
@@ -688,8 +694,16 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     for (int i = 0; i < 4; i++) { A.K[0][i] = K_left[i]; A.K[1][i] = K_right[i]; }
     for (int i = 0; i < 7; i++) { A.ext[0][i] = ext_left[i]; A.ext[1][i] = ext_right[i]; }
     A.huber_delta = huber_delta; A.max_iter = max_iter; A.jac_mode = jacobian_mode; A.smem_bytes = (int)max_smem;
-    SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_ba_window)));
-    SVS_KERNEL(c, KID_BA_WINDOW, k_ba_window<<<n_prob, BA_T, max_smem, c->stream>>>(A));
+    // more windows than SMs: 256-thread CTAs, two per SM, so that the launch is one wave (unless the windows are so large that
+    // two reduced systems do not fit an SM's shared memory)
+    const bool two_per_sm = n_prob > c->sm_count && 2 * (max_smem + 1024) <= 220 * 1024 && !getenv("SVS_BA_ONE_PER_SM");
+    if (two_per_sm) {
+        SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_ba_window<256>)));
+        SVS_KERNEL(c, KID_BA_WINDOW, k_ba_window<256><<<n_prob, 256, max_smem, c->stream>>>(A));
+    } else {
+        SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_ba_window<512>)));
+        SVS_KERNEL(c, KID_BA_WINDOW, k_ba_window<512><<<n_prob, BA_T, max_smem, c->stream>>>(A));
+    }
     uint8_t *ho = c->h_out.as<uint8_t>();
     SVS_CUDA(c, cudaMemcpyAsync(ho, c->d_out.p, out_b, cudaMemcpyDeviceToHost, c->stream));
     size_t ho_pose = align_up(out_b, 16), ho_lm = ho_pose + (size_t)sumN * 56;

@@ -1,9 +1,6 @@
 // Block-cooperative pivoted LDLT (Eigen::LDLT order of operations) shared by k_ba_window and the sharded solver.
 #pragma once
 #include <cfloat>
-#ifndef BA_T
-#define BA_T 256
-#endif
 
 // Pre-permuted variant (needs a second n x pitch buffer S2 and n ints).  Eigen's unblocked LDLT picks, at step k, the
 // largest |diagonal| entry of the trailing part, and that part of the diagonal is NOT updated before its turn
@@ -14,19 +11,20 @@
 // block-wide version is barrier-bound: measured 76 us per solve at n = 60 with 512 threads).  Arithmetic is identical to
 // block_ldlt_solve except for the order of exactly equal pivots.  The pivots d_k go to the unused upper-triangle slot
 // S2[k][k+1] (the pitch is n + 1) so that S2[k][k] stays read-only while the groups of step k still read it.
+template <int BT>
 __device__ __forceinline__ bool block_ldlt_solve_pp(const double *S, double *S2, int pitch, int n, const double *g, double *x,
                                                     int *perm, double *tmp)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     // rank of |S_ii| in decreasing order (ties: lower index first)
-    for (int i = tid; i < n; i += BA_T) {
+    for (int i = tid; i < n; i += BT) {
         const double di = fabs(S[i * pitch + i]);
         int r = 0;
         for (int j = 0; j < n; j++) { double dj = fabs(S[j * pitch + j]); r += (dj > di || (dj == di && j < i)) ? 1 : 0; }
         perm[r] = i;
     }
     __syncthreads();
-    for (int t = tid; t < n * n; t += BA_T) {
+    for (int t = tid; t < n * n; t += BT) {
         int a = t / n, b = t - a * n;
         if (b <= a) S2[a * pitch + b] = S[perm[a] * pitch + perm[b]];
     }
@@ -36,10 +34,10 @@ __device__ __forceinline__ bool block_ldlt_solve_pp(const double *S, double *S2,
     const int sub = tid & 3, grp = tid >> 2;
     for (int k = 0; k < n; k++) {
         const double *rowk = S2 + k * pitch;
-        const int trips = (n - k + (BA_T >> 2) - 1) / (BA_T >> 2);
+        const int trips = (n - k + (BT >> 2) - 1) / (BT >> 2);
         double akk = 0;
         for (int m = 0; m < trips; m++) {
-            const int i = k + grp + m * (BA_T >> 2);
+            const int i = k + grp + m * (BT >> 2);
             const double *rowi = S2 + (i < n ? i : k) * pitch;
             double acc_i = 0, acc_k = 0;
             for (int j = sub; j < k; j += 4) {
@@ -88,6 +86,7 @@ __device__ __forceinline__ bool block_ldlt_solve_pp(const double *S, double *S2,
 
 // Pivoted LDLT of the symmetric n x n matrix S (lower triangle used, row pitch `pitch`), then solve S x = g.
 // Returns Eigen::LDLT::isPositive().  All threads of the CTA must call it.
+template <int BT>
 __device__ __forceinline__ bool block_ldlt_solve(double *S, int pitch, int n, const double *g, double *x, int *tr, double *tmp, int *s_piv)
 {
     int tid = threadIdx.x, lane = tid & 31;
@@ -108,7 +107,7 @@ __device__ __forceinline__ bool block_ldlt_solve(double *S, int pitch, int n, co
         int piv = *s_piv;
         if (piv != k) {
             // disjoint element swaps: [0,k) row part, (piv,n) column part, (k,piv) cross part, diagonal
-            for (int t = tid; t < n + 1; t += BA_T) {
+            for (int t = tid; t < n + 1; t += BT) {
                 if (t < k) { double a = S[k * pitch + t]; S[k * pitch + t] = S[piv * pitch + t]; S[piv * pitch + t] = a; }
                 else if (t == k) { double a = S[k * pitch + k]; S[k * pitch + k] = S[piv * pitch + piv]; S[piv * pitch + piv] = a; }
                 else if (t < piv) { double a = S[t * pitch + k]; S[t * pitch + k] = S[piv * pitch + t]; S[piv * pitch + t] = a; }
@@ -116,14 +115,14 @@ __device__ __forceinline__ bool block_ldlt_solve(double *S, int pitch, int n, co
             }
             __syncthreads();
         }
-        for (int j = tid; j < k; j += BA_T) tmp[j] = S[j * pitch + j] * S[k * pitch + j];
+        for (int j = tid; j < k; j += BT) tmp[j] = S[j * pitch + j] * S[k * pitch + j];
         __syncthreads();
         if (k > 0) {
             // 4 lanes per row: interleaved partial dot products combined in a fixed order
             int sub = tid & 3;
-            int trips = (n - k + (BA_T >> 2) - 1) / (BA_T >> 2);   // uniform trip count (shuffles below)
+            int trips = (n - k + (BT >> 2) - 1) / (BT >> 2);   // uniform trip count (shuffles below)
             for (int m = 0; m < trips; m++) {
-                int i = k + (tid >> 2) + m * (BA_T >> 2);
+                int i = k + (tid >> 2) + m * (BT >> 2);
                 double acc = 0;
                 if (i < n) for (int j = sub; j < k; j += 4) acc += S[i * pitch + j] * tmp[j];
                 double a1 = __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -136,8 +135,8 @@ __device__ __forceinline__ bool block_ldlt_solve(double *S, int pitch, int n, co
         }
         double akk = S[k * pitch + k];
         bool valid = fabs(akk) > 0.0;
-        if (k == 0 && !valid) { for (int j = tid; j < n; j += BA_T) tr[j] = j; sign = 0; __syncthreads(); break; }
-        if (valid) for (int i = k + 1 + tid; i < n; i += BA_T) S[i * pitch + k] /= akk;
+        if (k == 0 && !valid) { for (int j = tid; j < n; j += BT) tr[j] = j; sign = 0; __syncthreads(); break; }
+        if (valid) for (int i = k + 1 + tid; i < n; i += BT) S[i * pitch + k] /= akk;
         if (sign == 1) { if (akk < 0) sign = 2; }
         else if (sign == -1) { if (akk > 0) sign = 2; }
         else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = -1; }

@@ -17,10 +17,12 @@
 // (ld.relaxed.sys, never cached) — an all-gather + local reduce: one NVLink crossing, identical bits everywhere.  A second,
 // 2-double exchange carries [trial chi2 | landmark part of the scale term].  Slots alternate, the flags only grow.
 // Every rank then solves the reduced system redundantly: pre-permuted (Eigen::LDLT pivot order = diagonal sorted by
-// magnitude, see ba_ldlt.cuh) right-looking blocked LDL^T, 32-column panels factorised in CTA 0's shared memory, trailing
-// updates by the whole grid, the right-hand side carried as an extra row so the forward substitution is free.
+// magnitude, see ba_ldlt.cuh) right-looking blocked LDL^T over the whole grid (coop_ldlt.cuh): 32 x 32 diagonal blocks by one
+// warp, panel rows and 64 x 64 trailing tiles by every CTA, the right-hand side carried as an extra row so the forward
+// substitution is free.
 #include "svs_internal.h"
 #include "geom_dev.cuh"
+#include "coop_ldlt.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cstring>
@@ -49,7 +51,7 @@ struct CbDev {
     const int32_t *pg_groups, *gitem_pose, *gitem_lo, *gitem_hi, *gpart_off;
     const int32_t *pr_e1, *pr_e2, *ch_off, *ubk_ch, *ubk_i, *ubk_j;
     double *Hpl, *WD, *Hll, *Dinv, *bl, *xl, *part, *ppart, *gpart, *cta;
-    double *Hpp, *bp, *Xsum, *X2, *A, *dvec, *xp, *ctl, *edge_chi2;
+    double *Hpp, *bp, *Xsum, *X2, *A, *dvec, *xs, *xp, *ctl, *edge_chi2;
     unsigned long long *seq;          // [0] exchange sequence number (persists across launches)
     int n_ranks, rank;
     double *win[CB_MAXR];
@@ -158,8 +160,8 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double smd[];
     double *red = smd;                         // CB_T
-    double *panel = smd + CB_T;                // (np + 1) x (CB_PW + 1)
-    double *sdiag = panel + (size_t)(D.np + 1) * (CB_PW + 1);   // np + 1
+    double *sm_ldlt = smd + CB_T;              // CL_SMEM_DOUBLES (coop_ldlt.cuh)
+    double *sdiag = sm_ldlt + CL_SMEM_DOUBLES; // np + 2
     int *sperm = reinterpret_cast<int *>(sdiag + D.np + 2);     // np
     __shared__ double s_w[CB_T / 32][28];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -413,84 +415,12 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
             }
             if (gtid == 0) ctl[CT_SIGN] = 0;
             grid.sync();
-            for (int k0 = 0; k0 < np; k0 += CB_PW) {
-                const int w = min(CB_PW, np - k0), rows = np + 1 - k0;
-                if (blockIdx.x == 0) {
-                    for (int t = tid; t < rows * w; t += CB_T) { const int i = t / w, c2 = t - i * w; panel[i * (CB_PW + 1) + c2] = D.A[(size_t)(k0 + i) * pitch + k0 + c2]; }
-                    __syncthreads();
-                    int sign = (int)ctl[CT_SIGN];      // 0 none yet, 1 / -1 all pivots so far of that sign, 2 mixed, 3 zero first pivot
-                    for (int kk = 0; kk < w; kk++) {
-                        const double akk = panel[kk * (CB_PW + 1) + kk];
-                        if (k0 + kk == 0 && !(fabs(akk) > 0.0)) sign = 3;
-                        if (sign == 1) { if (akk < 0) sign = 2; }
-                        else if (sign == -1) { if (akk > 0) sign = 2; }
-                        else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = -1; }
-                        const bool valid = fabs(akk) > 0.0;
-                        if (valid) {
-                            const double inv = 1.0 / akk;
-                            const int i = kk + 1 + tid;          // one row per thread (rows <= np + 1 <= CB_T)
-                            if (i < rows) {
-                                const double u = panel[i * (CB_PW + 1) + kk];
-                                const int cmax = min(w - 1, i);
-                                for (int c2 = kk + 1; c2 <= cmax; c2++) panel[i * (CB_PW + 1) + c2] -= u * (panel[c2 * (CB_PW + 1) + kk] * inv);
-                            }
-                        }
-                        __syncthreads();
-                    }
-                    // write back: d_k and the final L columns (unscaled values divided by their pivot)
-                    for (int t = tid; t < rows * w; t += CB_T) {
-                        const int i = t / w, c2 = t - i * w;
-                        if (i < c2) continue;
-                        const double dk = panel[c2 * (CB_PW + 1) + c2];
-                        if (i == c2) D.dvec[k0 + c2] = dk;
-                        else D.A[(size_t)(k0 + i) * pitch + k0 + c2] = (fabs(dk) > 0.0) ? panel[i * (CB_PW + 1) + c2] / dk : panel[i * (CB_PW + 1) + c2];
-                    }
-                    if (tid == 0) ctl[CT_SIGN] = sign;
-                }
-                grid.sync();
-                // trailing update by the whole grid: A[i][j] -= sum_c L[i][c] d_c L[j][c], k1 <= j <= i <= np (row np = rhs)
-                const int k1 = k0 + w, m = np + 1 - k1;
-                if (m > 0 && k1 < np) {
-                    const long long tot = (long long)m * m;
-                    for (long long t = gtid; t < tot; t += gsz) {
-                        const int ii = (int)(t / m), jj = (int)(t - (long long)ii * m);
-                        const int i = k1 + ii, j = k1 + jj;
-                        if (j > i || j >= np) continue;
-                        const double *Li = D.A + (size_t)i * pitch + k0, *Lj = D.A + (size_t)j * pitch + k0;
-                        double s = 0;
-                        for (int c2 = 0; c2 < w; c2++) s += Li[c2] * (D.dvec[k0 + c2] * Lj[c2]);
-                        D.A[(size_t)i * pitch + j] -= s;
-                    }
-                }
-                grid.sync();
-            }
-            if (blockIdx.x == 0) {      // z = D^-1 L^-1 g sits in row np; x = L^-T z, blocked from the end; un-permute
+            // right-looking blocked LDL^T over the whole grid + back-substitution (coop_ldlt.cuh); solution in D.xs (permuted)
+            coop_ldlt_solve<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt);
+            if (blockIdx.x == 0) {
                 const int sign = (int)ctl[CT_SIGN];
                 const bool ok = v_ok && (sign == 1 || sign == 0);
-                double *xs = sdiag;
-                for (int i = tid; i < np; i += CB_T) {
-                    const double dk = D.dvec[i];
-                    xs[i] = (fabs(dk) > DBL_MIN) ? D.A[(size_t)np * pitch + i] : 0.0;
-                }
-                __syncthreads();
-                for (int b1 = np; b1 > 0; b1 -= 32) {
-                    const int b0 = max(0, b1 - 32);
-                    if (warp == 0) {
-                        for (int i = b1 - 1; i >= b0; i--) {
-                            const double xi = xs[i];
-                            const int j = b0 + lane;
-                            if (j < i) xs[j] -= D.A[(size_t)i * pitch + j] * xi;
-                            __syncwarp();
-                        }
-                    }
-                    __syncthreads();
-                    for (int j = tid; j < b0; j += CB_T) {
-                        double s = 0;
-                        for (int i = b0; i < b1; i++) s += D.A[(size_t)i * pitch + j] * xs[i];
-                        xs[j] -= s;
-                    }
-                    __syncthreads();
-                }
+                const double *xs = D.xs;
                 for (int i = tid; i < np; i += CB_T) D.xp[sperm[i]] = ok ? xs[i] : 0.0;
                 __syncthreads();
                 for (int a = tid; a < N; a += CB_T) gd::se3_oplus(D.poses + 7 * a, D.xp + 6 * a, D.poseT + 7 * a);
@@ -595,7 +525,6 @@ svs_ba_shard *svs_ba_shard_create(svs_ctx *c, int n_kf, const double *poses, int
     if (!c || n_kf <= 0 || n_lm < 0 || n_edge < 0 || !poses) return nullptr;
     if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
     const int N = n_kf, L = n_lm, E = n_edge, np = 6 * N;
-    if (np + 1 > CB_T) { c->err = "ba_shard: more than 85 keyframes"; return nullptr; }
     for (int e = 0; e < E; e++) if (edge_kf[e] < 0 || edge_kf[e] >= N || edge_lm[e] < 0 || edge_lm[e] >= L) { c->err = "ba_shard: edge index out of range"; return nullptr; }
     // ---- structure (every keyframe is in the system: with landmark sharding a pose may have no LOCAL edge)
     std::vector<int32_t> l_off(L + 1, 0), l_edges(E), p_off(N + 1, 0), p_edges(E);
@@ -696,7 +625,7 @@ svs_ba_shard *svs_ba_shard_create(svs_ctx *c, int n_kf, const double *poses, int
     const size_t o_Hpl = res((size_t)G * 144), o_WD = res((size_t)G * 144), o_Hll = res((size_t)L * 72), o_Di = res((size_t)L * 72);
     const size_t o_bl = res((size_t)L * 24), o_xl = res((size_t)L * 24), o_part = res((size_t)nch * 288), o_pp = res(pitem_pose.size() * 216 + 8);
     const size_t o_gpt = res(gitem_pose.size() * 48 + 8), o_cta = res((size_t)max_cta * 64), o_Hpp = res((size_t)N * 288), o_bp = res((size_t)np * 8);
-    const size_t o_X = res((size_t)xn * 8), o_X2 = res(64), o_A = res((size_t)(np + 1) * (np + 1) * 8), o_dv = res((size_t)np * 8), o_xp = res((size_t)np * 8);
+    const size_t o_X = res((size_t)xn * 8), o_X2 = res(64), o_A = res((size_t)(np + 1) * (np + 1) * 8), o_dv = res((size_t)np * 8), o_xs = res((size_t)np * 8), o_xp = res((size_t)np * 8);
     const size_t o_ctl = res(CT_COUNT * 8), o_chi = res((size_t)E * 8 + 8), o_seq = res(64);
     sh->window_bytes = CB_FLAGS * 8 + 2 * (size_t)xn * 8;
     if (sh->buf.reserve(tot) != cudaSuccess || sh->window.reserve(sh->window_bytes) != cudaSuccess) { c->err = "ba_shard: cudaMalloc failed"; sh->buf.release(); sh->window.release(); delete sh; return nullptr; }
@@ -717,7 +646,7 @@ svs_ba_shard *svs_ba_shard_create(svs_ctx *c, int n_kf, const double *poses, int
     d.Hpl = (double *)(db + o_Hpl); d.WD = (double *)(db + o_WD); d.Hll = (double *)(db + o_Hll); d.Dinv = (double *)(db + o_Di);
     d.bl = (double *)(db + o_bl); d.xl = (double *)(db + o_xl); d.part = (double *)(db + o_part); d.ppart = (double *)(db + o_pp);
     d.gpart = (double *)(db + o_gpt); d.cta = (double *)(db + o_cta); d.Hpp = (double *)(db + o_Hpp); d.bp = (double *)(db + o_bp);
-    d.Xsum = (double *)(db + o_X); d.X2 = (double *)(db + o_X2); d.A = (double *)(db + o_A); d.dvec = (double *)(db + o_dv); d.xp = (double *)(db + o_xp);
+    d.Xsum = (double *)(db + o_X); d.X2 = (double *)(db + o_X2); d.A = (double *)(db + o_A); d.dvec = (double *)(db + o_dv); d.xs = (double *)(db + o_xs); d.xp = (double *)(db + o_xp);
     d.ctl = (double *)(db + o_ctl); d.edge_chi2 = (double *)(db + o_chi); d.seq = (unsigned long long *)(db + o_seq);
     d.n_ranks = 1; d.rank = 0;
     for (int r = 0; r < CB_MAXR; r++) d.win[r] = nullptr;
@@ -766,7 +695,7 @@ int svs_ba_shard_launch(svs_ctx *c, svs_ba_shard *sh, int max_iter)
     if (!c || !sh || max_iter < 0) return SVS_ERR_ARG;
     SVS_CUDA(c, cudaSetDevice(c->device));
     const int np = sh->d.np;
-    const size_t smem = ((size_t)CB_T + (size_t)(np + 1) * (CB_PW + 1) + np + 2) * 8 + (size_t)np * 4 + 16;
+    const size_t smem = ((size_t)CB_T + CL_SMEM_DOUBLES + np + 2) * 8 + (size_t)np * 4 + 16;
     SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_bs_lm)));
     int per_sm = 0;
     SVS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bs_lm, CB_T, smem));

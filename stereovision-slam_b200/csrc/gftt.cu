@@ -15,6 +15,7 @@
 #include "tma.cuh"
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 __device__ __forceinline__ int g_refl101(int i, int n)
 {
@@ -156,9 +157,9 @@ k_corner_response(const uint8_t *__restrict__ img_base, size_t img_pitch, const 
 // a RUNNING f64 column sum (SUM += new row; out = SUM; SUM -= old row), whose rounding depends on the history of the column.
 // But its intermediate values are only ever T_y = rs(y) + rs(y+1) and O_y = T_(y-1) + rs(y+1) (rs = f64 row sums of three f32
 // products): if every one of those sums is EXACTLY representable, every add / subtract of the running scheme is exact and the
-// result is the exact sum, whatever the order.  For 8-bit images that is always the case (the products span < 2^-1 .. 2^-47,
-// 46 bits < 53).  So: tiles compute out = (rs(y-1) + rs(y)) + rs(y+1) fully in parallel and CHECK exactness with TwoSum; a
-// tile that sees one inexact sum flags its image, and the flagged images (never seen so far) are recomputed by the
+// result is the exact sum, whatever the order.  That holds for most pixels of an 8-bit image (products between 2^-47 and 2^-1)
+// but not all: a cancelling Sobel sum leaves a ~1e-10 residual whose square sits 60+ bits below a strong neighbour.  So: tiles compute out = (rs(y-1) + rs(y)) + rs(y+1) fully in parallel and CHECK exactness with TwoSum; a
+// tile that sees one inexact sum flags its image, and the flagged images are recomputed by the
 // sequential kernel — bit-exactness is kept unconditionally, and the grid grows from 66 CTAs to one tile per 64x16 outputs.
 // Staging: the 96 x 20 source box (16 bytes left of the tile, see SVS_CR_BOX_W) arrives by cp.async.bulk.tensor (UTMALDG) into one of two buffers while the
 // previous tile is computed; zero-filled out-of-image bytes are patched to reflect-101 in shared memory.
@@ -457,8 +458,13 @@ int svs_i_gftt(svs_ctx *c, const uint8_t *img, int w, int h, int stride, size_t 
     if (!tmap && w >= 8 && h >= 8 && (stride & 15) == 0 && (img_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 && !img_ids &&
         svs_i_tmap_u8_3d(&tm_local, img, w, h, n_img, (size_t)stride, n_img > 1 ? img_pitch : align_up((size_t)stride * h, 16), SVS_CR_BOX_W, SVS_CR_BOX_H) == 0)
         tmap = &tm_local;
-    if (tmap && w >= 8 && h >= 8) {
-        // tiled + TMA-staged kernel with the exactness check; the sequential kernel re-does the images it flags (none so far)
+    // A big batch already fills the machine with one warp per 28-column strip (the sequential march), and the tiled kernel's
+    // exactness check does fire in practice (a residual gradient of ~1e-10 next to a strong one puts more than 53 bits between
+    // the products), so the tiled + fallback pair only pays when there are too few strips to occupy the SMs: small batches,
+    // single streams (latency), the full-resolution configuration.
+    const bool enough_strips = (long long)grd.x * grd.y >= 2LL * c->sm_count && !getenv("SVS_GFTT_TILED");
+    if (tmap && w >= 8 && h >= 8 && !enough_strips) {
+        // tiled + TMA-staged kernel with the exactness check; the sequential kernel re-does the images it flags
         const int tx = (w + CT_W - 1) / CT_W, ty = (h + CT_H - 1) / CT_H;
         const long long total = (long long)tx * ty * n_img;
         SVS_CUDA(c, c->d_tmp7.reserve((size_t)total * 4 + (size_t)n_img * 4 + 16));

@@ -352,6 +352,27 @@ def _pose_graph_move_landmarks(self, lms, lm_kf, old_poses, new_poses):
     return L
 
 
+def _pointcloud_sor(self, xyz, mean_k=50, stddev_mul=1.0):
+    P = _f32(xyz).reshape(-1, 3)
+    keep = np.zeros(len(P), np.uint8); md = np.zeros(len(P), np.float32)
+    nk = C.c_int(0)
+    self._chk(self.lib.svs_pointcloud_sor(C.c_void_p(self.h), _p(P), len(P), int(mean_k), C.c_double(stddev_mul), _p(keep), _p(md), C.byref(nk)))
+    return keep.astype(bool), md
+
+
+def _voxel_grid(self, xyz, rgb=None, leaf=0.02):
+    P = _f32(xyz).reshape(-1, 3)
+    col = _u8(rgb).reshape(-1, 3) if rgb is not None else None
+    out = np.zeros((len(P), 3), np.float32)
+    oc = np.zeros((len(P), 3), np.uint8) if col is not None else None
+    n = C.c_int(0)
+    self._chk(self.lib.svs_voxel_grid(C.c_void_p(self.h), _p(P), _p(col) if col is not None else None, len(P), C.c_double(leaf), _p(out),
+                                      _p(oc) if oc is not None else None, C.byref(n)))
+    return out[:n.value].copy(), (oc[:n.value].copy() if oc is not None else None)
+
+
+Context.pointcloud_sor = _pointcloud_sor
+Context.voxel_grid = _voxel_grid
 Context.pose_graph_optimize = _pose_graph_optimize
 Context.pose_graph_move_landmarks = _pose_graph_move_landmarks
 Context.pose_only_lm = _pose_only_lm
