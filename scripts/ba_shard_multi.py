@@ -21,6 +21,8 @@ p, ids = ba_shard.split_problem(prob, world)[rank]
 res = {}
 for rep in range(3):
     sh = ba_shard.Shard(ctx, p["poses"], p["lms"], p["edge_kf"], p["edge_lm"], p["edge_cam"], p["edge_uv"], K05, K05, EXT_L, EXT_R)
+    if os.environ.get("SVS_BS_GRID"):
+        sh.set_grid_limit(int(os.environ["SVS_BS_GRID"]))
     if world > 1:
         ba_shard.wire_distributed(sh, dist)
         dist.barrier()

@@ -169,12 +169,14 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
     const int N = D.N, L = D.L, np = D.np, n_cta = gridDim.x;
     const double hd = D.huber_delta;
     double *ctl = D.ctl;
+    unsigned ldlt_gen = 0;
 
     for (int i = gtid; i < 7 * N; i += gsz) D.poseT[i] = D.poses[i];
     for (int i = gtid; i < 3 * L; i += gsz) D.lmT[i] = D.lms[i];
     if (gtid == 0) {
         ctl[CT_LAMBDA] = 0; ctl[CT_NI] = 2; ctl[CT_CUR] = 0; ctl[CT_ABORT] = 0; ctl[CT_ITERS] = 0; ctl[CT_TRIALS] = 0; ctl[CT_STOP] = 0;
         ctl[CT_LINS] = 0; ctl[CT_CHI_INIT] = 0;
+        D.seq[2] = 0;          // sub-grid barrier counter of the LDLT (coop_ldlt.cuh)
     }
     grid.sync();
 
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
             if (gtid == 0) ctl[CT_SIGN] = 0;
             grid.sync();
             // right-looking blocked LDL^T over the whole grid + back-substitution (coop_ldlt.cuh); solution in D.xs (permuted)
-            coop_ldlt_solve<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt);
+            coop_ldlt_solve<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt, reinterpret_cast<unsigned *>(D.seq + 2), ldlt_gen);
             if (blockIdx.x == 0) {
                 const int sign = (int)ctl[CT_SIGN];
                 const bool ok = v_ok && (sign == 1 || sign == 0);

@@ -7,7 +7,7 @@
 //   (b) every CTA forward-substitutes a share of the rows below it (one row per thread)
 //   (c) every CTA updates 64 x 64 tiles of the trailing matrix from shared-memory copies of the panel rows
 // The right-hand side rides along as row n (so z = D^-1 L^-1 g falls out of the factorisation); CTA 0 finishes with the
-// blocked back-substitution x = L^-T z.  Three grid barriers per panel.
+// blocked back-substitution x = L^-T z.  Three barriers per panel, among the participating CTAs only (coop_sub_sync).
 #pragma once
 #include <cooperative_groups.h>
 #include <cfloat>
@@ -20,16 +20,39 @@
 // A: (n + 1) x pitch, lower triangle of the PERMUTED matrix in rows 0..n-1, right-hand side (permuted) in row n.
 // dvec: n pivots (out).  xs: n, solution in permuted order (out, valid in CTA 0's view after the final barrier).
 // sign_io: one double in global memory, 0 on entry; Eigen's sign tracking (1 / -1 / 2 mixed / 3 zero first pivot) on exit.
+// Barrier among the first n_part CTAs of the grid (a grid-wide barrier costs ~5 us with 148 x 512 threads, this one ~1 us with
+// 16 CTAs): monotonic counter in global memory, release / acquire at GPU scope.  `gen` is the caller's running target.
+__device__ __forceinline__ void coop_sub_sync(unsigned *ctr, unsigned n_part, unsigned &gen)
+{
+    __syncthreads();
+    gen += n_part;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < gen);
+    }
+    __syncthreads();
+}
+
+// sync_ctr: one unsigned in global memory, ZERO on entry of the kernel's first call (the routine keeps it monotonic: pass the
+// same `gen` variable, initialised to 0, to every call of one kernel launch).
 template <int T>
 __device__ void coop_ldlt_solve(cooperative_groups::grid_group &grid, double *A, int n, int pitch, double *dvec, double *xs,
-                                double *sign_io, double *sm)
+                                double *sign_io, double *sm, unsigned *sync_ctr, unsigned &gen)
 {
+    // the panel loop runs on as many CTAs as the trailing update has 64 x 64 tiles (at least 8): the others wait at the end
+    const int nt0 = (n + 1 + CL_TILE - 1) / CL_TILE;
+    const unsigned n_part = (unsigned)min((int)gridDim.x, max(8, nt0 * (nt0 + 1) / 2));
+    const bool part = blockIdx.x < n_part;
+    const int psz = (int)n_part * T;
     double *Ds = sm;                              // [CL_PW][CL_PW + 1]
     double *ds = Ds + CL_PW * (CL_PW + 1);        // [CL_PW]
     double *Li = ds + CL_PW;                      // [CL_TILE][CL_PW + 1]
     double *Lj = Li + CL_TILE * (CL_PW + 1);      // [CL_TILE][CL_PW + 1]  (rows of L times the pivots)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gtid = blockIdx.x * T + tid, gsz = gridDim.x * T;
+    const int gtid = blockIdx.x * T + tid;
+    if (part)
     for (int k0 = 0; k0 < n; k0 += CL_PW) {
         const int w = min(CL_PW, n - k0), k1 = k0 + w;
         if (blockIdx.x == 0) {
@@ -60,13 +83,13 @@ __device__ void coop_ldlt_solve(cooperative_groups::grid_group &grid, double *A,
                 }
             }
         }
-        grid.sync();
+        coop_sub_sync(sync_ctr, n_part, gen);
         // (b) rows k1..n: u_c = a_ic - sum_{j<c} u_j L11[c][j], l_ic = u_c / d_c
         {
             for (int t = tid; t < w * w; t += T) { const int i = t / w, c = t - i * w; Ds[i * (CL_PW + 1) + c] = (c < i) ? A[(size_t)(k0 + i) * pitch + k0 + c] : 0.0; }
             for (int t = tid; t < w; t += T) ds[t] = dvec[k0 + t];
             __syncthreads();
-            for (int i = k1 + gtid; i <= n; i += gsz) {
+            for (int i = k1 + gtid; i <= n; i += psz) {
                 double *row = A + (size_t)i * pitch + k0;
                 double u[CL_PW];
 #pragma unroll
@@ -83,14 +106,14 @@ __device__ void coop_ldlt_solve(cooperative_groups::grid_group &grid, double *A,
                     if (c < w) { const double dk = ds[c]; row[c] = (fabs(dk) > 0.0) ? u[c] / dk : u[c]; }
             }
         }
-        grid.sync();
+        coop_sub_sync(sync_ctr, n_part, gen);
         // (c) trailing update, 64 x 64 tiles of the lower triangle (rows up to n = the right-hand side row)
         {
             const int m = n + 1 - k1;                       // rows / columns k1 .. n (column n is never touched)
             if (m > 0 && k1 < n) {
                 const int nt = (m + CL_TILE - 1) / CL_TILE;
                 const int n_tiles = nt * (nt + 1) / 2;
-                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int tile = blockIdx.x; tile < n_tiles; tile += (int)n_part) {
                     int ti = 0, rem = tile;                 // tile -> (ti >= tj) of the lower triangle
                     while (rem > ti) { rem -= ti + 1; ti++; }
                     const int tj = rem;
@@ -121,7 +144,7 @@ __device__ void coop_ldlt_solve(cooperative_groups::grid_group &grid, double *A,
                 }
             }
         }
-        grid.sync();
+        coop_sub_sync(sync_ctr, n_part, gen);
     }
     if (blockIdx.x == 0) {      // z = row n where the pivot is usable; x = L^-T z, blocks of 32 from the end
         for (int i = tid; i < n; i += T) { const double dk = dvec[i]; xs[i] = (fabs(dk) > DBL_MIN) ? A[(size_t)n * pitch + i] : 0.0; }

@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(PG_T, 1) k_pg_lm(PgDev D, int max_iter)
     const int tid = threadIdx.x, gtid = blockIdx.x * PG_T + tid, gsz = gridDim.x * PG_T;
     const int n = D.n, pitch = n + 1, n_cta = gridDim.x;
     double *ctl = D.ctl;
+    unsigned ldlt_gen = 0;
+    if (gtid == 0) D.perm[D.n] = 0;          // sub-grid barrier counter of the LDLT
     for (int i = gtid; i < 7 * D.N; i += gsz) D.poseT[i] = D.poses[i];
     for (long long i = gtid; i < (long long)n * n; i += gsz) D.H[i] = 0.0;
     if (gtid == 0) for (int i = 0; i < PC_COUNT; i++) ctl[i] = 0.0;
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(PG_T, 1) k_pg_lm(PgDev D, int max_iter)
                 D.A[(size_t)a * pitch + c] = v;
             }
             grid.sync();
-            coop_ldlt_solve<PG_T>(grid, D.A, n, pitch, D.dvec, D.xs, ctl + PC_SIGN, sm_ldlt);
+            coop_ldlt_solve<PG_T>(grid, D.A, n, pitch, D.dvec, D.xs, ctl + PC_SIGN, sm_ldlt, reinterpret_cast<unsigned *>(D.perm + D.n), ldlt_gen);
             if (blockIdx.x == 0) {
                 const int sign = (int)ctl[PC_SIGN];
                 const bool ok = (sign == 1 || sign == 0);
@@ -345,7 +347,7 @@ int svs_pose_graph_optimize(svs_ctx *c, int n_kf, double *poses, const uint8_t *
     auto res = [&](size_t bytes) { size_t o = tot; tot = align_up(tot + bytes, 256); return o; };
     const size_t o_J = res((size_t)E * 576), o_err = res((size_t)E * 48), o_H = res((size_t)n * n * 8), o_b = res((size_t)n * 8);
     const size_t o_A = res((size_t)(n + 1) * (n + 1) * 8), o_dv = res((size_t)n * 8), o_xs = res((size_t)n * 8), o_x = res((size_t)n * 8);
-    const size_t o_cta = res(2048 * 32), o_ctl = res(PC_COUNT * 8), o_perm = res((size_t)n * 4);
+    const size_t o_cta = res(2048 * 32), o_ctl = res(PC_COUNT * 8), o_perm = res((size_t)n * 4 + 16);
     SVS_CUDA(c, c->d_tmp.reserve(tot));
     uint8_t *db = c->d_tmp.as<uint8_t>();
     SVS_CUDA(c, c->h_in.reserve(tot > 0 ? o_J : 0));

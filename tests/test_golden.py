@@ -82,3 +82,47 @@ def test_cuda_geometry_matches_golden(ctx):
     assert (sb.iterations, sb.trials) == (int(GG["ba_stats"][0]), int(GG["ba_stats"][1]))
     assert abs(sb.chi2 - GG["ba_stats"][2]) < 1e-8 * GG["ba_stats"][2] and _rel(P, GG["ba_P"]) < 1e-7 and _rel(L, GG["ba_L"]) < 1e-7
     assert np.abs(chi2 - GG["ba_chi2"]).max() < 1e-6 * max(1.0, GG["ba_chi2"].max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The REAL g2o: tests/golden/golden_g2o.npz is produced by tests/golden/g2o/make_golden_g2o.cpp, which runs the committed
+# problems through the reference's own g2o_types.h on top of an installed g2o / Sophus / Eigen.  Those libraries do not exist
+# in the build image, so the file is absent there and the g2o half of the oracle stays "parity unpinned" (DESIGN.md §3); where
+# somebody has run the recipe the comparisons below turn that into a pin.
+_G2O = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_g2o.npz")
+_need_g2o = pytest.mark.skipif(not os.path.exists(_G2O), reason="golden_g2o.npz not generated (needs the real g2o: tests/golden/g2o/CMakeLists.txt)")
+
+
+def _pg_problem():
+    from util import pose_graph_problem
+    return pose_graph_problem(40, n=40, loops=((-1, 2),))
+
+
+@_need_g2o
+def test_oracle_matches_real_g2o():
+    R = np.load(_G2O)
+    T, outl, ninl, st = geom.pose_only_lm(GG["po_pts"], GG["po_uv"], GG["po_K"], GG["po_T0"])
+    assert np.array_equal(outl, R["po_outlier"]) and _rel(T, R["po_T"]) < 1e-8
+    # Backend::Optimize: g2o differentiates EdgeProjection numerically (delta 1e-9) -> 1e-4 relative-to-norm is what is defined
+    P, L, chi2, sb = geom.ba_optimize(GG["ba_poses"], GG["ba_lms"], GG["ba_edge_kf"], GG["ba_edge_lm"], GG["ba_edge_cam"], GG["ba_edge_uv"],
+                                      _K05, _K05, _EXT_L, _EXT_R, jac_mode=1)
+    rl = np.linalg.norm(L - R["ba_L"], axis=1) / np.linalg.norm(R["ba_L"], axis=1)
+    assert np.median(rl) < 1e-4 and np.quantile(rl, 0.95) < 1e-4 and _rel(P, R["ba_P"]) < 1e-4
+    pr = _pg_problem()
+    Pg, _ = geom.pose_graph_optimize(pr["poses"], pr["fixed"], pr["edge_a"], pr["edge_b"], pr["meas"], 22, 1)
+    assert _rel(Pg, R["pg_P"]) < 1e-5
+
+
+@_need_g2o
+@pytest.mark.gpu
+def test_cuda_matches_real_g2o(ctx):
+    R = np.load(_G2O)
+    (T, outl, ninl, st), = ctx.pose_only_lm([(GG["po_pts"], GG["po_uv"], GG["po_K"], GG["po_T0"])])
+    assert np.array_equal(outl, R["po_outlier"]) and _rel(T, R["po_T"]) < 1e-7
+    prob = {k[3:]: GG[k] for k in ("ba_poses", "ba_lms", "ba_edge_kf", "ba_edge_lm", "ba_edge_cam", "ba_edge_uv")}
+    (P, L, chi2, sb), = ctx.ba_optimize([prob], _K05, _K05, _EXT_L, _EXT_R, jac_mode=1)
+    rl = np.linalg.norm(L - R["ba_L"], axis=1) / np.linalg.norm(R["ba_L"], axis=1)
+    assert np.median(rl) < 1e-4 and np.quantile(rl, 0.95) < 1e-4 and _rel(P, R["ba_P"]) < 1e-4
+    pr = _pg_problem()
+    Pg, _ = ctx.pose_graph_optimize(pr["poses"], pr["fixed"], pr["edge_a"], pr["edge_b"], pr["meas"], 22, 1)
+    assert _rel(Pg, R["pg_P"]) < 1e-5
