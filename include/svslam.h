@@ -224,6 +224,8 @@ SVS_API int svs_ba_shard_optimize(svs_ctx *ctx, svs_ba_shard *sh, int max_iter, 
 SVS_API int svs_ba_shard_launch(svs_ctx *ctx, svs_ba_shard *sh, int max_iter);        /* asynchronous half of _optimize */
 SVS_API int svs_ba_shard_finish(svs_ctx *ctx, svs_ba_shard *sh, svs_ba_stats *stats); /* waits, returns the statistics */
 SVS_API int svs_ba_shard_get(svs_ctx *ctx, svs_ba_shard *sh, double *poses_out, double *lms_out, double *edge_chi2_out);
+/* diagnostics: nanoseconds per solver phase of the last optimize, measured in the kernel (phase list in csrc/ba_shard.cu) */
+SVS_API int svs_ba_shard_phase_ns(svs_ctx *ctx, svs_ba_shard *sh, double out[16]);
 /* CUDA IPC plumbing for the windows (cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle): 64-byte handles */
 SVS_API int svs_ipc_export(svs_ctx *ctx, const void *dev_ptr, unsigned char handle_out[64]);
 SVS_API int svs_ipc_import(svs_ctx *ctx, const unsigned char handle[64], void **dev_ptr_out);

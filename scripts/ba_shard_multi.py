@@ -32,12 +32,13 @@ for rep in range(3):
     if world > 1:
         t = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
     P, L, c2 = sh.get()
+    phases = sh.phase_ns()
     if world > 1:
         dist.barrier()          # nobody unmaps a window a peer may still read
     sh.close()
     res = dict(n_gpus=world, n_kf=50, n_lm=n_lm, n_edges=int(len(prob["edge_kf"])), local_edges=int(len(p["edge_kf"])), seconds=dt,
                lm_iterations=st["iterations"], trials=st["trials"], iters_per_sec=st["iterations"] / dt, chi2_init=st["chi2_init"],
-               chi2=st["chi2"], pose_checksum=float(np.abs(P).sum()))
+               chi2=st["chi2"], pose_checksum=float(np.abs(P).sum()), phase_us_per_trial={k: round(v / 1e3 / max(1, st["trials"]), 1) for k, v in phases.items()})
 if rank == 0:
     print(json.dumps(res))
 if world > 1:

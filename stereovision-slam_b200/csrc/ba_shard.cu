@@ -38,8 +38,10 @@ namespace cg = cooperative_groups;
 #define CB_MAXR 8       // ranks
 #define CB_FLAGS 64     // u64 arrival flags at the head of a window
 
+// in-kernel phase clock (gtid 0, %globaltimer): nanoseconds accumulated per phase into ctl[CT_TIME + k]
+#define CB_TSTAMP(k) do { if (gtid == 0) { const unsigned long long now_ = cb_globaltimer(); ctl[CT_TIME + (k)] += (double)(now_ - t_prev); t_prev = now_; } } while (0)
 enum { CT_LAMBDA = 0, CT_NI, CT_CUR, CT_RHO, CT_ACCEPT, CT_OK, CT_SCALE_POSE, CT_ABORT, CT_CHI_INIT, CT_ITERS, CT_TRIALS, CT_STOP,
-       CT_LINS, CT_SIGN, CT_CUR_LOCAL, CT_COUNT = 16 };
+       CT_LINS, CT_SIGN, CT_CUR_LOCAL, CT_TIME = 16, CT_COUNT = 32 };
 
 struct CbDev {
     int N, L, E, G, nch, n_pitems, n_gitems, np, nbu, xn;
@@ -68,6 +70,12 @@ struct svs_ba_shard {
 };
 
 // ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ unsigned long long cb_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ int ubk_id(int i, int j, int N) { return i * N - (i * (i - 1)) / 2 + (j - i); }      // i <= j
 
 __device__ __forceinline__ double cb_block_sum(double v, double *red)
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
     extern __shared__ double smd[];
     double *red = smd;                         // CB_T
     double *sm_ldlt = smd + CB_T;              // CL_SMEM_DOUBLES (coop_ldlt.cuh)
-    double *sdiag = sm_ldlt + CL_SMEM_DOUBLES; // np + 2
+    double *sdiag = sm_ldlt + (D.np + 1 <= CB_T ? CL_SMALL_SMEM_DOUBLES(D.np) : (size_t)CL_SMEM_DOUBLES); // np + 2
     int *sperm = reinterpret_cast<int *>(sdiag + D.np + 2);     // np
     __shared__ double s_w[CB_T / 32][28];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -170,12 +178,14 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
     const double hd = D.huber_delta;
     double *ctl = D.ctl;
     unsigned ldlt_gen = 0;
+    unsigned long long t_prev = cb_globaltimer();
 
     for (int i = gtid; i < 7 * N; i += gsz) D.poseT[i] = D.poses[i];
     for (int i = gtid; i < 3 * L; i += gsz) D.lmT[i] = D.lms[i];
     if (gtid == 0) {
         ctl[CT_LAMBDA] = 0; ctl[CT_NI] = 2; ctl[CT_CUR] = 0; ctl[CT_ABORT] = 0; ctl[CT_ITERS] = 0; ctl[CT_TRIALS] = 0; ctl[CT_STOP] = 0;
         ctl[CT_LINS] = 0; ctl[CT_CHI_INIT] = 0;
+        for (int i = CT_TIME; i < CT_COUNT; i++) ctl[i] = 0;
         D.seq[2] = 0;          // sub-grid barrier counter of the LDLT (coop_ldlt.cuh)
     }
     grid.sync();
@@ -262,6 +272,7 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
             __syncthreads();
         }
         grid.sync();
+        CB_TSTAMP(0);
         if (blockIdx.x == 0) {      // ordered sums of the item partials -> Hpp, bp; chi2; iteration-0 payload
             for (int t = tid; t < 27 * N; t += CB_T) {
                 const int a = t / 27, v = t - 27 * a;
@@ -286,6 +297,7 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
             if (tid == 0) { ctl[CT_CUR_LOCAL] = cur; ctl[CT_LINS] += 1; }     // local chi2; the global one comes with the payload
         }
         grid.sync();
+        CB_TSTAMP(1);
         if (it == 0) {      // lambda_init = tau * max diagonal over ALL vertices (global Hpp diagonal, every rank's Hll)
             if (!cb_exchange(D, grid, np + 1, np, D.Xsum)) return;
             if (gtid == 0) {
@@ -327,6 +339,7 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
                 if (tid == 0) D.cta[8 * blockIdx.x + 2] = tb;
             }
             grid.sync();
+            CB_TSTAMP(2);
             // chunk partials: 4 threads per chunk of <= CB_CH (group, group) pairs of one 6x6 block, one 3x3 quadrant each
             for (int t = gtid; t < 4 * D.nch; t += gsz) {
                 const int ch = t >> 2, qr = (t >> 1) & 1, qc = t & 1;
@@ -362,12 +375,22 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
                 __syncthreads();
             }
             grid.sync();
+            CB_TSTAMP(3);
             {   // payload into the own slot: [S_partial upper blocks | g_partial | bp_local | chi2_local | bad]
                 double *slot = D.win[D.rank] + CB_FLAGS + (size_t)((D.seq[0] + 1) & 1) * D.xn;
                 for (int t = gtid; t < D.nbu * 36; t += gsz) {
                     const int u = t / 36, ent = t - 36 * u;
-                    double sum = 0;
-                    for (int c2 = D.ubk_ch[u]; c2 < D.ubk_ch[u + 1]; c2++) sum += D.part[36 * (size_t)c2 + ent];
+                    // a near-diagonal block has hundreds of chunks: four independent partial sums keep four loads in flight (the
+                    // order of the additions stays fixed, so the result is still reproducible bit for bit)
+                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                    const int c_lo = D.ubk_ch[u], c_hi = D.ubk_ch[u + 1];
+                    int c2 = c_lo;
+                    for (; c2 + 4 <= c_hi; c2 += 4) {
+                        s0 += D.part[36 * (size_t)c2 + ent]; s1 += D.part[36 * (size_t)(c2 + 1) + ent];
+                        s2 += D.part[36 * (size_t)(c2 + 2) + ent]; s3 += D.part[36 * (size_t)(c2 + 3) + ent];
+                    }
+                    for (; c2 < c_hi; c2++) s0 += D.part[36 * (size_t)c2 + ent];
+                    const double sum = (s0 + s1) + (s2 + s3);
                     const int i = D.ubk_i[u];
                     slot[t] = ((i == D.ubk_j[u]) ? D.Hpp[36 * i + ent] : 0.0) - sum;
                 }
@@ -385,7 +408,9 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
                 }
             }
             grid.sync();
+            CB_TSTAMP(4);
             if (!cb_exchange(D, grid, D.xn, -1, D.Xsum)) return;
+            CB_TSTAMP(5);
             // ================= reduced system: S = Xsum_S + lambda I, solve S x = g =================
             const double *XS = D.Xsum, *Xg = D.Xsum + (size_t)D.nbu * 36, *Xbp = Xg + np;
             const double chi_cur = Xg[2 * np];
@@ -417,8 +442,11 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
             }
             if (gtid == 0) ctl[CT_SIGN] = 0;
             grid.sync();
+            CB_TSTAMP(6);
             // right-looking blocked LDL^T over the whole grid + back-substitution (coop_ldlt.cuh); solution in D.xs (permuted)
-            coop_ldlt_solve<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt, reinterpret_cast<unsigned *>(D.seq + 2), ldlt_gen);
+            if (np + 1 <= CB_T) coop_ldlt_solve_small<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt, reinterpret_cast<unsigned *>(D.seq + 2), ldlt_gen);
+            else coop_ldlt_solve<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt, reinterpret_cast<unsigned *>(D.seq + 2), ldlt_gen);
+            CB_TSTAMP(7);
             if (blockIdx.x == 0) {
                 const int sign = (int)ctl[CT_SIGN];
                 const bool ok = v_ok && (sign == 1 || sign == 0);
@@ -433,6 +461,7 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
                 }
             }
             grid.sync();
+            CB_TSTAMP(8);
             {   // back-substitution, trial landmarks, landmark part of the scale term, trial chi2
                 const bool ok = ctl[CT_OK] != 0.0;
                 double sc = 0, acc = 0;
@@ -476,13 +505,16 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
                 if (tid == 0) { D.cta[8 * blockIdx.x + 3] = t1; D.cta[8 * blockIdx.x + 4] = t2; }
             }
             grid.sync();
+            CB_TSTAMP(9);
             if (blockIdx.x == 0) {
                 const double scl = cb_cta_column(D.cta, 3, n_cta, false, red), chn = cb_cta_column(D.cta, 4, n_cta, false, red);
                 double *slot = D.win[D.rank] + CB_FLAGS + (size_t)((D.seq[0] + 1) & 1) * D.xn;
                 if (tid == 0) { slot[0] = chn; slot[1] = scl; }
             }
             grid.sync();
+            CB_TSTAMP(10);
             if (!cb_exchange(D, grid, 2, -1, D.X2)) return;
+            CB_TSTAMP(11);
             if (gtid == 0) {
                 const bool ok = ctl[CT_OK] != 0.0;
                 const double tc = ok ? D.X2[0] : DBL_MAX;
@@ -496,12 +528,14 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
                 ctl[CT_TRIALS] += 1;
             }
             grid.sync();
+            CB_TSTAMP(12);
             rho = ctl[CT_RHO];
             if (ctl[CT_ACCEPT] != 0.0) {
                 for (int i = gtid; i < 7 * N; i += gsz) D.poses[i] = D.poseT[i];
                 for (int i = gtid; i < 3 * L; i += gsz) D.lms[i] = D.lmT[i];
             }
             grid.sync();
+            CB_TSTAMP(13);
             q++;
         } while (rho < 0 && q < 10);
         if (gtid == 0) ctl[CT_ITERS] += 1;
@@ -697,7 +731,7 @@ int svs_ba_shard_launch(svs_ctx *c, svs_ba_shard *sh, int max_iter)
     if (!c || !sh || max_iter < 0) return SVS_ERR_ARG;
     SVS_CUDA(c, cudaSetDevice(c->device));
     const int np = sh->d.np;
-    const size_t smem = ((size_t)CB_T + CL_SMEM_DOUBLES + np + 2) * 8 + (size_t)np * 4 + 16;
+    const size_t smem = ((size_t)CB_T + (np + 1 <= CB_T ? CL_SMALL_SMEM_DOUBLES(np) : (size_t)CL_SMEM_DOUBLES) + np + 2) * 8 + (size_t)np * 4 + 16;
     SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_bs_lm)));
     int per_sm = 0;
     SVS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bs_lm, CB_T, smem));
@@ -734,6 +768,18 @@ int svs_ba_shard_optimize(svs_ctx *c, svs_ba_shard *sh, int max_iter, svs_ba_sta
 {
     SVS_TRY(svs_ba_shard_launch(c, sh, max_iter));
     return svs_ba_shard_finish(c, sh, stats);
+}
+
+/* Nanoseconds the last svs_ba_shard_optimize spent per phase, measured inside the kernel with %globaltimer (diagnostics):
+ * 0 linearise | 1 Hpp/bp reduce | 2 V^-1, W V^-1 | 3 Schur chunks + g | 4 payload | 5 exchange | 6 permute | 7 LDLT + back-subst |
+ * 8 trial poses | 9 landmark back-subst + chi2 | 10 reduce | 11 exchange (2 doubles) | 12 accept test | 13 commit */
+int svs_ba_shard_phase_ns(svs_ctx *c, svs_ba_shard *sh, double out[16])
+{
+    if (!c || !sh || !out) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    SVS_CUDA(c, cudaMemcpyAsync(out, sh->d.ctl + CT_TIME, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SVS_OK;
 }
 
 int svs_ba_shard_get(svs_ctx *c, svs_ba_shard *sh, double *poses_out, double *lms_out, double *edge_chi2_out)

@@ -173,3 +173,118 @@ __device__ void coop_ldlt_solve(cooperative_groups::grid_group &grid, double *A,
     }
     grid.sync();
 }
+
+// Variant for systems with at most T - 1 unknowns (the sharded BA's 6N x 6N reduced system, N <= 85): the whole 32-column panel
+// (all rows below the diagonal block, one row per thread) is factorised by CTA 0 in shared memory with ONE block barrier per
+// column (the row owner divides by the pivot lazily, so a step only reads column kk of the other rows), which replaces the
+// warp-sequential diagonal block + the separate row pass of the general routine and one of its three barriers per panel.
+// Shared scratch: (n + 1) * (CL_PW + 1) + CL_PW + 2 * CL_TILE * (CL_PW + 1) doubles.
+#define CL_SMALL_SMEM_DOUBLES(n) ((size_t)((n) + 1) * (CL_PW + 1) + CL_PW + 2 * CL_TILE * (CL_PW + 1))
+template <int T>
+__device__ void coop_ldlt_solve_small(cooperative_groups::grid_group &grid, double *A, int n, int pitch, double *dvec, double *xs,
+                                      double *sign_io, double *sm, unsigned *sync_ctr, unsigned &gen)
+{
+    double *P = sm;                                        // [n + 1][CL_PW + 1]
+    double *ds = P + (size_t)(n + 1) * (CL_PW + 1);        // [CL_PW]
+    double *Li = ds + CL_PW, *Lj = Li + CL_TILE * (CL_PW + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nt0 = (n + 1 + CL_TILE - 1) / CL_TILE;
+    const unsigned n_part = (unsigned)min((int)gridDim.x, max(8, nt0 * (nt0 + 1) / 2));
+    if (blockIdx.x < n_part)
+    for (int k0 = 0; k0 < n; k0 += CL_PW) {
+        const int w = min(CL_PW, n - k0), k1 = k0 + w, rows = n + 1 - k0;
+        if (blockIdx.x == 0) {
+            for (int t = tid; t < rows * w; t += T) { const int i = t / w, c = t - i * w; P[i * (CL_PW + 1) + c] = A[(size_t)(k0 + i) * pitch + k0 + c]; }
+            __syncthreads();
+            int sign = (int)sign_io[0];
+            for (int kk = 0; kk < w; kk++) {
+                const double akk = P[kk * (CL_PW + 1) + kk];
+                if (k0 + kk == 0 && !(fabs(akk) > 0.0)) sign = 3;
+                if (sign == 1) { if (akk < 0) sign = 2; }
+                else if (sign == -1) { if (akk > 0) sign = 2; }
+                else if (sign == 0) { if (akk > 0) sign = 1; else if (akk < 0) sign = -1; }
+                const int i = kk + 1 + tid;
+                if (fabs(akk) > 0.0 && i < rows) {
+                    const double u = P[i * (CL_PW + 1) + kk] * (1.0 / akk);
+                    const int cmax = min(w - 1, i);
+                    for (int c = kk + 1; c <= cmax; c++) P[i * (CL_PW + 1) + c] -= u * P[c * (CL_PW + 1) + kk];
+                }
+                __syncthreads();
+            }
+            for (int t = tid; t < rows * w; t += T) {
+                const int i = t / w, c = t - i * w;
+                if (i < c) continue;
+                const double dk = P[c * (CL_PW + 1) + c];
+                if (i == c) dvec[k0 + c] = dk;
+                else A[(size_t)(k0 + i) * pitch + k0 + c] = (fabs(dk) > 0.0) ? P[i * (CL_PW + 1) + c] / dk : P[i * (CL_PW + 1) + c];
+            }
+            if (tid == 0) sign_io[0] = (double)sign;
+        }
+        coop_sub_sync(sync_ctr, n_part, gen);
+        {
+            const int m = n + 1 - k1;
+            if (m > 0 && k1 < n) {
+                for (int t = tid; t < w; t += T) ds[t] = dvec[k0 + t];
+                const int nt = (m + CL_TILE - 1) / CL_TILE;
+                const int n_tiles = nt * (nt + 1) / 2;
+                for (int tile = blockIdx.x; tile < n_tiles; tile += (int)n_part) {
+                    int ti = 0, rem = tile;
+                    while (rem > ti) { rem -= ti + 1; ti++; }
+                    const int tj = rem;
+                    const int i0 = k1 + ti * CL_TILE, j0 = k1 + tj * CL_TILE;
+                    __syncthreads();
+                    for (int t = tid; t < CL_TILE * CL_PW; t += T) {
+                        const int r = t / CL_PW, c = t - r * CL_PW;
+                        const int i = i0 + r, j = j0 + r;
+                        Li[r * (CL_PW + 1) + c] = (i <= n && c < w) ? A[(size_t)i * pitch + k0 + c] : 0.0;
+                        Lj[r * (CL_PW + 1) + c] = (j < n && c < w) ? A[(size_t)j * pitch + k0 + c] * ds[c] : 0.0;
+                    }
+                    __syncthreads();
+                    const int tr = (tid >> 5) * 4, tc = tid & 31;
+                    double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+#pragma unroll 8
+                    for (int c = 0; c < CL_PW; c++) {
+                        const double b0 = Lj[tc * (CL_PW + 1) + c], b1 = Lj[(tc + 32) * (CL_PW + 1) + c];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { const double a = Li[(tr + q) * (CL_PW + 1) + c]; acc[q][0] += a * b0; acc[q][1] += a * b1; }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int i = i0 + tr + q, j = j0 + tc + 32 * h;
+                            if (i <= n && j < n && j <= i) A[(size_t)i * pitch + j] -= acc[q][h];
+                        }
+                }
+            }
+        }
+        coop_sub_sync(sync_ctr, n_part, gen);
+    }
+    if (blockIdx.x == 0) {      // x = L^-T z with z = row n, blocks of 32 from the end
+        double *Ds = P;
+        for (int i = tid; i < n; i += T) { const double dk = dvec[i]; xs[i] = (fabs(dk) > DBL_MIN) ? A[(size_t)n * pitch + i] : 0.0; }
+        __syncthreads();
+        for (int b1 = n; b1 > 0; b1 -= CL_PW) {
+            const int b0 = max(0, b1 - CL_PW), w = b1 - b0;
+            for (int t = tid; t < w * w; t += T) { const int i = t / w, c = t - i * w; Ds[i * (CL_PW + 1) + c] = A[(size_t)(b0 + i) * pitch + b0 + c]; }
+            for (int t = tid; t < w; t += T) ds[t] = xs[b0 + t];
+            __syncthreads();
+            if (warp == 0) {
+                for (int i = w - 1; i >= 0; i--) {
+                    const double xi = ds[i];
+                    if (lane < i) ds[lane] -= Ds[i * (CL_PW + 1) + lane] * xi;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            for (int t = tid; t < w; t += T) xs[b0 + t] = ds[t];
+            for (int j = tid; j < b0; j += T) {
+                double s = 0;
+                for (int i = 0; i < w; i++) s += A[(size_t)(b0 + i) * pitch + j] * ds[i];
+                xs[j] -= s;
+            }
+            __syncthreads();
+        }
+    }
+    grid.sync();
+}

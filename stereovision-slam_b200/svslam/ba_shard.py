@@ -62,6 +62,14 @@ class Shard:
         self._imported.append(ptr.value)
         return ptr.value
 
+    PHASES = ("linearise", "hpp_reduce", "vinv_wd", "schur_chunks", "payload", "exchange", "permute", "ldlt", "trial_poses",
+              "backsubst_chi2", "reduce", "exchange2", "accept", "commit")
+
+    def phase_ns(self):
+        out = np.zeros(16)
+        self.ctx._chk(self.ctx.lib.svs_ba_shard_phase_ns(C.c_void_p(self.ctx.h), C.c_void_p(self.h), _p(out)))
+        return dict(zip(self.PHASES, out.tolist()))
+
     def get(self):
         poses = np.zeros((self.N, 7)); lms = np.zeros((self.L, 3)); chi2 = np.zeros(max(self.E, 1))
         self.ctx._chk(self.ctx.lib.svs_ba_shard_get(C.c_void_p(self.ctx.h), C.c_void_p(self.h), _p(poses), _p(lms), _p(chi2)))
