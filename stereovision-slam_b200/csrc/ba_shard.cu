@@ -41,7 +41,7 @@ namespace cg = cooperative_groups;
 // in-kernel phase clock (gtid 0, %globaltimer): nanoseconds accumulated per phase into ctl[CT_TIME + k]
 #define CB_TSTAMP(k) do { if (gtid == 0) { const unsigned long long now_ = cb_globaltimer(); ctl[CT_TIME + (k)] += (double)(now_ - t_prev); t_prev = now_; } } while (0)
 enum { CT_LAMBDA = 0, CT_NI, CT_CUR, CT_RHO, CT_ACCEPT, CT_OK, CT_SCALE_POSE, CT_ABORT, CT_CHI_INIT, CT_ITERS, CT_TRIALS, CT_STOP,
-       CT_LINS, CT_SIGN, CT_CUR_LOCAL, CT_TIME = 16, CT_COUNT = 32 };
+       CT_LINS, CT_SIGN, CT_CUR_LOCAL, CT_HB, CT_TIME = 16, CT_COUNT = 32 };
 
 struct CbDev {
     int N, L, E, G, nch, n_pitems, n_gitems, np, nbu, xn;
@@ -60,6 +60,8 @@ struct CbDev {
     double K[2][4], ext[2][7];
     double huber_delta;
     int jac_mode;
+    int bmax_local;                   // largest keyframe distance |i - j| over this shard's co-observing (pose, pose) blocks
+    int band_cap;                     // doubles of dynamic shared memory behind `red` (set per launch)
 };
 
 struct svs_ba_shard {
@@ -124,7 +126,7 @@ __device__ __forceinline__ double ld_relaxed_sys(const double *p)
 }
 
 // All ranks: own slot (seq & 1) holds `count` doubles (written by any CTA BEFORE the grid barrier the caller has just
-// passed).  Result: dst[i] = sum over ranks (max for i == max_idx) in rank order.  Returns false after a timeout.
+// passed).  Result: dst[i] = sum over ranks (max for i >= max_idx, when max_idx >= 0) in rank order.  Returns false after a timeout.
 __device__ bool cb_exchange(const CbDev &D, cg::grid_group &grid, int count, int max_idx, double *dst)
 {
     const unsigned long long seq = D.seq[0] + 1;
@@ -148,7 +150,7 @@ __device__ bool cb_exchange(const CbDev &D, cg::grid_group &grid, int count, int
             double acc = ld_relaxed_sys(D.win[0] + base + i);
             for (int p = 1; p < D.n_ranks; p++) {
                 const double v = ld_relaxed_sys(D.win[p] + base + i);
-                acc = (i == max_idx) ? fmax(acc, v) : acc + v;
+                acc = (max_idx >= 0 && i >= max_idx) ? fmax(acc, v) : acc + v;
             }
             dst[i] = acc;
         }
@@ -292,18 +294,23 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
             double *slot = D.win[D.rank] + CB_FLAGS + (size_t)((D.seq[0] + 1) & 1) * D.xn;
             if (it == 0) {
                 for (int i = tid; i < np; i += CB_T) slot[i] = D.Hpp[36 * (i / 6) + 7 * (i % 6)];
-                if (tid == 0) slot[np] = mh;
+                if (tid == 0) { slot[np] = mh; slot[np + 1] = (double)D.bmax_local; slot[np + 2] = -(double)D.band_cap; }
             }
             if (tid == 0) { ctl[CT_CUR_LOCAL] = cur; ctl[CT_LINS] += 1; }     // local chi2; the global one comes with the payload
         }
         grid.sync();
         CB_TSTAMP(1);
         if (it == 0) {      // lambda_init = tau * max diagonal over ALL vertices (global Hpp diagonal, every rank's Hll)
-            if (!cb_exchange(D, grid, np + 1, np, D.Xsum)) return;
+            if (!cb_exchange(D, grid, np + 3, np, D.Xsum)) return;
             if (gtid == 0) {
                 double md = D.Xsum[np];
                 for (int i = 0; i < np; i++) md = fmax(md, fabs(D.Xsum[i]));
                 ctl[CT_LAMBDA] = 1e-5 * md; ctl[CT_NI] = 2;
+                // scalar half bandwidth of S over ALL ranks' blocks; -1 (dense path) unless the band fits EVERY rank's
+                // shared memory, so that all ranks factor the same way and stay bit-identical replicas of each other
+                const int hb_all = min(np - 1, 6 * ((int)D.Xsum[np + 1] + 1) - 1);
+                const bool fits = hb_all >= 1 && hb_all <= 255 && CL_BAND_DOUBLES(np, hb_all) <= (size_t)(-D.Xsum[np + 2]);
+                ctl[CT_HB] = fits ? (double)hb_all : -1.0;
             }
             grid.sync();
         }
@@ -416,42 +423,68 @@ __global__ void __launch_bounds__(CB_T, 1) k_bs_lm(CbDev D, int max_iter)
             const double chi_cur = Xg[2 * np];
             const bool v_ok = Xg[2 * np + 1] == 0.0;
             const int pitch = np + 1;
-            // pivot order: diagonal sorted by decreasing magnitude (ties: lower index first), computed by every CTA
-            for (int i = tid; i < np; i += CB_T) {
-                const int a = i / 6, r = i - 6 * a;
-                sdiag[i] = fabs(XS[(size_t)ubk_id(a, a, N) * 36 + r * 7] + lambda);
+            // A window whose landmarks are seen by keyframes at most b apart has a block-banded S: when the band fits
+            // shared memory one CTA factors it in natural order (no fill outside the band, no grid barrier); otherwise the
+            // dense system goes through the grid-wide blocked LDL^T in Eigen's pivot order.  Same inertia test, same
+            // solution up to rounding (deviation from Eigen's elimination order for banded windows).
+            const int hb = (int)ctl[CT_HB];
+            const bool band = hb > 0;
+            if (band) {
+                if (blockIdx.x == 0) {
+                    double *Bb = sm_ldlt, *zb = Bb + (size_t)np * (hb + 1);
+                    const int w = hb + 1;
+                    for (int t = tid; t < np * w; t += CB_T) {
+                        const int r = t / w, d = t - r * w, c2 = r - d;
+                        double v = 0.0;
+                        if (c2 >= 0) {
+                            const int i = c2 / 6, j = r / 6;
+                            v = XS[(size_t)ubk_id(i, j, N) * 36 + (c2 - 6 * i) * 6 + (r - 6 * j)];
+                            if (d == 0) v += lambda;
+                        }
+                        Bb[t] = v;
+                    }
+                    for (int i = tid; i < np; i += CB_T) zb[i] = Xg[i];
+                    CB_TSTAMP(6);
+                    band_ldlt_solve_cta<CB_T>(Bb, zb, np, hb, D.xs, ctl + CT_SIGN);
+                }
+            } else {
+                // pivot order: diagonal sorted by decreasing magnitude (ties: lower index first), computed by every CTA
+                for (int i = tid; i < np; i += CB_T) {
+                    const int a = i / 6, r = i - 6 * a;
+                    sdiag[i] = fabs(XS[(size_t)ubk_id(a, a, N) * 36 + r * 7] + lambda);
+                }
+                __syncthreads();
+                for (int i = tid; i < np; i += CB_T) {
+                    const double di = sdiag[i];
+                    int r = 0;
+                    for (int j = 0; j < np; j++) { const double dj = sdiag[j]; r += (dj > di || (dj == di && j < i)) ? 1 : 0; }
+                    sperm[r] = i;
+                }
+                __syncthreads();
+                // permuted lower triangle + the right-hand side as row np
+                for (int t = gtid; t < (np + 1) * np; t += gsz) {
+                    const int a = t / np, b = t - a * np;
+                    if (a == np) { D.A[(size_t)a * pitch + b] = Xg[sperm[b]]; continue; }
+                    if (b > a) continue;
+                    const int r = sperm[a], c2 = sperm[b], i = r / 6, j = c2 / 6;
+                    double v = (i <= j) ? XS[(size_t)ubk_id(i, j, N) * 36 + (r - 6 * i) * 6 + (c2 - 6 * j)]
+                                        : XS[(size_t)ubk_id(j, i, N) * 36 + (c2 - 6 * j) * 6 + (r - 6 * i)];
+                    if (a == b) v += lambda;
+                    D.A[(size_t)a * pitch + b] = v;
+                }
+                if (gtid == 0) ctl[CT_SIGN] = 0;
+                grid.sync();
+                CB_TSTAMP(6);
+                // right-looking blocked LDL^T over the whole grid + back-substitution (coop_ldlt.cuh); solution in D.xs (permuted)
+                if (np + 1 <= CB_T) coop_ldlt_solve_small<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt, reinterpret_cast<unsigned *>(D.seq + 2), ldlt_gen);
+                else coop_ldlt_solve<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt, reinterpret_cast<unsigned *>(D.seq + 2), ldlt_gen);
             }
-            __syncthreads();
-            for (int i = tid; i < np; i += CB_T) {
-                const double di = sdiag[i];
-                int r = 0;
-                for (int j = 0; j < np; j++) { const double dj = sdiag[j]; r += (dj > di || (dj == di && j < i)) ? 1 : 0; }
-                sperm[r] = i;
-            }
-            __syncthreads();
-            // permuted lower triangle + the right-hand side as row np
-            for (int t = gtid; t < (np + 1) * np; t += gsz) {
-                const int a = t / np, b = t - a * np;
-                if (a == np) { D.A[(size_t)a * pitch + b] = Xg[sperm[b]]; continue; }
-                if (b > a) continue;
-                const int r = sperm[a], c2 = sperm[b], i = r / 6, j = c2 / 6;
-                double v = (i <= j) ? XS[(size_t)ubk_id(i, j, N) * 36 + (r - 6 * i) * 6 + (c2 - 6 * j)]
-                                    : XS[(size_t)ubk_id(j, i, N) * 36 + (c2 - 6 * j) * 6 + (r - 6 * i)];
-                if (a == b) v += lambda;
-                D.A[(size_t)a * pitch + b] = v;
-            }
-            if (gtid == 0) ctl[CT_SIGN] = 0;
-            grid.sync();
-            CB_TSTAMP(6);
-            // right-looking blocked LDL^T over the whole grid + back-substitution (coop_ldlt.cuh); solution in D.xs (permuted)
-            if (np + 1 <= CB_T) coop_ldlt_solve_small<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt, reinterpret_cast<unsigned *>(D.seq + 2), ldlt_gen);
-            else coop_ldlt_solve<CB_T>(grid, D.A, np, pitch, D.dvec, D.xs, ctl + CT_SIGN, sm_ldlt, reinterpret_cast<unsigned *>(D.seq + 2), ldlt_gen);
             CB_TSTAMP(7);
             if (blockIdx.x == 0) {
                 const int sign = (int)ctl[CT_SIGN];
                 const bool ok = v_ok && (sign == 1 || sign == 0);
                 const double *xs = D.xs;
-                for (int i = tid; i < np; i += CB_T) D.xp[sperm[i]] = ok ? xs[i] : 0.0;
+                for (int i = tid; i < np; i += CB_T) D.xp[band ? i : sperm[i]] = ok ? xs[i] : 0.0;
                 __syncthreads();
                 for (int a = tid; a < N; a += CB_T) gd::se3_oplus(D.poses + 7 * a, D.xp + 6 * a, D.poseT + 7 * a);
                 if (tid == 0) {
@@ -626,6 +659,8 @@ svs_ba_shard *svs_ba_shard_create(svs_ctx *c, int n_kf, const double *poses, int
         run += bcount[u + 1];
     }
     ubk_ch[nbu] = (int32_t)ch_off.size();
+    int bmax_local = 0;
+    for (int u = 0; u < nbu; u++) if (bcount[u + 1] > 0) bmax_local = std::max(bmax_local, ubk_j[u] - ubk_i[u]);
     const int nch = (int)ch_off.size();
     ch_off.push_back((int32_t)run);
     if (run > 0x7fffffffLL / 2) { c->err = "ba_shard: too many edge pairs for one shard"; return nullptr; }
@@ -670,7 +705,7 @@ svs_ba_shard *svs_ba_shard_create(svs_ctx *c, int n_kf, const double *poses, int
     cudaMemsetAsync(db + scratch0, 0, tot - scratch0, c->stream);
     cudaMemsetAsync(sh->window.p, 0, sh->window_bytes, c->stream);
     CbDev &d = sh->d;
-    d.N = N; d.L = L; d.E = E; d.G = G; d.nch = nch; d.n_pitems = (int)pitem_pose.size(); d.n_gitems = (int)gitem_pose.size(); d.np = np; d.nbu = nbu; d.xn = xn;
+    d.N = N; d.L = L; d.E = E; d.G = G; d.nch = nch; d.n_pitems = (int)pitem_pose.size(); d.n_gitems = (int)gitem_pose.size(); d.np = np; d.nbu = nbu; d.xn = xn; d.bmax_local = bmax_local; d.band_cap = 0;
     d.poses = (double *)(db + o_pose); d.poseT = (double *)(db + o_poseT); d.lms = (double *)(db + o_lm); d.lmT = (double *)(db + o_lmT);
     d.edge_p = (int32_t *)(db + o_ep); d.edge_l = (int32_t *)(db + o_el); d.edge_cam = db + o_ec; d.edge_uv = (double *)(db + o_uv);
     d.l_off = (int32_t *)(db + o_lo); d.l_edges = (int32_t *)(db + o_le); d.p_edges = (int32_t *)(db + o_pe);
@@ -731,8 +766,16 @@ int svs_ba_shard_launch(svs_ctx *c, svs_ba_shard *sh, int max_iter)
     if (!c || !sh || max_iter < 0) return SVS_ERR_ARG;
     SVS_CUDA(c, cudaSetDevice(c->device));
     const int np = sh->d.np;
-    const size_t smem = ((size_t)CB_T + (np + 1 <= CB_T ? CL_SMALL_SMEM_DOUBLES(np) : (size_t)CL_SMEM_DOUBLES) + np + 2) * 8 + (size_t)np * 4 + 16;
+    size_t smem = ((size_t)CB_T + (np + 1 <= CB_T ? CL_SMALL_SMEM_DOUBLES(np) : (size_t)CL_SMEM_DOUBLES) + np + 2) * 8 + (size_t)np * 4 + 16;
     SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_bs_lm)));
+    {   // room for the banded factorisation at THIS shard's bandwidth (landmark-sharded windows see the same bandwidth on
+        // every rank; the kernel takes the band path only when the global band fits every rank, see CT_HB)
+        cudaFuncAttributes fa;
+        SVS_CUDA(c, cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(k_bs_lm)));
+        const int hb = std::min(np - 1, 6 * (sh->d.bmax_local + 1) - 1);
+        const size_t want = ((size_t)CB_T + CL_BAND_DOUBLES(np, hb)) * 8 + 16;
+        if (want <= (size_t)fa.maxDynamicSharedSizeBytes) smem = std::max(smem, want);
+    }
     int per_sm = 0;
     SVS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bs_lm, CB_T, smem));
     if (per_sm < 1) SVS_FAIL(c, SVS_ERR_CAPACITY, "ba_shard: the cooperative solver does not fit an SM");
@@ -740,6 +783,7 @@ int svs_ba_shard_launch(svs_ctx *c, svs_ba_shard *sh, int max_iter)
     if (sh->grid_limit > 0) grid = std::min(grid, sh->grid_limit);
     grid = std::max(1, std::min(grid, 2048));
     CbDev d = sh->d;
+    d.band_cap = getenv("SVS_BS_DENSE") ? 0 : (int)(smem / 8) - CB_T - 2;
     void *args[] = {&d, &max_iter};
     svs_i_prof_begin(c, KID_BA_WINDOW);
     cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k_bs_lm), dim3(grid), dim3(CB_T), args, smem, c->stream);

@@ -288,3 +288,78 @@ __device__ void coop_ldlt_solve_small(cooperative_groups::grid_group &grid, doub
     }
     grid.sync();
 }
+
+// ------------------------------------------------------------------------------------------------ banded system, one CTA
+// A symmetric system whose entries vanish beyond `hb` sub-diagonals (the reduced camera system of a window in which a
+// landmark is seen by keyframes at most hb/6 apart) is factored IN NATURAL ORDER inside one CTA's shared memory: no fill
+// outside the band, n steps of <= hb (hb + 3) / 2 updates, one block barrier per step and no grid barrier at all.
+// Band storage: Bb[i * (hb + 1) + d] = A(i, i - d), d = 0 .. min(i, hb); z[i] = rhs; both are overwritten.  Behind z the
+// routine keeps the inverse pivots (n doubles) and the (a, b) item table (hb (hb + 3) / 2 words).  hb <= 255.
+// One SM issues 4 warp-instructions per clock, so the step is kept to ~10 instructions per update: every thread owns
+// the same (a, b) offsets in every step, the pivot's reciprocal is computed once (by the thread that finishes the next
+// pivot) and the triangular solves multiply by it.
+// On exit x[i] (shared or global) holds the solution and *sign_out Eigen's sign tracking as in coop_ldlt_solve.
+#define CL_BAND_DOUBLES(n, hb) ((size_t)(n) * ((hb) + 1) + 2 * (size_t)(n) + ((size_t)(hb) * ((hb) + 3) / 2 + 2) / 2 + 1)
+template <int T, bool DBG = false>
+__device__ void band_ldlt_solve_cta(double *Bb, double *z, int n, int hb, double *x, double *sign_out, long long *dbg = nullptr)
+{
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w = hb + 1, w1 = w + 1;
+    double *invd = z + n;
+    unsigned *tab = reinterpret_cast<unsigned *>(invd + n);
+    for (int a = 1 + warp; a <= hb; a += T / 32)
+        for (int b = lane; b <= a; b += 32) tab[a * (a + 1) / 2 - 1 + b] = (unsigned)a | ((unsigned)b << 16);
+    int sign = 0;
+    auto pivot = [&](int k, double d) {       // thread 1 only: sign tracking + reciprocal of pivot k
+        if (k == 0 && !(fabs(d) > 0.0)) sign = 3;
+        if (sign == 1) { if (d < 0) sign = 2; }
+        else if (sign == -1) { if (d > 0) sign = 2; }
+        else if (sign == 0) { if (d > 0) sign = 1; else if (d < 0) sign = -1; }
+        invd[k] = (fabs(d) > DBL_MIN) ? 1.0 / d : 0.0;
+    };
+    if (tid == 1) pivot(0, Bb[0]);
+    for (int k = 0; k < n; k++) {
+        if (DBG) c0 = clock64();
+        __syncthreads();
+        if (DBG) c1 = clock64();
+        const double inv = invd[k];
+        const int m = min(hb, n - 1 - k);
+        double *base = Bb + (size_t)k * w;
+        if (DBG) { if (inv == 12345.0) c2 = 0; c2 = clock64(); }
+        if (inv != 0.0 && m > 0) {
+            const double zs = z[k] * inv;
+            const int cnt = m * (m + 3) / 2;
+            for (int t = tid; t < cnt; t += T) {
+                const unsigned ab = tab[t];
+                const int a = (int)(ab & 0xffffu), b = (int)(ab >> 16);
+                const double ua = base[a * w1];
+                if (b == 0) z[k + a] -= ua * zs;
+                else {
+                    const double v = base[a * w1 - b] - ua * (base[b * w1] * inv);
+                    base[a * w1 - b] = v;
+                    if (DBG && t == 1) c3 = clock64();
+                    if (t == 1) pivot(k + 1, v);
+                }
+            }
+        } else if (tid == 1 && k + 1 < n) pivot(k + 1, base[w]);
+        if (DBG) { const long long c4 = clock64(); acc0 += c1 - c0; acc1 += c2 - c1; acc2 += c3 - c2; acc3 += c4 - c3; }
+    }
+    if (DBG && tid == 1) { dbg[0] = acc0; dbg[1] = acc1; dbg[2] = acc2; dbg[3] = acc3; }
+    __syncthreads();
+    // z = D^-1 y, then x = L^-T z column by column from the last row up (one warp, no reductions)
+    for (int i = tid; i < n; i += T) z[i] *= invd[i];
+    __syncthreads();
+    if (warp == 0) {
+        for (int k = n - 1; k >= 1; k--) {
+            __syncwarp();
+            const double xk = z[k];
+            const int m = min(hb, k);
+            for (int a = 1 + lane; a <= m; a += 32) z[k - a] -= Bb[(size_t)k * w + a] * invd[k - a] * xk;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += T) x[i] = z[i];
+    if (tid == 1) sign_out[0] = (double)sign;
+    __syncthreads();
+}
