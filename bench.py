@@ -62,6 +62,27 @@ CONFIGS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Libraries (NCCL's version banner) print to fd 1; the contract is ONE JSON line there.  Route fd 1 to stderr and keep
+    the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def log(*a):
     if os.environ.get("SVS_BENCH_VERBOSE", "1") != "0":
         print("[bench %.1fs]" % (time.perf_counter() - _T0), *a, file=sys.stderr, flush=True)
@@ -317,7 +338,7 @@ def run_reference(args, rank, world):
                          "sample": cpu_sample_text(cores, n, args.steps, spec, int(np.median(cs.window)))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def cpu_baseline_subprocess(clip_path, cid, frames, timeout=300):
@@ -417,6 +438,8 @@ class Rig:
         self.ctxs = [svslam.Context(dev) for _ in range(self.G)]   # raises if libsvslam.so / a B200 is missing: no fallback
         self.lib = self.ctxs[0].lib
         self.lib.svs_kernel_name.restype = C.c_char_p
+        for c in self.ctxs:
+            c.set_wait_mode(1 if getattr(args, "wait_block", False) else 0)
         self.gsz = [streams // self.G + (1 if g < streams % self.G else 0) for g in range(self.G)]
         self.goff = np.concatenate([[0], np.cumsum(self.gsz)]).astype(int)
         K = cor.K_half() if spec["half"] else cor.K_full()
@@ -506,10 +529,12 @@ class Rig:
         if profile_window:     # `ncu --profile-from-start off`: only the steady-state steps below are captured
             torch.cuda.profiler.start()
         t0 = time.perf_counter()
+        cpu0 = time.process_time()
         e0.record()
         self.run_steps(steps, on_device)
         torch.cuda.synchronize(self.dev)
         e1.record()
+        cpu_s = time.process_time() - cpu0      # user + system time of every thread of this rank over the timed steps
         if profile_window:
             torch.cuda.profiler.stop()
         e1.synchronize()
@@ -539,7 +564,7 @@ class Rig:
         phases.update({"ba:host_build": bh1[0] - bh0[0], "ba:pack_enqueue": bh1[1] - bh0[1], "ba:device_wait_unpack": bh1[2] - bh0[2]})
         counts = {k: sum(c1[1][k] - c0[1][k] for c0, c1 in zip(cn0, cn1)) for k in cn1[0][1]}
         log("region (on_device=%s, instrumented=%s): %.2f ms/step" % (on_device, timing, ms / steps))
-        return dict(ms=ms, wall=wall, launches=launches, phases=phases, counts=counts, kern=kern, lost=lost)
+        return dict(ms=ms, wall=wall, launches=launches, phases=phases, counts=counts, kern=kern, lost=lost, cpu_s=cpu_s)
 
     def close(self):
         for s in self.slams:
@@ -821,6 +846,9 @@ def build_report(args, world, B, G, cor, spec, dev_pass, e2e_pass, kern_pass, cl
                    "kernel_time_share": shares, "kernel_roofline": kr, "kernel_pass_ms_per_step": kern_pass["ms"] / args.steps,
                    "summed_kernel_ms_over_wall_ms": dev_total / kern_pass["ms"] if kern_pass["ms"] else None,
                    "lost_streams": dev_pass["lost"], "host_cores": cores, "host_cores_this_rank": my_cores, "host_threads_per_group": host_threads,
+                   "host_wait_mode": "block" if getattr(args, "wait_block", False) else "spin",
+                   "host_cpu_ms_per_step": {"value": round(1e3 * dev_pass.get("cpu_s", 0.0) / args.steps, 2), "e2e": round(1e3 * e2e_pass.get("cpu_s", 0.0) / args.steps, 2),
+                                            "note": "user + system time of every thread of rank 0 per timed step (spinning waits count as busy)"},
                    "ba_lm_iterations_per_sec": dev_pass["counts"]["ba_iterations"] * world / (dev_pass["ms"] * 1e-3),
                    "accuracy": ate, "ba_config4": ba4, "latency": lat, **detail_cfg},
     }
@@ -846,6 +874,8 @@ def run_gpu(args, rank, world, local_rank):
     my_cores = max(1, cores // max(1, local_world))
     G = max(1, min(args.groups, args.streams, my_cores))
     host_threads = max(1, my_cores // G)
+    # host wait policy: with few cores per rank the pipeline threads sleep on a blocking-sync event instead of spinning
+    args.wait_block = (args.wait_mode == "block") or (args.wait_mode == "auto" and my_cores < 4 * G)
     spec = CONFIGS[2]
     log("rendering clip ...")
     clip = make_clip(spec["calib"], args.clip_frames)
@@ -957,7 +987,7 @@ def run_gpu(args, rank, world, local_rank):
 
     out = build_report(args, world, B, G, cor, spec, dev_pass, e2e_pass, kern_pass, clocks, peak, peak_src, traffic, cpu, ate, ba4, lat,
                        detail_cfg, distinct, V, cores, my_cores, host_threads, len(L))
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -980,6 +1010,9 @@ def main():
     ap.add_argument("--eager-right", action="store_true",
                     help="ingest the right image of every frame (default: only for the streams that insert a keyframe in the step)")
     ap.add_argument("--host-tracking", action="store_true", help="device_tracking = 0: every seam of Track() is a host round trip (round-1 path)")
+    ap.add_argument("--wait-mode", default="auto", choices=["auto", "spin", "block"],
+                    help="host wait policy (svs_set_wait_mode): spin = cudaStreamSynchronize, block = blocking-sync event, auto = block when "
+                         "this rank has fewer than 4 cores per context group")
     ap.add_argument("--no-prefetch", action="store_true", help="disable the double-buffered ingest (svs_slam_hint_next)")
     ap.add_argument("--cpu-frames", type=int, default=0,
                     help="frames per stream per step of the CPU arms (0 = automatic)")
@@ -1015,6 +1048,7 @@ def main():
                           "sample": cpu_sample_text(cores, n, 1, spec, int(np.median(cs.window))) +
                                     "; one core alone: %.1f frames/s" % fps1}))
         return
+    guard_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -44,7 +44,11 @@ SVS_API const char *svs_create_error(void);
 SVS_API void svs_destroy(svs_ctx *ctx);
 SVS_API const char *svs_last_error(svs_ctx *ctx);
 SVS_API int svs_version(void);
-SVS_API int svs_sync(svs_ctx *ctx);                       /* cudaStreamSynchronize on the context stream */
+SVS_API int svs_sync(svs_ctx *ctx);                       /* wait for the context stream (by the wait mode below) */
+/* Host wait policy of every blocking call on this context: 0 (default) = cudaStreamSynchronize, the driver spins on the
+ * stream (lowest wake-up latency, one busy core per waiting host thread); 1 = the thread sleeps on a blocking-sync event
+ * (for hosts with fewer cores than waiting threads, e.g. 8 ranks x 2 contexts on a 32-core box).  Results are identical. */
+SVS_API int svs_set_wait_mode(svs_ctx *ctx, int mode);
 SVS_API void *svs_stream(svs_ctx *ctx);                   /* the cudaStream_t, for event timing */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 SVS_API long long svs_launch_count(svs_ctx *ctx);

@@ -142,8 +142,22 @@ svs_ctx *svs_create(int device)
         delete c;
         return nullptr;
     }
+    if (const char *z = getenv("SVS_WAIT_MODE")) c->wait_mode = atoi(z) == 1 ? 1 : 0;
+    if ((e = cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return nullptr;
+    }
     g_live_ctx++;
     return c;
+}
+
+int svs_set_wait_mode(svs_ctx *c, int mode)
+{
+    if (!c || (mode != 0 && mode != 1)) return SVS_ERR_ARG;
+    c->wait_mode = mode;
+    return SVS_OK;
 }
 
 void svs_destroy(svs_ctx *c)
@@ -158,12 +172,13 @@ void svs_destroy(svs_ctx *c)
     c->h_in.release(); c->h_out.release();
     cudaStreamDestroy(c->stream);
     if (c->stream_in) cudaStreamDestroy(c->stream_in);
+    if (c->ev_wait) cudaEventDestroy(c->ev_wait);
     { std::lock_guard<std::mutex> lk(g_mutex); g_live_ctx--; }
     delete c;
 }
 
 const char *svs_last_error(svs_ctx *c) { return c ? c->err.c_str() : "null context"; }
-int svs_sync(svs_ctx *c) { SVS_CUDA(c, cudaStreamSynchronize(c->stream)); if (c->prof_pending.size() > 4096) prof_harvest(c); return SVS_OK; }
+int svs_sync(svs_ctx *c) { SVS_CUDA(c, svs_i_wait(c)); if (c->prof_pending.size() > 4096) prof_harvest(c); return SVS_OK; }
 void *svs_stream(svs_ctx *c) { return (void *)c->stream; }
 long long svs_launch_count(svs_ctx *c) { return c->launches; }
 void *svs_host_alloc(size_t bytes) { void *p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }
@@ -318,7 +333,7 @@ static int frameset_ingest_ptrs(svs_ctx *c, svs_frameset *fs, const PyrDesc &Lc,
     SVS_CUDA(c, ptr_table.reserve(ptr_b + ids_b + 16));
     SVS_CUDA(c, ptr_table_h.reserve(ptr_b + ids_b + 16));
     // the previous table copy must have been consumed before the pinned table is overwritten
-    if (table_may_be_in_flight) SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (table_may_be_in_flight) SVS_CUDA(c, svs_i_wait(c));
     const uint8_t **hp = ptr_table_h.as<const uint8_t *>();
     int aligned4 = 1;
     for (int b = 0; b < n_img; b++) {
@@ -429,7 +444,7 @@ int svs_frameset_download(svs_ctx *c, svs_frameset *fs, int stream, int which, i
     const PyrDesc &d = which == 0 ? fs->Lcur() : which == 1 ? fs->Lprev() : fs->Rcur();
     SVS_CUDA(c, cudaMemcpy2DAsync(out, out_stride, d.base + (size_t)stream * d.img_pitch + d.off[level], d.stride[level],
                                   d.w[level], d.h[level], cudaMemcpyDeviceToHost, c->stream));
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     return SVS_OK;
 }
 
@@ -445,7 +460,7 @@ int svs_half_nearest(svs_ctx *c, const uint8_t *src, int w, int h, int stride, i
     SVS_CUDA(c, cudaMemcpyAsync(c->d_in.p, src, in_bytes, cudaMemcpyHostToDevice, c->stream));
     SVS_TRY(svs_i_half_nearest(c, c->d_in.as<uint8_t>(), w, h, stride, img_stride, n, c->d_out.as<uint8_t>(), dw, dh, dw, (size_t)dw * dh));
     SVS_CUDA(c, cudaMemcpyAsync(dst, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     return SVS_OK;
 }
 
@@ -489,7 +504,7 @@ static int gftt_common(svs_ctx *c, const uint8_t *img_dev, int w, int h, int str
     SVS_CUDA(c, cudaMemcpyAsync(hob, dob, oxy_b + orp_b + on_b, cudaMemcpyDeviceToHost, c->stream));
     int *ovf = reinterpret_cast<int *>(hob + align_up(oxy_b + orp_b + on_b, 4));
     SVS_TRY(svs_i_gftt_overflow(c, n_img, ovf));
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     if (*ovf) SVS_FAIL(c, SVS_ERR_CAPACITY, "gftt: more local-maximum candidates than the candidate buffer holds (w*h/4)");
     memcpy(out_xy, hob, oxy_b);
     if (out_resp) memcpy(out_resp, hob + oxy_b, orp_b);
@@ -526,7 +541,7 @@ int svs_corner_min_eig(svs_ctx *c, const uint8_t *img, int w, int h, int stride,
     SVS_TRY(svs_i_gftt(c, c->d_in.as<uint8_t>(), w, h, dstride, 0, 1, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.01, 1.0,
                        granule, nullptr, nullptr, nullptr, c->d_out2.as<float>()));
     SVS_CUDA(c, cudaMemcpyAsync(out, c->d_out2.p, (size_t)w * h * 4, cudaMemcpyDeviceToHost, c->stream));
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     return SVS_OK;
 }
 
@@ -567,7 +582,7 @@ static int lk_common(svs_ctx *c, const PyrDesc &prev, const PyrDesc &next, int n
     uint8_t *ho = c->h_out.as<uint8_t>();
     SVS_CUDA(c, cudaMemcpyAsync(ho, nxt_dev, xy_b, cudaMemcpyDeviceToHost, c->stream));
     SVS_CUDA(c, cudaMemcpyAsync(ho + xy_b, c->d_out.p, n, cudaMemcpyDeviceToHost, c->stream));
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     memcpy(next_xy, ho, xy_b);
     memcpy(status, ho + xy_b, n);
     return SVS_OK;

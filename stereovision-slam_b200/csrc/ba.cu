@@ -710,7 +710,7 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     SVS_CUDA(c, cudaMemcpyAsync(ho + ho_pose, A.poses, (size_t)sumN * 56, cudaMemcpyDeviceToHost, c->stream));
     if (sumL) SVS_CUDA(c, cudaMemcpyAsync(ho + ho_lm, A.lms, (size_t)sumL * 24, cudaMemcpyDeviceToHost, c->stream));
     const double t_queued = now_s();
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     if (sumE) memcpy(edge_chi2_out, ho, (size_t)sumE * 8);
     if (stats) memcpy(stats, ho + (size_t)sumE * 8, (size_t)n_prob * sizeof(svs_ba_stats));
     memcpy(poses, ho + ho_pose, (size_t)sumN * 56);

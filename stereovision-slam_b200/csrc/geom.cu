@@ -400,7 +400,7 @@ int svs_triangulate(svs_ctx *c, const float *left_xy, const float *right_xy, int
                                                           Kl[0], Kl[1], Kl[2], Kl[3], Kr[0], Kr[1], Kr[2], Kr[3], baseline,
                                                           reinterpret_cast<double *>(dob), dob + o_b));
     SVS_CUDA(c, cudaMemcpyAsync(c->h_out.p, dob, o_b + n, cudaMemcpyDeviceToHost, c->stream));
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     memcpy(out_xyz, c->h_out.p, o_b);
     memcpy(out_ok, c->h_out.as<uint8_t>() + o_b, n);
     return SVS_OK;
@@ -437,7 +437,7 @@ int svs_pose_only_lm(svs_ctx *c, int n_prob, const int32_t *off, const double *p
         iters, reinterpret_cast<double *>(dob), dob + t_b + st_b + ni_b, reinterpret_cast<int32_t *>(dob + t_b + st_b),
         reinterpret_cast<svs_lm_stats *>(dob + t_b), nullptr));
     SVS_CUDA(c, cudaMemcpyAsync(c->h_out.p, dob, out_b, cudaMemcpyDeviceToHost, c->stream));
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     uint8_t *ho = c->h_out.as<uint8_t>();
     memcpy(T_out, ho, t_b);
     if (stats) memcpy(stats, ho + t_b, st_b);

@@ -73,6 +73,10 @@ struct svs_ctx {
     int device = 0;
     int sm_count = 0;
     int host_threads = 0;   // OpenMP team size for host-side problem construction in this context's calls (0 = OpenMP's default)
+    // Host wait policy: 0 = cudaStreamSynchronize (the driver spins: lowest latency, one busy core per waiting thread),
+    // 1 = record + wait on a cudaEventBlockingSync event (the thread sleeps: for boxes with fewer cores than waiting threads)
+    int wait_mode = 0;
+    cudaEvent_t ev_wait = nullptr;
     int zc_ctas = 0;    // persistent grid of the zero-copy (PCIe) ingest kernel: 0 = automatic (svs_i_zc_grid), env SVS_ZC_CTAS overrides
     cudaStream_t stream = nullptr;
     cudaStream_t stream_in = nullptr;   // ingest stream: prefetch of the NEXT frame pair overlaps this step's compute
@@ -122,6 +126,14 @@ struct svs_frameset {
     PinBuf pf_ptr_table_h;
     long long prefetch_hits = 0, prefetch_misses = 0;
 };
+
+// wait for everything enqueued on the context stream, by the context's wait policy
+inline cudaError_t svs_i_wait(svs_ctx *c)
+{
+    if (c->wait_mode == 0 || !c->ev_wait) return cudaStreamSynchronize(c->stream);
+    cudaError_t e = cudaEventRecord(c->ev_wait, c->stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_wait);
+}
 
 #define SVS_CUDA(ctx, call)                                                              \
     do {                                                                                 \

@@ -277,7 +277,7 @@ int svs_i_trk_step(svs_ctx *c, svs_tracker *t, svs_frameset *fs, long long *lk_p
                                    t->d.outl, t->d.n_inl));
     SVS_KERNEL(c, KID_TRACK_STATE, k_trk_end<<<grid, TRK_WARPS * 32, 0, c->stream>>>(t->d, p.num_features_tracking, p.num_features_tracking_bad,
                                                                                    p.num_features_needed_for_keyframe));
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     long long edges = 0;
     const TrkOut *o = t->d.out;
     for (int b = 0; b < B; b++) {
@@ -299,7 +299,7 @@ int svs_i_trk_upload(svs_ctx *c, svs_tracker *t, int n_sel, const TrkUpHdr *hdrs
     }
     const size_t hb = align_up((size_t)n_sel * sizeof(TrkUpHdr), 256), fb = (size_t)n_feats * sizeof(TrkUpFeat);
     SVS_CUDA(c, cudaEventSynchronize(t->up_done));      // the previous upload has left the pinned staging buffer
-    if (hb + fb + 16 > t->up_dev.cap) SVS_CUDA(c, cudaStreamSynchronize(c->stream));   // regrow frees a buffer the scatter kernel may still read
+    if (hb + fb + 16 > t->up_dev.cap) SVS_CUDA(c, svs_i_wait(c));   // regrow frees a buffer the scatter kernel may still read
     SVS_CUDA(c, t->up_h.reserve(hb + fb + 16));
     SVS_CUDA(c, t->up_dev.reserve(hb + fb + 16));
     uint8_t *h = t->up_h.as<uint8_t>(), *dv = t->up_dev.as<uint8_t>();
@@ -318,7 +318,7 @@ int svs_i_trk_fetch(svs_ctx *c, svs_tracker *t, int stream, const TrkFeat **feat
     if (stream < 0 || stream >= t->p.B) return SVS_ERR_ARG;
     SVS_CUDA(c, cudaSetDevice(c->device));
     SVS_KERNEL(c, KID_TRACK_STATE, k_trk_export<<<1, 128, 0, c->stream>>>(t->d, stream));
-    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVS_CUDA(c, svs_i_wait(c));
     *feats = t->d.kf_feats + (size_t)stream * t->p.cap;
     *n = t->d.out[stream].nfeat;
     return SVS_OK;

@@ -165,6 +165,10 @@ class Context:
     def sync(self):
         self._chk(self.lib.svs_sync(C.c_void_p(self.h)))
 
+    def set_wait_mode(self, mode):
+        """0: blocking calls spin on the stream (default); 1: they sleep on a blocking-sync event (svs_set_wait_mode)."""
+        self._chk(self.lib.svs_set_wait_mode(C.c_void_p(self.h), int(mode)))
+
     def stream_ptr(self):
         return self.lib.svs_stream(C.c_void_p(self.h))
 
