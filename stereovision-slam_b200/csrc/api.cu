@@ -105,7 +105,7 @@ const char *svs_kernel_name(int kid)
 {
     static const char *names[KID_COUNT] = {"k_half_nearest", "k_copy2d", "k_pyr_down", "k_mask_boxes", "k_corner_response",
                                            "k_corner_select", "k_corner_greedy", "k_lk_track", "k_triangulate", "k_pose_only_lm",
-                                           "k_ba_window", "k_bm_prefilter", "k_bm_sad", "k_backproject", "k_bgr2gray", "misc", "k_trk_state"};
+                                           "k_ba_window", "k_bm_prefilter", "k_bm_sad", "k_backproject", "k_bgr2gray", "misc", "k_trk_state", "k_ba_build"};
     return (kid >= 0 && kid < KID_COUNT) ? names[kid] : "";
 }
 const char *svs_create_error(void) { return g_create_err.c_str(); }
@@ -167,9 +167,10 @@ void svs_destroy(svs_ctx *c)
     cudaStreamSynchronize(c->stream);
     prof_harvest(c);
     for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
-    DevBuf *d[] = {&c->d_in, &c->d_in2, &c->d_out, &c->d_out2, &c->d_tmp, &c->d_tmp2, &c->d_tmp3, &c->d_tmp4, &c->d_tmp5, &c->d_tmp6, &c->d_tmp7};
+    DevBuf *d[] = {&c->d_in, &c->d_in2, &c->d_out, &c->d_out2, &c->d_tmp, &c->d_tmp2, &c->d_tmp3, &c->d_tmp4, &c->d_tmp5, &c->d_tmp6, &c->d_tmp7, &c->d_tmp8};
     for (DevBuf *b : d) b->release();
     c->h_in.release(); c->h_out.release();
+    svs_i_ba_ws_free(c->ba_ws); c->ba_ws = nullptr;
     cudaStreamDestroy(c->stream);
     if (c->stream_in) cudaStreamDestroy(c->stream_in);
     if (c->ev_wait) cudaEventDestroy(c->ev_wait);

@@ -465,7 +465,211 @@ k_ba_window(BaArgs A)
     }
 }
 
+
 // ---------------------------------------------------------------------------------------------
+// Window structure on the device.  The lists k_ba_window walks (active poses, edges by pose, (landmark, pose) groups by
+// landmark and by pose, (group, group) pairs per 6x6 block cut into chunks) used to be built by the host for every window
+// of every step (0.3 ms of one core per window: the largest host cost of a keyframe).  One CTA per window builds the SAME
+// lists from the raw edge arrays, for the edge order the pipeline emits: landmark-major, keyframe-ascending inside a
+// landmark (svs_ba_optimize checks this and keeps the host construction for any other order).  Every step is a stable
+// counting sort or a prefix sum whose result does not depend on the thread schedule, so the lists — and with them the
+// summation order of k_ba_window — are identical to the host construction's.
+//   * a window has <= 32 keyframes here, so a landmark's keyframes are a 32-bit mask; the pairs of block (i, j) are the
+//     landmarks whose mask has bits i and j, in landmark order: ballots + popcounts, no sort
+//   * the lists are laid out per window at offsets the host derives from UPPER BOUNDS (groups <= E, pairs <= E (N + 1) / 2,
+//     chunks <= pairs / BA_CH + blocks), so no size has to travel back to the host before k_ba_window is launched
+#define BB_T 512
+struct BaBuildArgs {
+    BaProb *probs;
+    const int32_t *edge_kf, *edge_lm;
+    int32_t *act_pose, *edge_p, *l_off, *l_edges, *p_off, *p_edges;
+    int32_t *blk_i, *blk_j, *blk_ch, *pr_e1, *pr_e2, *ch_blk, *ch_off;
+    int32_t *lg_off, *g_lm, *g_pose, *pg_off, *pg_groups;
+    uint32_t *lm_mask;
+};
+
+// stable counting sort of n elements by key(e) in [0, NA), NA <= 32: off_out[0 .. NA] = bucket offsets, list_out = element
+// indices bucket by bucket, ascending inside a bucket.  Warp w owns a contiguous range; lane a carries bucket a's counters.
+template <class KeyF>
+__device__ void bb_bucket_sort(KeyF key, int n, int NA, int32_t *off_out, int32_t *list_out, int (*wcnt)[32], int *s_off)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = BB_T / 32;
+    const int per = ((n + NW - 1) / NW + 31) & ~31;
+    const int lo = min(n, warp * per), hi = min(n, lo + per);
+    int cnt = 0;
+    for (int e0 = lo; e0 < hi; e0 += 32) {
+        const int e = e0 + lane;
+        const int k = e < hi ? key(e) : -1;
+        for (int a = 0; a < NA; a++) { const unsigned bal = __ballot_sync(0xffffffffu, k == a); if (lane == a) cnt += __popc(bal); }
+    }
+    wcnt[warp][lane] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        int tot = 0;
+        for (int w = 0; w < NW; w++) tot += wcnt[w][lane];
+        if (lane >= NA) tot = 0;
+        int incl = tot;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        s_off[lane] = incl - tot;
+        if (lane == 31) s_off[32] = incl;
+    }
+    __syncthreads();
+    if (tid <= NA) off_out[tid] = s_off[tid];
+    int base = s_off[lane];
+    for (int w = 0; w < warp; w++) base += wcnt[w][lane];
+    for (int e0 = lo; e0 < hi; e0 += 32) {
+        const int e = e0 + lane;
+        const int k = e < hi ? key(e) : -1;
+        for (int a = 0; a < NA; a++) {
+            const unsigned bal = __ballot_sync(0xffffffffu, k == a);
+            const int ba = __shfl_sync(0xffffffffu, base, a);
+            if (k == a) list_out[ba + __popc(bal & ((1u << lane) - 1u))] = e;
+            if (lane == a) base += __popc(bal);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(BB_T) k_ba_build(BaBuildArgs B)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = BB_T / 32;
+    BaProb P = B.probs[blockIdx.x];
+    const int N = P.NA /* keyframes of the window on entry */, L = P.L, E = P.E;
+    const int32_t *ekf = B.edge_kf + P.e0, *elm = B.edge_lm + P.e0;
+    int32_t *edge_p = B.edge_p + P.e0, *l_edges = B.l_edges + P.e0, *p_edges = B.p_edges + P.e0;
+    int32_t *l_off = B.l_off + P.loff0, *p_off = B.p_off + P.poff0, *lg_off = B.lg_off + P.lgoff0, *pg_off = B.pg_off + P.pgoff0;
+    int32_t *g_lm = B.g_lm + P.grp0, *g_pose = B.g_pose + P.grp0, *pg_groups = B.pg_groups + P.grp0;
+    uint32_t *mask = B.lm_mask + P.lm0;
+    __shared__ unsigned s_act;
+    __shared__ int s_wsum[BB_T / 32], s_base, s_off[33], s_wcnt[BB_T / 32][32];
+    __shared__ int s_bcnt[528], s_bstart[528], s_bch[528], s_bidx[528], s_tot[3];
+    // ---- active poses
+    if (tid == 0) { s_act = 0; s_base = 0; }
+    for (int l = tid; l < L; l += BB_T) mask[l] = 0;
+    __syncthreads();
+    {
+        unsigned act = 0;
+        for (int e = tid; e < E; e += BB_T) act |= 1u << ekf[e];
+        act = __reduce_or_sync(0xffffffffu, act);
+        if (lane == 0 && act) atomicOr(&s_act, act);
+    }
+    __syncthreads();
+    const unsigned act = s_act;
+    const int NA = __popc(act);
+    if (tid < N && ((act >> tid) & 1u)) B.act_pose[P.act0 + __popc(act & ((1u << tid) - 1u))] = tid;
+    auto pidx = [act](int k) { return __popc(act & ((1u << k) - 1u)); };
+    for (int e = tid; e < E; e += BB_T) { edge_p[e] = pidx(ekf[e]); l_edges[e] = e; }
+    // ---- groups = runs of equal (landmark, pose) in the sorted edge list; CSR of edges and groups by landmark; pose masks
+    for (int t0 = 0; t0 < E; t0 += BB_T) {
+        const int e = t0 + tid;
+        int flag = 0, l = -1, pp = -1, lp = -1;
+        if (e < E) {
+            l = elm[e]; pp = pidx(ekf[e]);
+            if (e == 0) flag = 1;
+            else { lp = elm[e - 1]; flag = (lp != l || pidx(ekf[e - 1]) != pp) ? 1 : 0; }
+        }
+        int incl = flag;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int wbase = s_base;
+        for (int w = 0; w < warp; w++) wbase += s_wsum[w];
+        const int gid = wbase + incl - 1;
+        if (flag) {
+            g_lm[gid] = l; g_pose[gid] = pp;
+            atomicOr(&mask[l], 1u << pp);
+            if (lp != l) for (int ll = lp + 1; ll <= l; ll++) { lg_off[ll] = gid; l_off[ll] = e; }
+        }
+        __syncthreads();
+        if (tid == 0) { int tot = s_base; for (int w = 0; w < NW; w++) tot += s_wsum[w]; s_base = tot; }
+        __syncthreads();
+    }
+    const int G = s_base;
+    {
+        const int last = E > 0 ? elm[E - 1] : -1;
+        for (int ll = last + 1 + tid; ll <= L; ll += BB_T) { lg_off[ll] = G; l_off[ll] = E; }
+    }
+    __syncthreads();
+    // ---- edges by pose, groups by pose (stable)
+    bb_bucket_sort([edge_p](int e) { return edge_p[e]; }, E, NA, p_off, p_edges, s_wcnt, s_off);
+    bb_bucket_sort([g_pose](int g) { return g_pose[g]; }, G, NA, pg_off, pg_groups, s_wcnt, s_off);
+    // ---- pairs per upper block (i <= j): the landmarks seen from both poses, in landmark order
+    const int NB = NA * (NA + 1) / 2;
+    for (int q = warp; q < NB; q += NW) {
+        int i = 0, r = q;
+        while (r >= NA - i) { r -= NA - i; i++; }
+        const int j = i + r;
+        const unsigned need = (1u << i) | (1u << j);
+        int cnt = 0;
+        for (int l0 = 0; l0 < L; l0 += 32) {
+            const int l = l0 + lane;
+            const unsigned m = l < L ? mask[l] : 0u;
+            cnt += __popc(__ballot_sync(0xffffffffu, (m & need) == need));
+        }
+        if (lane == 0) s_bcnt[q] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0, nch = 0, nblk = 0, q = 0;
+        for (int i = 0; i < NA; i++)
+            for (int j = i; j < NA; j++, q++) {
+                const int cn = s_bcnt[q];
+                if (cn > 0) {
+                    s_bidx[q] = nblk; s_bstart[q] = run; s_bch[q] = nch;
+                    B.blk_i[P.blk0 + nblk] = i; B.blk_j[P.blk0 + nblk] = j; B.blk_ch[P.bch0 + nblk] = nch;
+                    nch += (cn + BA_CH - 1) / BA_CH; run += cn; nblk++;
+                } else s_bidx[q] = -1;
+            }
+        B.blk_ch[P.bch0 + nblk] = nch;
+        B.ch_off[P.choff0 + nch] = run;
+        s_tot[0] = nblk; s_tot[1] = nch; s_tot[2] = run;
+    }
+    __syncthreads();
+    for (int q = tid; q < NB; q += BB_T) {
+        if (s_bidx[q] < 0) continue;
+        const int cn = s_bcnt[q];
+        for (int c0 = 0, cc = 0; c0 < cn; c0 += BA_CH, cc++) { B.ch_blk[P.ch0 + s_bch[q] + cc] = s_bidx[q]; B.ch_off[P.choff0 + s_bch[q] + cc] = s_bstart[q] + c0; }
+    }
+    for (int q = warp; q < NB; q += NW) {
+        if (s_bcnt[q] == 0) continue;
+        int i = 0, r = q;
+        while (r >= NA - i) { r -= NA - i; i++; }
+        const int j = i + r;
+        const unsigned need = (1u << i) | (1u << j), lo_i = (1u << i) - 1u, lo_j = (1u << j) - 1u;
+        int run = s_bstart[q];
+        for (int l0 = 0; l0 < L; l0 += 32) {
+            const int l = l0 + lane;
+            const unsigned m = l < L ? mask[l] : 0u;
+            const bool has = (m & need) == need;
+            const unsigned bal = __ballot_sync(0xffffffffu, has);
+            if (has) {
+                const int pos = P.pair0 + run + __popc(bal & ((1u << lane) - 1u)), g0 = lg_off[l];
+                B.pr_e1[pos] = g0 + __popc(m & lo_i); B.pr_e2[pos] = g0 + __popc(m & lo_j);
+            }
+            run += __popc(bal);
+        }
+    }
+    if (tid == 0) {
+        P.NA = NA; P.G = G; P.nblk = s_tot[0]; P.nch = s_tot[1];
+        B.probs[blockIdx.x] = P;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side workspace of svs_ba_optimize, owned by the context (svs_ctx::ba_ws) and reused by every call.
+struct alignas(128) BaBuilt {      // one problem's structure pieces; aligned: neighbouring problems are filled by different threads
+    std::vector<int32_t> act_pose, l_off, p_off, blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off, lg_off, g_lm, g_pose, pg_off, pg_groups;
+    int bad = 0;
+};
+struct BaSeg { const void *src; size_t bytes; size_t off; };
+struct BaHostWs {
+    std::vector<BaProb> probs;
+    std::vector<BaBuilt> built;
+    std::vector<int32_t> edge_p, l_edges, p_edges;
+    std::vector<BaSeg> segs;
+};
+void svs_i_ba_ws_free(void *p) { delete static_cast<BaHostWs *>(p); }
+
 extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, double *poses, const int32_t *lm_off, double *lms,
                                const int32_t *e_off, const int32_t *edge_kf, const int32_t *edge_lm, const uint8_t *edge_cam,
                                const double *edge_uv, const double K_left[4], const double K_right[4], const double ext_left[7],
@@ -480,119 +684,215 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now_s();
 
-    // ---- host-side structure: active poses, CSR by landmark / pose, per-block pair lists.  The problems are independent:
-    // each is built into its own vectors by an OpenMP team (the windows of one step come from different streams), then the
-    // per-problem pieces are laid out back to back with prefix offsets.
-    struct Built {
-        std::vector<int32_t> act_pose, l_off, p_off, blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off, lg_off, g_lm, g_pose, pg_off, pg_groups;
-        int bad = 0;
-    };
-    std::vector<BaProb> probs(n_prob);
-    std::vector<Built> built(n_prob);
-    std::vector<int32_t> edge_p(sumE), l_edges(sumE), p_edges(sumE);
-    const size_t smem_cap = 200 * 1024;
-    const int omp_team = c->host_threads > 0 ? c->host_threads : omp_get_max_threads();
-#pragma omp parallel for schedule(dynamic, 1) num_threads(omp_team)
-    for (int b = 0; b < n_prob; b++) {
-        int N = kf_off[b + 1] - kf_off[b], L = lm_off[b + 1] - lm_off[b], E = e_off[b + 1] - e_off[b], e0 = e_off[b];
-        BaProb &P = probs[b];
-        Built &B = built[b];
-        std::vector<int> pidx(N, -1);
-        for (int e = 0; e < E; e++) {
-            int k = edge_kf[e0 + e], l = edge_lm[e0 + e];
-            if (k < 0 || k >= N || l < 0 || l >= L) { B.bad = 1; break; }
-            pidx[k] = 0;
-        }
-        if (B.bad) continue;
-        int NA = 0;
-        for (int k = 0; k < N; k++) if (pidx[k] == 0) { pidx[k] = NA++; B.act_pose.push_back(k); }
-        P.NA = NA; P.L = L; P.E = E; P.pose0 = kf_off[b]; P.lm0 = lm_off[b]; P.e0 = e0;
-        for (int e = 0; e < E; e++) edge_p[e0 + e] = pidx[edge_kf[e0 + e]];
-        // CSR by landmark; inside a landmark the edges are listed pose-ascending (stable: creation order inside a pose),
-        // so that the edges of one GROUP = (landmark, pose) form a run
-        std::vector<int> cnt(L + 1, 0);
-        for (int e = 0; e < E; e++) cnt[edge_lm[e0 + e] + 1]++;
-        for (int l = 0; l < L; l++) cnt[l + 1] += cnt[l];
-        B.l_off.assign(cnt.begin(), cnt.end());
-        { std::vector<int> fill(cnt.begin(), cnt.end() - 1);
-          for (int e = 0; e < E; e++) l_edges[e0 + fill[edge_lm[e0 + e]]++] = e; }
-        for (int l = 0; l < L; l++) {      // stable insertion sort: a landmark has a handful of edges
-            int32_t *a = l_edges.data() + e0 + cnt[l];
-            const int m = cnt[l + 1] - cnt[l];
-            for (int i = 1; i < m; i++) {
-                const int32_t v = a[i], pv = edge_p[e0 + v];
-                int j = i - 1;
-                while (j >= 0 && edge_p[e0 + a[j]] > pv) { a[j + 1] = a[j]; j--; }
-                a[j + 1] = v;
-            }
-        }
-        // CSR by active pose
-        std::vector<int> pc(NA + 1, 0);
-        for (int e = 0; e < E; e++) pc[edge_p[e0 + e] + 1]++;
-        for (int a = 0; a < NA; a++) pc[a + 1] += pc[a];
-        B.p_off.assign(pc.begin(), pc.end());
-        { std::vector<int> fill(pc.begin(), pc.end() - 1);
-          for (int e = 0; e < E; e++) p_edges[e0 + fill[edge_p[e0 + e]]++] = e; }
-        // groups, landmark-major / pose-ascending; CSR by landmark and by pose
-        int G = 0;
-        std::vector<int> pgc(NA + 1, 0);
-        B.lg_off.reserve(L + 1); B.g_lm.reserve(E); B.g_pose.reserve(E);
-        for (int l = 0; l < L; l++) {
-            B.lg_off.push_back(G);
-            int cur = -1;
-            for (int s1 = cnt[l]; s1 < cnt[l + 1]; s1++) {
-                int pp = edge_p[e0 + l_edges[e0 + s1]];
-                if (pp != cur) { cur = pp; B.g_lm.push_back(l); B.g_pose.push_back(pp); pgc[pp + 1]++; G++; }
-            }
-        }
-        B.lg_off.push_back(G);
-        P.G = G;
-        for (int a = 0; a < NA; a++) pgc[a + 1] += pgc[a];
-        B.pg_off.assign(pgc.begin(), pgc.end());
-        { std::vector<int> fill(pgc.begin(), pgc.end() - 1);
-          B.pg_groups.resize(G);
-          for (int g = 0; g < G; g++) B.pg_groups[fill[B.g_pose[g]]++] = g; }
-        // (group, group) pairs per upper block (i <= j): the groups of a landmark have distinct, ascending poses, so the
-        // pairs are (a, b) with a <= b in list order.  Sorted by block id i*NA + j (counting sort; inside a block in
-        // landmark order), then cut into chunks of <= BA_CH pairs that never span two blocks
-        std::vector<int> bcount((size_t)NA * NA + 1, 0);
-        const int32_t *lgo = B.lg_off.data(), *gp = B.g_pose.data();
-        for (int l = 0; l < L; l++)
-            for (int g1 = lgo[l]; g1 < lgo[l + 1]; g1++)
-                for (int g2 = g1; g2 < lgo[l + 1]; g2++) bcount[(size_t)gp[g1] * NA + gp[g2] + 1]++;
-        int nblk = 0, run = 0, nch = 0;
-        std::vector<int> bstart((size_t)NA * NA, 0);
-        for (size_t k = 0; k < (size_t)NA * NA; k++) {
-            int cn = bcount[k + 1];
-            if (cn > 0) {
-                nblk++; bstart[k] = run;
-                B.blk_i.push_back((int)(k / NA)); B.blk_j.push_back((int)(k % NA));
-                B.blk_ch.push_back(nch);
-                for (int c0 = 0; c0 < cn; c0 += BA_CH) { B.ch_blk.push_back(nblk - 1); B.ch_off.push_back(run + c0); nch++; }
-                run += cn;
-            }
-        }
-        B.blk_ch.push_back(nch);
-        B.ch_off.push_back(run);
-        P.nblk = nblk; P.nch = nch;
-        B.pr_e1.resize(run); B.pr_e2.resize(run);
-        for (int l = 0; l < L; l++)
-            for (int g1 = lgo[l]; g1 < lgo[l + 1]; g1++)
-                for (int g2 = g1; g2 < lgo[l + 1]; g2++) {
-                    int q = bstart[(size_t)gp[g1] * NA + gp[g2]]++;
-                    B.pr_e1[q] = g1; B.pr_e2[q] = g2;
-                }
-    }
-    // ---- lay the pieces out back to back
-    std::vector<int32_t> act_pose, l_off, p_off, blk_i, blk_j, blk_ch, pr_e1, pr_e2, ch_blk, ch_off, lg_off, g_lm, g_pose, pg_off, pg_groups;
-    size_t max_smem = 0;
+    BaArgs A;
+    size_t sumG = 0, sumCh = 0, max_smem = 0;
     long long S_tot = 0;
-    {
+    double t_built = t_begin;
+    const size_t smem_cap = 200 * 1024;
+    BaHostWs *ws = static_cast<BaHostWs *>(c->ba_ws);
+    if (!ws) { ws = new (std::nothrow) BaHostWs(); if (!ws) SVS_FAIL(c, SVS_ERR_CUDA, "ba: out of host memory"); c->ba_ws = ws; }
+    const int omp_team = c->host_threads > 0 ? c->host_threads : omp_get_max_threads();
+
+    // ---- where is the window structure built?  On the device (k_ba_build) when every window has <= 32 keyframes, fits the
+    // shared-memory solver and lists its edges landmark-major / keyframe-ascending (what Backend::Optimize emits); on the
+    // host otherwise.  Both give the same lists.
+    bool dev_build = !getenv("SVS_BA_HOST_BUILD");
+    if (dev_build) {
+        int ok = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(omp_team) reduction(& : ok)
+        for (int b = 0; b < n_prob; b++) {
+            const int N = kf_off[b + 1] - kf_off[b], L = lm_off[b + 1] - lm_off[b], E = e_off[b + 1] - e_off[b], e0 = e_off[b];
+            int good = (N >= 0 && N <= 32 && L >= 0 && E >= 0 && ba_smem_need(N, 1) <= smem_cap) ? 1 : 0;
+            int lp = -1, kp = -1;
+            for (int e = 0; good && e < E; e++) {
+                const int k = edge_kf[e0 + e], l = edge_lm[e0 + e];
+                if (k < 0 || k >= N || l < 0 || l >= L || l < lp || (l == lp && k < kp)) good = 0;
+                lp = l; kp = k;
+            }
+            ok &= good;
+        }
+        dev_build = ok != 0;
+    }
+    if (dev_build) {
+        std::vector<BaProb> &probs = ws->probs;
+        probs.resize(n_prob);
+        long long a_pair = 0, a_ch = 0, a_blk = 0;
+        for (int b = 0; b < n_prob; b++) {
+            const int N = kf_off[b + 1] - kf_off[b], L = lm_off[b + 1] - lm_off[b], E = e_off[b + 1] - e_off[b];
+            BaProb &P = probs[b];
+            P.NA = N; P.L = L; P.E = E; P.nblk = 0; P.G = 0; P.nch = 0;
+            P.pose0 = kf_off[b]; P.lm0 = lm_off[b]; P.e0 = e_off[b];
+            P.act0 = kf_off[b]; P.loff0 = lm_off[b] + b; P.poff0 = kf_off[b] + b; P.lgoff0 = lm_off[b] + b; P.pgoff0 = kf_off[b] + b;
+            P.grp0 = e_off[b];
+            const long long NB = (long long)N * (N + 1) / 2, PB = ((long long)E * (N + 1) + 1) / 2;
+            P.blk0 = (int)a_blk; P.bch0 = (int)(a_blk + b); P.pair0 = (int)a_pair; P.ch0 = (int)a_ch; P.choff0 = (int)(a_ch + b);
+            P.part0 = a_ch; P.S_off = -1;
+            a_blk += NB; a_pair += PB; a_ch += PB / BA_CH + NB + 1;
+            max_smem = std::max(max_smem, ba_smem_need(N, 2) <= smem_cap ? ba_smem_need(N, 2) : ba_smem_need(N, 1));
+            if (a_pair > 0x7fffffffLL / 2 || a_ch > 0x7fffffffLL / 2) SVS_FAIL(c, SVS_ERR_CAPACITY, "ba: too many windows in one call");
+        }
+        sumG = (size_t)sumE; sumCh = (size_t)a_ch; S_tot = 0;
+        t_built = now_s();
+        // inputs host -> device
+        std::vector<BaSeg> &segs = ws->segs;
+        segs.clear();
+        size_t tot = 0;
+        auto add = [&](const void *p, size_t bytes) { size_t o = tot; segs.push_back({p, bytes, o}); tot = align_up(tot + bytes, 16); return o; };
+        const size_t o_probs = add(probs.data(), probs.size() * sizeof(BaProb));
+        const size_t o_ek = add(edge_kf, (size_t)sumE * 4), o_el = add(edge_lm, (size_t)sumE * 4), o_ec = add(edge_cam, (size_t)sumE);
+        const size_t o_uv = add(edge_uv, (size_t)sumE * 16), o_pose = add(poses, (size_t)sumN * 56), o_lm = add(lms, (size_t)sumL * 24);
+        SVS_CUDA(c, c->h_in.reserve(tot + 16));
+        SVS_CUDA(c, c->d_in2.reserve(tot + 16));
+        uint8_t *hb = c->h_in.as<uint8_t>(), *db = c->d_in2.as<uint8_t>();
+        {
+            struct Piece { const uint8_t *src; uint8_t *dst; size_t n; };
+            static thread_local std::vector<Piece> pieces;
+            pieces.clear();
+            for (const BaSeg &sg : segs)
+                for (size_t o = 0; o < sg.bytes; o += 262144) pieces.push_back({(const uint8_t *)sg.src + o, hb + sg.off + o, std::min<size_t>(262144, sg.bytes - o)});
+            const int n_pieces = (int)pieces.size();
+            const Piece *pc_ = pieces.data();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(omp_team)
+            for (int i = 0; i < n_pieces; i++) memcpy(pc_[i].dst, pc_[i].src, pc_[i].n);
+        }
+        SVS_CUDA(c, cudaMemcpyAsync(db, hb, tot, cudaMemcpyHostToDevice, c->stream));
+        // structure lists: device scratch at upper-bound offsets
+        size_t st = 0;
+        auto res = [&](size_t n_i32) { size_t o = st; st = align_up(st + n_i32 * 4, 16); return o; };
+        const size_t s_act = res(sumN), s_ep = res(sumE), s_lo = res((size_t)sumL + n_prob), s_le = res(sumE), s_po = res((size_t)sumN + n_prob),
+                     s_pe = res(sumE), s_bi = res(a_blk), s_bj = res(a_blk), s_bc = res((size_t)a_blk + n_prob), s_p1 = res(a_pair), s_p2 = res(a_pair),
+                     s_cb = res(a_ch), s_co = res((size_t)a_ch + n_prob), s_lg = res((size_t)sumL + n_prob), s_gl = res(sumE), s_gp = res(sumE),
+                     s_pgo = res((size_t)sumN + n_prob), s_pgg = res(sumE), s_mask = res(sumL);
+        SVS_CUDA(c, c->d_tmp8.reserve(st + 16));
+        uint8_t *sb = c->d_tmp8.as<uint8_t>();
+        auto I = [sb](size_t o) { return reinterpret_cast<int32_t *>(sb + o); };
+        BaBuildArgs Bd;
+        Bd.probs = reinterpret_cast<BaProb *>(db + o_probs);
+        Bd.edge_kf = reinterpret_cast<const int32_t *>(db + o_ek); Bd.edge_lm = reinterpret_cast<const int32_t *>(db + o_el);
+        Bd.act_pose = I(s_act); Bd.edge_p = I(s_ep); Bd.l_off = I(s_lo); Bd.l_edges = I(s_le); Bd.p_off = I(s_po); Bd.p_edges = I(s_pe);
+        Bd.blk_i = I(s_bi); Bd.blk_j = I(s_bj); Bd.blk_ch = I(s_bc); Bd.pr_e1 = I(s_p1); Bd.pr_e2 = I(s_p2); Bd.ch_blk = I(s_cb); Bd.ch_off = I(s_co);
+        Bd.lg_off = I(s_lg); Bd.g_lm = I(s_gl); Bd.g_pose = I(s_gp); Bd.pg_off = I(s_pgo); Bd.pg_groups = I(s_pgg);
+        Bd.lm_mask = reinterpret_cast<uint32_t *>(sb + s_mask);
+        SVS_KERNEL(c, KID_BA_BUILD, k_ba_build<<<n_prob, BB_T, 0, c->stream>>>(Bd));
+        A.probs = Bd.probs;
+        A.poses = reinterpret_cast<double *>(db + o_pose); A.lms = reinterpret_cast<double *>(db + o_lm);
+        A.act_pose = Bd.act_pose; A.edge_p = Bd.edge_p; A.edge_l = Bd.edge_lm;
+        A.edge_cam = db + o_ec; A.edge_uv = reinterpret_cast<double *>(db + o_uv);
+        A.l_off = Bd.l_off; A.l_edges = Bd.l_edges; A.p_off = Bd.p_off; A.p_edges = Bd.p_edges;
+        A.blk_i = Bd.blk_i; A.blk_j = Bd.blk_j; A.blk_ch = Bd.blk_ch; A.pr_e1 = Bd.pr_e1; A.pr_e2 = Bd.pr_e2; A.ch_blk = Bd.ch_blk; A.ch_off = Bd.ch_off;
+        A.lg_off = Bd.lg_off; A.g_lm = Bd.g_lm; A.g_pose = Bd.g_pose; A.pg_off = Bd.pg_off; A.pg_groups = Bd.pg_groups;
+    } else {
+        // ---- host-side structure: active poses, CSR by landmark / pose, per-block pair lists.  The problems are independent:
+        // each is built into its own vectors by an OpenMP team (the windows of one step come from different streams); the pieces
+        // are then copied ONCE, straight into the pinned staging buffer at prefix offsets.  All vectors live in a per-context
+        // workspace and the per-thread temporaries are thread_local, so a steady-state call allocates nothing (fresh vectors cost
+        // page faults under the process-wide mmap lock, which serialises the team).
+        std::vector<BaProb> &probs = ws->probs;
+        std::vector<BaBuilt> &built = ws->built;
+        std::vector<int32_t> &edge_p = ws->edge_p, &l_edges = ws->l_edges, &p_edges = ws->p_edges;
+        probs.resize(n_prob);
+        if ((int)built.size() < n_prob) built.resize(n_prob);
+        edge_p.resize(sumE); l_edges.resize(sumE); p_edges.resize(sumE);
+    #pragma omp parallel for schedule(dynamic, 1) num_threads(omp_team)
+        for (int b = 0; b < n_prob; b++) {
+            int N = kf_off[b + 1] - kf_off[b], L = lm_off[b + 1] - lm_off[b], E = e_off[b + 1] - e_off[b], e0 = e_off[b];
+            BaProb &P = probs[b];
+            BaBuilt &B = built[b];
+            B.act_pose.clear(); B.blk_i.clear(); B.blk_j.clear(); B.blk_ch.clear(); B.ch_blk.clear(); B.ch_off.clear();
+            B.lg_off.clear(); B.g_lm.clear(); B.g_pose.clear(); B.bad = 0;
+            static thread_local std::vector<int> pidx, cnt, fill, pc, pgc, bcount, bstart;
+            pidx.assign(N, -1);
+            for (int e = 0; e < E; e++) {
+                int k = edge_kf[e0 + e], l = edge_lm[e0 + e];
+                if (k < 0 || k >= N || l < 0 || l >= L) { B.bad = 1; break; }
+                pidx[k] = 0;
+            }
+            if (B.bad) continue;
+            int NA = 0;
+            for (int k = 0; k < N; k++) if (pidx[k] == 0) { pidx[k] = NA++; B.act_pose.push_back(k); }
+            P.NA = NA; P.L = L; P.E = E; P.pose0 = kf_off[b]; P.lm0 = lm_off[b]; P.e0 = e0;
+            for (int e = 0; e < E; e++) edge_p[e0 + e] = pidx[edge_kf[e0 + e]];
+            // CSR by landmark; inside a landmark the edges are listed pose-ascending (stable: creation order inside a pose),
+            // so that the edges of one GROUP = (landmark, pose) form a run
+            cnt.assign(L + 1, 0);
+            for (int e = 0; e < E; e++) cnt[edge_lm[e0 + e] + 1]++;
+            for (int l = 0; l < L; l++) cnt[l + 1] += cnt[l];
+            B.l_off.assign(cnt.begin(), cnt.end());
+            fill.assign(cnt.begin(), cnt.end() - 1);
+            for (int e = 0; e < E; e++) l_edges[e0 + fill[edge_lm[e0 + e]]++] = e;
+            for (int l = 0; l < L; l++) {      // stable insertion sort: a landmark has a handful of edges
+                int32_t *a = l_edges.data() + e0 + cnt[l];
+                const int m = cnt[l + 1] - cnt[l];
+                for (int i = 1; i < m; i++) {
+                    const int32_t v = a[i], pv = edge_p[e0 + v];
+                    int j = i - 1;
+                    while (j >= 0 && edge_p[e0 + a[j]] > pv) { a[j + 1] = a[j]; j--; }
+                    a[j + 1] = v;
+                }
+            }
+            // CSR by active pose
+            pc.assign(NA + 1, 0);
+            for (int e = 0; e < E; e++) pc[edge_p[e0 + e] + 1]++;
+            for (int a = 0; a < NA; a++) pc[a + 1] += pc[a];
+            B.p_off.assign(pc.begin(), pc.end());
+            fill.assign(pc.begin(), pc.end() - 1);
+            for (int e = 0; e < E; e++) p_edges[e0 + fill[edge_p[e0 + e]]++] = e;
+            // groups, landmark-major / pose-ascending; CSR by landmark and by pose
+            int G = 0;
+            pgc.assign(NA + 1, 0);
+            B.lg_off.reserve(L + 1); B.g_lm.reserve(E); B.g_pose.reserve(E);
+            for (int l = 0; l < L; l++) {
+                B.lg_off.push_back(G);
+                int cur = -1;
+                for (int s1 = cnt[l]; s1 < cnt[l + 1]; s1++) {
+                    int pp = edge_p[e0 + l_edges[e0 + s1]];
+                    if (pp != cur) { cur = pp; B.g_lm.push_back(l); B.g_pose.push_back(pp); pgc[pp + 1]++; G++; }
+                }
+            }
+            B.lg_off.push_back(G);
+            P.G = G;
+            for (int a = 0; a < NA; a++) pgc[a + 1] += pgc[a];
+            B.pg_off.assign(pgc.begin(), pgc.end());
+            fill.assign(pgc.begin(), pgc.end() - 1);
+            B.pg_groups.resize(G);
+            for (int g = 0; g < G; g++) B.pg_groups[fill[B.g_pose[g]]++] = g;
+            // (group, group) pairs per upper block (i <= j): the groups of a landmark have distinct, ascending poses, so the
+            // pairs are (a, b) with a <= b in list order.  Sorted by block id i*NA + j (counting sort; inside a block in
+            // landmark order), then cut into chunks of <= BA_CH pairs that never span two blocks
+            bcount.assign((size_t)NA * NA + 1, 0);
+            const int32_t *lgo = B.lg_off.data(), *gp = B.g_pose.data();
+            for (int l = 0; l < L; l++)
+                for (int g1 = lgo[l]; g1 < lgo[l + 1]; g1++)
+                    for (int g2 = g1; g2 < lgo[l + 1]; g2++) bcount[(size_t)gp[g1] * NA + gp[g2] + 1]++;
+            int nblk = 0, run = 0, nch = 0;
+            bstart.assign((size_t)NA * NA, 0);
+            for (size_t k = 0; k < (size_t)NA * NA; k++) {
+                int cn = bcount[k + 1];
+                if (cn > 0) {
+                    nblk++; bstart[k] = run;
+                    B.blk_i.push_back((int)(k / NA)); B.blk_j.push_back((int)(k % NA));
+                    B.blk_ch.push_back(nch);
+                    for (int c0 = 0; c0 < cn; c0 += BA_CH) { B.ch_blk.push_back(nblk - 1); B.ch_off.push_back(run + c0); nch++; }
+                    run += cn;
+                }
+            }
+            B.blk_ch.push_back(nch);
+            B.ch_off.push_back(run);
+            P.nblk = nblk; P.nch = nch;
+            B.pr_e1.resize(run); B.pr_e2.resize(run);
+            for (int l = 0; l < L; l++)
+                for (int g1 = lgo[l]; g1 < lgo[l + 1]; g1++)
+                    for (int g2 = g1; g2 < lgo[l + 1]; g2++) {
+                        int q = bstart[(size_t)gp[g1] * NA + gp[g2]]++;
+                        B.pr_e1[q] = g1; B.pr_e2[q] = g2;
+                    }
+        }
+        // ---- prefix offsets of the per-problem pieces
         size_t n_act = 0, n_lo = 0, n_po = 0, n_blk = 0, n_bch = 0, n_pr = 0, n_ch = 0, n_co = 0, n_lg = 0, n_g = 0, n_pgo = 0;
         for (int b = 0; b < n_prob; b++) {
             if (built[b].bad) SVS_FAIL(c, SVS_ERR_ARG, "ba: edge index out of range");
             BaProb &P = probs[b];
-            const Built &B = built[b];
+            const BaBuilt &B = built[b];
             P.act0 = (int)n_act; P.loff0 = (int)n_lo; P.poff0 = (int)n_po; P.blk0 = (int)n_blk; P.bch0 = (int)n_bch; P.pair0 = (int)n_pr;
             P.ch0 = (int)n_ch; P.choff0 = (int)n_co; P.part0 = (long long)n_ch; P.grp0 = (int)n_g; P.lgoff0 = (int)n_lg; P.pgoff0 = (int)n_pgo;
             n_act += B.act_pose.size(); n_lo += B.l_off.size(); n_po += B.p_off.size(); n_blk += B.blk_i.size(); n_bch += B.blk_ch.size();
@@ -603,87 +903,86 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
             else if (ba_smem_need(NA, 1) <= smem_cap) { P.S_off = -1; max_smem = std::max(max_smem, ba_smem_need(NA, 1)); }
             else { P.S_off = S_tot; size_t np = 6 * (size_t)NA; S_tot += (long long)(np * (np | 1)); max_smem = std::max(max_smem, ba_smem_need(NA, 0)); }
         }
-        act_pose.resize(n_act); l_off.resize(n_lo); p_off.resize(n_po); blk_i.resize(n_blk); blk_j.resize(n_blk); blk_ch.resize(n_bch);
-        pr_e1.resize(n_pr); pr_e2.resize(n_pr); ch_blk.resize(n_ch); ch_off.resize(n_co); lg_off.resize(n_lg); g_lm.resize(n_g);
-        g_pose.resize(n_g); pg_off.resize(n_pgo); pg_groups.resize(n_g);
-#pragma omp parallel for schedule(dynamic, 1) num_threads(omp_team)
-        for (int b = 0; b < n_prob; b++) {
-            const BaProb &P = probs[b];
-            const Built &B = built[b];
-            auto put = [](std::vector<int32_t> &dst, size_t at, const std::vector<int32_t> &src) { if (!src.empty()) memcpy(dst.data() + at, src.data(), src.size() * 4); };
-            put(act_pose, P.act0, B.act_pose); put(l_off, P.loff0, B.l_off); put(p_off, P.poff0, B.p_off); put(blk_i, P.blk0, B.blk_i);
-            put(blk_j, P.blk0, B.blk_j); put(blk_ch, P.bch0, B.blk_ch); put(pr_e1, P.pair0, B.pr_e1); put(pr_e2, P.pair0, B.pr_e2);
-            put(ch_blk, P.ch0, B.ch_blk); put(ch_off, P.choff0, B.ch_off); put(lg_off, P.lgoff0, B.lg_off); put(g_lm, P.grp0, B.g_lm);
-            put(g_pose, P.grp0, B.g_pose); put(pg_off, P.pgoff0, B.pg_off); put(pg_groups, P.grp0, B.pg_groups);
-        }
-    }
-    if (max_smem > 220 * 1024) SVS_FAIL(c, SVS_ERR_CAPACITY, "ba: window too large for the single-CTA solver");
+        if (max_smem > 220 * 1024) SVS_FAIL(c, SVS_ERR_CAPACITY, "ba: window too large for the single-CTA solver");
 
-    const double t_built = now_s();
-    // ---- pack host -> device
-    struct Seg { const void *src; size_t bytes; size_t off; };
-    std::vector<Seg> segs;
-    size_t tot = 0;
-    auto add = [&](const void *p, size_t bytes) { size_t o = tot; segs.push_back({p, bytes, o}); tot = align_up(tot + bytes, 16); return o; };
-    size_t o_probs = add(probs.data(), probs.size() * sizeof(BaProb));
-    size_t o_act = add(act_pose.data(), act_pose.size() * 4);
-    size_t o_ep = add(edge_p.data(), (size_t)sumE * 4);
-    size_t o_el = add(edge_lm, (size_t)sumE * 4);
-    size_t o_ec = add(edge_cam, (size_t)sumE);
-    size_t o_uv = add(edge_uv, (size_t)sumE * 16);
-    size_t o_lo = add(l_off.data(), l_off.size() * 4);
-    size_t o_le = add(l_edges.data(), (size_t)sumE * 4);
-    size_t o_po = add(p_off.data(), p_off.size() * 4);
-    size_t o_pe = add(p_edges.data(), (size_t)sumE * 4);
-    size_t o_bi = add(blk_i.data(), blk_i.size() * 4);
-    size_t o_bj = add(blk_j.data(), blk_j.size() * 4);
-    size_t o_bc = add(blk_ch.data(), blk_ch.size() * 4);
-    size_t o_p1 = add(pr_e1.data(), pr_e1.size() * 4);
-    size_t o_p2 = add(pr_e2.data(), pr_e2.size() * 4);
-    size_t o_cb = add(ch_blk.data(), ch_blk.size() * 4);
-    size_t o_co = add(ch_off.data(), ch_off.size() * 4);
-    size_t o_lg = add(lg_off.data(), lg_off.size() * 4);
-    size_t o_gl = add(g_lm.data(), g_lm.size() * 4);
-    size_t o_gp = add(g_pose.data(), g_pose.size() * 4);
-    size_t o_pgo = add(pg_off.data(), pg_off.size() * 4);
-    size_t o_pgg = add(pg_groups.data(), pg_groups.size() * 4);
-    const size_t sumG = g_lm.size();
-    size_t o_pose = add(poses, (size_t)sumN * 56);
-    size_t o_lm = add(lms, (size_t)sumL * 24);
-    SVS_CUDA(c, c->h_in.reserve(tot + 16));
-    SVS_CUDA(c, c->d_in2.reserve(tot + 16));
-    uint8_t *hb = c->h_in.as<uint8_t>(), *db = c->d_in2.as<uint8_t>();
-    {   // parallel pack: the big segments (pair lists, edge arrays) are cut into 256 KB pieces
-        struct Piece { const uint8_t *src; uint8_t *dst; size_t n; };
-        std::vector<Piece> pieces;
-        for (const Seg &s : segs)
-            for (size_t o = 0; o < s.bytes; o += 262144) pieces.push_back({(const uint8_t *)s.src + o, hb + s.off + o, std::min<size_t>(262144, s.bytes - o)});
-#pragma omp parallel for schedule(static) num_threads(omp_team)
-        for (int i = 0; i < (int)pieces.size(); i++) memcpy(pieces[i].dst, pieces[i].src, pieces[i].n);
+        t_built = now_s();
+        // ---- pack host -> device: flat arrays as 256 KB pieces, per-problem pieces straight from their vectors
+        typedef BaSeg Seg;
+        std::vector<Seg> &segs = ws->segs;
+        segs.clear();
+        size_t tot = 0;
+        auto add = [&](const void *p, size_t bytes) { size_t o = tot; if (p) segs.push_back({p, bytes, o}); tot = align_up(tot + bytes, 16); return o; };
+        size_t o_probs = add(probs.data(), probs.size() * sizeof(BaProb));
+        size_t o_act = add(nullptr, n_act * 4);
+        size_t o_ep = add(edge_p.data(), (size_t)sumE * 4);
+        size_t o_el = add(edge_lm, (size_t)sumE * 4);
+        size_t o_ec = add(edge_cam, (size_t)sumE);
+        size_t o_uv = add(edge_uv, (size_t)sumE * 16);
+        size_t o_lo = add(nullptr, n_lo * 4);
+        size_t o_le = add(l_edges.data(), (size_t)sumE * 4);
+        size_t o_po = add(nullptr, n_po * 4);
+        size_t o_pe = add(p_edges.data(), (size_t)sumE * 4);
+        size_t o_bi = add(nullptr, n_blk * 4);
+        size_t o_bj = add(nullptr, n_blk * 4);
+        size_t o_bc = add(nullptr, n_bch * 4);
+        size_t o_p1 = add(nullptr, n_pr * 4);
+        size_t o_p2 = add(nullptr, n_pr * 4);
+        size_t o_cb = add(nullptr, n_ch * 4);
+        size_t o_co = add(nullptr, n_co * 4);
+        size_t o_lg = add(nullptr, n_lg * 4);
+        size_t o_gl = add(nullptr, n_g * 4);
+        size_t o_gp = add(nullptr, n_g * 4);
+        size_t o_pgo = add(nullptr, n_pgo * 4);
+        size_t o_pgg = add(nullptr, n_g * 4);
+        sumG = n_g; sumCh = n_ch;
+        size_t o_pose = add(poses, (size_t)sumN * 56);
+        size_t o_lm = add(lms, (size_t)sumL * 24);
+        SVS_CUDA(c, c->h_in.reserve(tot + 16));
+        SVS_CUDA(c, c->d_in2.reserve(tot + 16));
+        uint8_t *hb = c->h_in.as<uint8_t>(), *db = c->d_in2.as<uint8_t>();
+        {
+            struct Piece { const uint8_t *src; uint8_t *dst; size_t n; };
+            static thread_local std::vector<Piece> pieces;
+            pieces.clear();
+            for (const Seg &sg : segs)
+                for (size_t o = 0; o < sg.bytes; o += 262144) pieces.push_back({(const uint8_t *)sg.src + o, hb + sg.off + o, std::min<size_t>(262144, sg.bytes - o)});
+            const int n_pieces = (int)pieces.size();
+            const Piece *pc_ = pieces.data();
+    #pragma omp parallel for schedule(dynamic, 1) num_threads(omp_team)
+            for (int i = 0; i < n_pieces + n_prob; i++) {
+                if (i < n_pieces) { memcpy(pc_[i].dst, pc_[i].src, pc_[i].n); continue; }
+                const BaProb &P = probs[i - n_pieces];
+                const BaBuilt &B = built[i - n_pieces];
+                auto put = [hb](size_t seg, size_t at, const std::vector<int32_t> &src) { if (!src.empty()) memcpy(hb + seg + at * 4, src.data(), src.size() * 4); };
+                put(o_act, P.act0, B.act_pose); put(o_lo, P.loff0, B.l_off); put(o_po, P.poff0, B.p_off); put(o_bi, P.blk0, B.blk_i);
+                put(o_bj, P.blk0, B.blk_j); put(o_bc, P.bch0, B.blk_ch); put(o_p1, P.pair0, B.pr_e1); put(o_p2, P.pair0, B.pr_e2);
+                put(o_cb, P.ch0, B.ch_blk); put(o_co, P.choff0, B.ch_off); put(o_lg, P.lgoff0, B.lg_off); put(o_gl, P.grp0, B.g_lm);
+                put(o_gp, P.grp0, B.g_pose); put(o_pgo, P.pgoff0, B.pg_off); put(o_pgg, P.grp0, B.pg_groups);
+            }
+        }
+        SVS_CUDA(c, cudaMemcpyAsync(db, hb, tot, cudaMemcpyHostToDevice, c->stream));
+        A.probs = reinterpret_cast<BaProb *>(db + o_probs);
+        A.poses = reinterpret_cast<double *>(db + o_pose); A.lms = reinterpret_cast<double *>(db + o_lm);
+        A.act_pose = reinterpret_cast<int32_t *>(db + o_act);
+        A.edge_p = reinterpret_cast<int32_t *>(db + o_ep); A.edge_l = reinterpret_cast<int32_t *>(db + o_el);
+        A.edge_cam = db + o_ec; A.edge_uv = reinterpret_cast<double *>(db + o_uv);
+        A.l_off = reinterpret_cast<int32_t *>(db + o_lo); A.l_edges = reinterpret_cast<int32_t *>(db + o_le);
+        A.p_off = reinterpret_cast<int32_t *>(db + o_po); A.p_edges = reinterpret_cast<int32_t *>(db + o_pe);
+        A.blk_i = reinterpret_cast<int32_t *>(db + o_bi); A.blk_j = reinterpret_cast<int32_t *>(db + o_bj);
+        A.blk_ch = reinterpret_cast<int32_t *>(db + o_bc);
+        A.pr_e1 = reinterpret_cast<int32_t *>(db + o_p1); A.pr_e2 = reinterpret_cast<int32_t *>(db + o_p2);
+        A.ch_blk = reinterpret_cast<int32_t *>(db + o_cb); A.ch_off = reinterpret_cast<int32_t *>(db + o_co);
+        A.lg_off = reinterpret_cast<int32_t *>(db + o_lg); A.g_lm = reinterpret_cast<int32_t *>(db + o_gl);
+        A.g_pose = reinterpret_cast<int32_t *>(db + o_gp); A.pg_off = reinterpret_cast<int32_t *>(db + o_pgo);
+        A.pg_groups = reinterpret_cast<int32_t *>(db + o_pgg);
     }
-    SVS_CUDA(c, cudaMemcpyAsync(db, hb, tot, cudaMemcpyHostToDevice, c->stream));
     // scratch
-    size_t sc_b = (sumG * 36 + (size_t)sumL * 27 + (size_t)S_tot + ch_blk.size() * 36) * 8 + 64;
+    size_t sc_b = (sumG * 36 + (size_t)sumL * 27 + (size_t)S_tot + sumCh * 36) * 8 + 64;
     SVS_CUDA(c, c->d_tmp.reserve(sc_b));
     size_t out_b = (size_t)sumE * 8 + (size_t)n_prob * sizeof(svs_ba_stats);
     SVS_CUDA(c, c->d_out.reserve(out_b + 16));
     SVS_CUDA(c, c->h_out.reserve(out_b + (size_t)sumN * 56 + (size_t)sumL * 24 + 64));
     double *scr = c->d_tmp.as<double>();
-    BaArgs A;
-    A.probs = reinterpret_cast<BaProb *>(db + o_probs);
-    A.poses = reinterpret_cast<double *>(db + o_pose); A.lms = reinterpret_cast<double *>(db + o_lm);
-    A.act_pose = reinterpret_cast<int32_t *>(db + o_act);
-    A.edge_p = reinterpret_cast<int32_t *>(db + o_ep); A.edge_l = reinterpret_cast<int32_t *>(db + o_el);
-    A.edge_cam = db + o_ec; A.edge_uv = reinterpret_cast<double *>(db + o_uv);
-    A.l_off = reinterpret_cast<int32_t *>(db + o_lo); A.l_edges = reinterpret_cast<int32_t *>(db + o_le);
-    A.p_off = reinterpret_cast<int32_t *>(db + o_po); A.p_edges = reinterpret_cast<int32_t *>(db + o_pe);
-    A.blk_i = reinterpret_cast<int32_t *>(db + o_bi); A.blk_j = reinterpret_cast<int32_t *>(db + o_bj);
-    A.blk_ch = reinterpret_cast<int32_t *>(db + o_bc);
-    A.pr_e1 = reinterpret_cast<int32_t *>(db + o_p1); A.pr_e2 = reinterpret_cast<int32_t *>(db + o_p2);
-    A.ch_blk = reinterpret_cast<int32_t *>(db + o_cb); A.ch_off = reinterpret_cast<int32_t *>(db + o_co);
-    A.lg_off = reinterpret_cast<int32_t *>(db + o_lg); A.g_lm = reinterpret_cast<int32_t *>(db + o_gl);
-    A.g_pose = reinterpret_cast<int32_t *>(db + o_gp); A.pg_off = reinterpret_cast<int32_t *>(db + o_pgo);
-    A.pg_groups = reinterpret_cast<int32_t *>(db + o_pgg);
     A.Hpl = scr; A.WD = A.Hpl + sumG * 18;
     A.Hll = A.WD + sumG * 18; A.Dinv = A.Hll + (size_t)sumL * 9;
     A.bl = A.Dinv + (size_t)sumL * 9; A.xl = A.bl + (size_t)sumL * 3; A.lmT = A.xl + (size_t)sumL * 3;

@@ -61,7 +61,7 @@ struct PinBuf {
 // Kernel classes for the optional per-kernel CUDA-event timing (svs_kernel_timing_*; bench.py's roofline).
 enum SvsKernelId { KID_HALF = 0, KID_COPY0, KID_PYRDOWN, KID_MASK, KID_CORNER_RESPONSE, KID_CORNER_SELECT, KID_CORNER_GREEDY,
                    KID_LK, KID_TRIANGULATE, KID_POSE_LM, KID_BA_WINDOW, KID_BM_PREFILTER, KID_BM_SAD, KID_BACKPROJECT,
-                   KID_BGR2GRAY, KID_MISC, KID_TRACK_STATE, KID_COUNT };
+                   KID_BGR2GRAY, KID_MISC, KID_TRACK_STATE, KID_BA_BUILD, KID_COUNT };
 struct SvsPendingEv { int kid; cudaEvent_t a, b; };
 
 struct svs_ctx {
@@ -82,9 +82,10 @@ struct svs_ctx {
     cudaStream_t stream_in = nullptr;   // ingest stream: prefetch of the NEXT frame pair overlaps this step's compute
     std::string err;
     long long launches = 0;
+    void *ba_ws = nullptr;              // svs_ba_optimize's persistent host workspace (ba.cu; freed by svs_i_ba_ws_free)
     double ba_host_s[3] = {0, 0, 0};   // svs_ba_optimize wall time: structure build | pack + enqueue | wait for the device + unpack
     // scratch (named by user)
-    DevBuf d_in, d_in2, d_out, d_out2, d_tmp, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_tmp6, d_tmp7;
+    DevBuf d_in, d_in2, d_out, d_out2, d_tmp, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_tmp6, d_tmp7, d_tmp8;
     PinBuf h_in, h_out;
 };
 
@@ -126,6 +127,8 @@ struct svs_frameset {
     PinBuf pf_ptr_table_h;
     long long prefetch_hits = 0, prefetch_misses = 0;
 };
+
+void svs_i_ba_ws_free(void *ws);
 
 // wait for everything enqueued on the context stream, by the context's wait policy
 inline cudaError_t svs_i_wait(svs_ctx *c)

@@ -152,7 +152,7 @@ int StreamBatch::track_host(double &t0)
     const int B = n();
     double t1;
     int rc;
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         s.ran_track = s.ran_detect = s.ran_backend = s.is_kf = false;
@@ -167,7 +167,7 @@ int StreamBatch::track_host(double &t0)
     t1 = now_s(); t_phase[1] += t1 - t0; t0 = t1;
 
     // ---------------- EstimateCurrentPose: pose-only LM (src/frontend.cpp:408-527)
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (!s.ran_track) continue;
@@ -207,7 +207,7 @@ int StreamBatch::track_host(double &t0)
         }
         t1 = now_s(); t_phase[2] += t1 - t0; t0 = t1;
     }
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (s.ran_track) s.frontend->finish_EstimateCurrentPose(s.pose);
@@ -224,7 +224,7 @@ int StreamBatch::track_device(double &t0)
     if (rc) return rc;
     t1 = now_s(); t_phase[1] += t1 - t0; t0 = t1;
     const TrkOut *o = svs_i_trk_out(trk_);
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         s.ran_track = s.ran_detect = s.ran_backend = s.is_kf = false;
@@ -277,7 +277,7 @@ int StreamBatch::upload_states()
         tot += h.n;
     }
     up_feat_.resize((size_t)tot);
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads_)
     for (int k = 0; k < ns; k++) {
         Stream &s = streams_[ids_[k]];
         const Frame &f = *s.frontend->current_frame_;
@@ -335,7 +335,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         t1 = now_s(); t_phase[3] += t1 - t0; t0 = t1;
     }
     // ---------------- FindFeaturesInRight: LK current-left -> current-right (src/frontend.cpp:105-109)
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (!s.ran_detect) continue;
@@ -354,7 +354,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
     if ((rc = run_lk(1, [](const Stream &s) { return s.ran_detect; }))) return rc;
     t1 = now_s(); t_phase[4] += t1 - t0; t0 = t1;
     // ---------------- triangulation of new landmarks (src/frontend.cpp:174, :286)
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (!s.ran_detect) continue;
@@ -388,7 +388,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         t1 = now_s(); t_phase[5] += t1 - t0; t0 = t1;
     }
     // ---------------- Backend::UpdateMap -> Optimize, synchronous schedule (src/backend.cpp:9-248)
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (!s.ran_detect) continue;
@@ -411,7 +411,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
             int sN = off_[np], sL = off2_[np], sE = off3_[np];
             d0_.resize((size_t)7 * sN); d1_.resize((size_t)3 * sL + 1); d2_.resize((size_t)2 * sE); d3_.resize(sE);
             i0_.resize(sE); i1_.resize(sE); u0_.resize(sE); bast_.resize(np);
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads_)
             for (int k = 0; k < np; k++) {
                 const BaRequest &q = streams_[ids_[k]].ba;
                 memcpy(&d0_[7 * (size_t)off_[k]], q.poses.data(), q.poses.size() * 8);
@@ -428,7 +428,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
                                  u0_.data(), d2_.data(), Kl, Kr, el.d, er.d, cfg_.chi2_th, cfg_.ba_max_iter, cfg_.ba_jacobian_mode,
                                  d3_.data(), bast_.data());
             if (rc) return rc;
-#pragma omp parallel for schedule(static) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads_)
             for (int k = 0; k < np; k++) {
                 BaRequest &q = streams_[ids_[k]].ba;
                 memcpy(q.poses.data(), &d0_[7 * (size_t)off_[k]], q.poses.size() * 8);
@@ -445,7 +445,7 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         t1 = now_s(); t_phase[6] += t1 - t0; t0 = t1;
     }
     long long nkf = 0;
-#pragma omp parallel for schedule(static) reduction(+ : nkf) num_threads(threads_)
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : nkf) num_threads(threads_)
     for (int b = 0; b < B; b++) {
         Stream &s = streams_[b];
         if (!s.on_host) continue;           // device-resident tracking: this stream's frame never left the GPU

@@ -82,6 +82,28 @@ def test_ba_window_vs_oracle(ctx, n_kf, n_lm):
     assert np.array_equal(P[0], probs[2]["poses"][0]) and np.array_equal(L[-3:], probs[2]["lms"][-3:])
 
 
+def test_ba_structure_built_on_device_equals_host_build(ctx, monkeypatch):
+    """k_ba_build (window structure on the device, the default for landmark-major edge lists) and the host construction give
+    the same lists, hence bit-identical results; an edge list in another order takes the host construction."""
+    probs = [ba_problem(s, n_kf=n, n_lm=m)[0] for s, n, m in ((0, 10, 300), (1, 20, 500), (2, 3, 20), (3, 10, 2200))]
+    probs.append(ba_problem(4, n_kf=6, n_lm=80, unused_kf=True, unused_lm=3)[0])
+    dev = ctx.ba_optimize(probs, K05, K05, EXT_L, EXT_R)
+    monkeypatch.setenv("SVS_BA_HOST_BUILD", "1")
+    host = ctx.ba_optimize(probs, K05, K05, EXT_L, EXT_R)
+    monkeypatch.delenv("SVS_BA_HOST_BUILD")
+    for (P, L, chi2, st), (hP, hL, hchi2, hst) in zip(dev, host):
+        assert np.array_equal(P, hP) and np.array_equal(L, hL) and np.array_equal(chi2, hchi2)
+        assert (st.iterations, st.trials, st.chi2) == (hst.iterations, hst.trials, hst.chi2)
+    # a shuffled edge list (same graph): host construction, same minimum
+    pr = dict(probs[0])
+    perm = np.random.RandomState(0).permutation(len(pr["edge_kf"]))
+    for k in ("edge_kf", "edge_lm", "edge_cam", "edge_uv"):
+        pr[k] = np.ascontiguousarray(np.asarray(pr[k])[perm])
+    (P, L, chi2, st), = ctx.ba_optimize([pr], K05, K05, EXT_L, EXT_R)
+    assert np.abs(P - dev[0][0]).max() < 1e-8 and rel_to_norm(L, dev[0][1]).max() < 1e-8
+    assert np.abs(chi2 - dev[0][2][perm]).max() < 1e-6 * max(1.0, dev[0][2].max())
+
+
 def test_ba_large_window_global_S(ctx):
     pr = ba_problem(9, n_kf=30, n_lm=500)[0]          # 180x180 reduced system: beyond shared memory
     (P, L, chi2, st), = ctx.ba_optimize([pr], K05, K05, EXT_L, EXT_R)
