@@ -371,10 +371,27 @@ def ncu_traffic():
     try:
         import csv
         for row in csv.DictReader(l for l in open(os.path.join(ROOT, "profiles", "r02_ncu_full_summary.csv")) if not l.startswith("#")):
-            k = row["kernel"].replace("void ", "").split("<")[0].split("(")[0]
+            k = row["kernel"].replace("void ", "").split("<")[0].split("(")[0].replace("_tma", "")
+            if k in out:
+                continue
             out[k] = dict(traffic=(float(row["dram_rd_MB"]) + float(row["dram_wr_MB"])) * 1e6, dur_us=float(row["dur_us"]),
                           dram_pct=float(row["dram_pct"]), issue_active_pct=float(row["issue_active_pct"]),
                           fp64_pipe_pct=float(row["fp64_pipe_pct"]), registers=float(row["regs"]), grid=row.get("grid"))
+    except Exception:
+        pass
+    return out
+
+
+def ncu_shares():
+    """Share of the serialised step per kernel class from the committed ncu launch list of this configuration
+    (profiles/r02_launches_summary.csv).  Event-bracketed durations cannot rank the kernels: the ingest-stream kernels run
+    underneath the compute kernels of the other context group and their brackets include the time they wait for SMs."""
+    out = {}
+    try:
+        import csv
+        for row in csv.DictReader(l for l in open(os.path.join(ROOT, "profiles", "r02_launches_summary.csv")) if not l.startswith("#")):
+            k = row["kernel"].replace("void ", "").split("<")[0].split("(")[0].replace("_tma", "")
+            out[k] = out.get(k, 0.0) + float(row["share"])
     except Exception:
         pass
     return out
@@ -385,7 +402,7 @@ LIMITER = {
     "k_pose_only_lm": "dependent FP64 latency, one warp per problem",
     "k_lk_track": "integer instruction issue (warp per keypoint, smem-staged patches)",
     "k_pyr_down": "HBM / issue (TMA-staged tiles, packed 16-bit arithmetic)",
-    "k_corner_response": "HBM (TMA-staged tile, exact f64 box sums)",
+    "k_corner_response": "latency (sequential f64 column march forced by bit-exactness)",
     "k_half_nearest": "HBM", "k_corner_select": "HBM", "k_bm_sad": "INT32 ALU + shared memory", "k_bm_prefilter": "HBM",
 }
 
@@ -795,7 +812,14 @@ def build_report(args, world, B, G, cor, spec, dev_pass, e2e_pass, kern_pass, cl
     cnt = kern_pass["counts"]
     P = int(round(cor.W * 0.5)) * int(round(cor.H * 0.5))
     kr = kernel_rooflines(kern, cnt, P, 10, peak, 150)
-    dom = max((k for k in kern if k in kr), key=lambda k: kern[k][0], default=None)
+    shares_ncu = ncu_shares()
+    ingest = ("k_half_nearest", "k_pyr_down")     # launched on the ingest stream, overlapped with the other kernels
+    if any(k in shares_ncu for k in kr):
+        dom = max((k for k in kr), key=lambda k: shares_ncu.get(k, 0.0), default=None)
+        dom_src = "largest share of the serialised step in profiles/r02_launches_summary.csv (%.0f %%)" % (100 * shares_ncu.get(dom, 0.0))
+    else:
+        dom = max((k for k in kern if k in kr and k not in ingest), key=lambda k: kern[k][0], default=None)
+        dom_src = "largest summed event-bracketed time among the compute-stream kernels"
     roof = None
     if dom:
         tr = traffic.get(dom)
@@ -804,6 +828,7 @@ def build_report(args, world, B, G, cor, spec, dev_pass, e2e_pass, kern_pass, cl
                 "traffic_source": "profiles/r02_ncu_full_summary.csv (ncu --set full of this configuration, mean per launch)" if tr else None,
                 "avg_launch_ms": kr[dom]["avg_launch_ms"], "launches": kr[dom]["launches"],
                 "algorithmic_bytes_per_launch": kr[dom]["algorithmic_bytes_per_launch"], "peak_source": peak_src,
+                "dominant_by": dom_src,
                 "note": "launch durations from CUDA events on the launching stream, %d context group(s) overlapping; limiter: %s (DESIGN.md §4)"
                         % (G, LIMITER.get(dom, "HBM streaming"))}
     for k, v in kr.items():

@@ -16,7 +16,10 @@
 //  * Every third-party call site (GFTT detect, calcOpticalFlowPyrLK, triangulation, the two g2o blocks)
 //    is split into a prepare_* / finish_* pair so that many independent streams can be stepped in
 //    lock-step and each seam becomes ONE batched svs_* call over all streams (slam::StreamBatch).
-//  * Bundle adjustment runs on the synchronous schedule (inside UpdateMap), SURVEY.md §5.
+//  * Bundle adjustment runs on the synchronous schedule (inside UpdateMap), SURVEY.md §5.  One consequence: on a keyframe
+//    step relative_motion_ (src/frontend.cpp:685) is formed AFTER Backend::Optimize has refined the current keyframe's
+//    pose, whereas the reference's backend thread usually has not touched it yet when Track() reads it (a race the
+//    reference leaves open).  The constant-velocity prior of the next frame therefore already contains the BA correction.
 //  * Hash-map iteration orders that the reference leaves unspecified are fixed to ascending id.
 #pragma once
 #include <algorithm>
