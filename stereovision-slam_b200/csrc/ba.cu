@@ -85,29 +85,29 @@ __host__ __device__ inline size_t ba_smem_need(int NA, int n_S)
 
 template <int BT>
 __device__ __forceinline__ double block_sum(double v, double *red)
-{   // deterministic tree reduction; result broadcast to all threads
-    int tid = threadIdx.x;
-    red[tid] = v;
+{   // deterministic: xor-butterfly inside each warp, then every thread adds the BT/32 warp totals in the same order;
+    // result broadcast to all threads; two barriers (the second lets `red` be reused at once)
+    const int tid = threadIdx.x;
+    v = gd::warp_sum(v);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
-    for (int s = BT / 2; s > 0; s >>= 1) {
-        if (tid < s) red[tid] += red[tid + s];
-        __syncthreads();
-    }
-    double r = red[0];
+    double r = 0;
+#pragma unroll
+    for (int w = 0; w < BT / 32; w++) r += red[w];
     __syncthreads();
     return r;
 }
 template <int BT>
 __device__ __forceinline__ double block_max(double v, double *red)
 {
-    int tid = threadIdx.x;
-    red[tid] = v;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
-    for (int s = BT / 2; s > 0; s >>= 1) {
-        if (tid < s) red[tid] = fmax(red[tid], red[tid + s]);
-        __syncthreads();
-    }
     double r = red[0];
+#pragma unroll
+    for (int w = 1; w < BT / 32; w++) r = fmax(r, red[w]);
     __syncthreads();
     return r;
 }
@@ -421,9 +421,11 @@ k_ba_window(BaArgs A)
             for (int a = tid; a < NA; a += BT) gd::se3_oplus(poseA + 7 * a, xp + 6 * a, poseT + 7 * a);
             double scl = block_sum<BT>(sc, red);     // also orders the trial-state writes before chi2_of reads them
             double tmpchi = chi2_of(poseT, lmT);
-            if (tid == 0) {
+            if (warp == 0) {
                 double scp = 0;
-                for (int i = 0; i < np; i++) scp += xp[i] * (lambda * xp[i] + bp[i]);
+                for (int i = lane; i < np; i += 32) scp += xp[i] * (lambda * xp[i] + bp[i]);
+                scp = gd::warp_sum(scp);
+                if (lane == 0) {
                 double scale = scp + scl + 1e-3;
                 double tc = ok ? tmpchi : DBL_MAX;
                 double r = (cur - tc) / scale;
@@ -431,6 +433,7 @@ k_ba_window(BaArgs A)
                 int acc2 = gd::lm_accept(lm, r, tc) ? 1 : 0;
                 s_lambda = lm.lambda; s_ni = lm.ni; s_rho = r; s_q = acc2;
                 if (acc2) s_cur = tc;
+                }
             }
             __syncthreads();
             rho = s_rho;
