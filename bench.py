@@ -545,6 +545,8 @@ class Rig:
         barrier()
         if profile_window:     # `ncu --profile-from-start off`: only the steady-state steps below are captured
             torch.cuda.profiler.start()
+        lib.svs_buffer_regrowths.restype = C.c_longlong
+        rg0 = lib.svs_buffer_regrowths()
         t0 = time.perf_counter()
         cpu0 = time.process_time()
         e0.record()
@@ -581,7 +583,8 @@ class Rig:
         phases.update({"ba:host_build": bh1[0] - bh0[0], "ba:pack_enqueue": bh1[1] - bh0[1], "ba:device_wait_unpack": bh1[2] - bh0[2]})
         counts = {k: sum(c1[1][k] - c0[1][k] for c0, c1 in zip(cn0, cn1)) for k in cn1[0][1]}
         log("region (on_device=%s, instrumented=%s): %.2f ms/step" % (on_device, timing, ms / steps))
-        return dict(ms=ms, wall=wall, launches=launches, phases=phases, counts=counts, kern=kern, lost=lost, cpu_s=cpu_s)
+        return dict(ms=ms, wall=wall, launches=launches, phases=phases, counts=counts, kern=kern, lost=lost, cpu_s=cpu_s,
+                    regrowths=int(lib.svs_buffer_regrowths() - rg0))
 
     def close(self):
         for s in self.slams:
@@ -871,6 +874,7 @@ def build_report(args, world, B, G, cor, spec, dev_pass, e2e_pass, kern_pass, cl
                    "kernel_time_share": shares, "kernel_roofline": kr, "kernel_pass_ms_per_step": kern_pass["ms"] / args.steps,
                    "summed_kernel_ms_over_wall_ms": dev_total / kern_pass["ms"] if kern_pass["ms"] else None,
                    "lost_streams": dev_pass["lost"], "host_cores": cores, "host_cores_this_rank": my_cores, "host_threads_per_group": host_threads,
+                   "buffer_regrowths_in_timed_regions": {"value": dev_pass.get("regrowths"), "e2e": e2e_pass.get("regrowths")},
                    "host_wait_mode": "block" if getattr(args, "wait_block", False) else "spin",
                    "host_cpu_ms_per_step": {"value": round(1e3 * dev_pass.get("cpu_s", 0.0) / args.steps, 2), "e2e": round(1e3 * e2e_pass.get("cpu_s", 0.0) / args.steps, 2),
                                             "note": "user + system time of every thread of rank 0 per timed step (spinning waits count as busy)"},
@@ -897,7 +901,7 @@ def run_gpu(args, rank, world, local_rank):
     except Exception:
         cores = os.cpu_count() or 1
     my_cores = max(1, cores // max(1, local_world))
-    G = max(1, min(args.groups, args.streams, my_cores))
+    G = max(1, min(args.groups, args.streams, max(1, my_cores // 2)))     # a context group wants its driver thread + one helper
     host_threads = max(1, my_cores // G)
     # host wait policy: with few cores per rank the pipeline threads sleep on a blocking-sync event instead of spinning
     args.wait_block = (args.wait_mode == "block") or (args.wait_mode == "auto" and my_cores < 4 * G)
@@ -1024,7 +1028,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=int(os.environ.get("SVS_BENCH_STREAMS", "4096")))
-    ap.add_argument("--groups", type=int, default=int(os.environ.get("SVS_BENCH_GROUPS", "2")),
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("SVS_BENCH_GROUPS", "4")),
                     help="independent contexts (one CUDA stream pair + one driver thread each) the streams are split over: one "
                          "group's host keyframe bookkeeping overlaps the other group's kernels")
     ap.add_argument("--variants", type=int, default=24, help="photometric variants of the clip (distinct frame bytes per stream)")

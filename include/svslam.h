@@ -49,6 +49,9 @@ SVS_API int svs_sync(svs_ctx *ctx);                       /* wait for the contex
  * stream (lowest wake-up latency, one busy core per waiting host thread); 1 = the thread sleeps on a blocking-sync event
  * (for hosts with fewer cores than waiting threads, e.g. 8 ranks x 2 contexts on a 32-core box).  Results are identical. */
 SVS_API int svs_set_wait_mode(svs_ctx *ctx, int mode);
+/* Diagnostic: how many times an internal grow-only device / pinned buffer was (re)allocated in this process so far.  A
+ * regrowth synchronises the device; a primed steady-state step does none. */
+SVS_API long long svs_buffer_regrowths(void);
 SVS_API void *svs_stream(svs_ctx *ctx);                   /* the cudaStream_t, for event timing */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 SVS_API long long svs_launch_count(svs_ctx *ctx);

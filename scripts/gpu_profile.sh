@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence of the bench's own configuration (B200_PROFILING.md recipe).  One gpurun call:
 #   gpurun --timeout 2400 -- 'bash scripts/gpu_profile.sh r02'
-# (1) launch list (gpu__time_duration.sum) of steady-state steps of the bench's own configuration (4096 streams, 2 context groups)
+# (1) launch list (gpu__time_duration.sum) of steady-state steps of the bench's own configuration (4096 streams, 4 context groups)
 # (2) ncu --set full of the kernels that carry the step, of the sharded-BA solver and of StereoBM
 # (3) sysmem (PCIe) sector counters of the zero-copy ingest kernel in the e2e configuration
 # The .ncu-rep files are summarised ON THE BOX (gpurun brings back at most 64 MiB) and deleted.
@@ -9,7 +9,7 @@ TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT /tmp/cub
 STREAMS=${STREAMS:-4096}
-GROUPS_=${GROUPS_:-2}
+GROUPS_=${GROUPS_:-4}
 COMMON="bench.py --profile-window --streams $STREAMS --groups $GROUPS_ --steps 2 --warmup 3 --no-cpu-baseline --configs= --no-ba4 --no-latency --sampler none"
 (cd /tmp/cub && rm -f *.cubin && cuobjdump -xelf all $OLDPWD/stereovision-slam_b200/libsvslam.so > /dev/null)
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/${TAG}_launches.csv \
@@ -19,7 +19,7 @@ python scripts/launch_summary.py $OUT/${TAG}_launches.csv "ncu --metrics gpu__ti
 head -20 $OUT/${TAG}_launches_summary.csv
 if [ -z "$SKIP_FULL" ]; then
 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:'k_lk_track|k_ba_window|k_pose_only_lm|k_pyr_down|k_corner_response|k_corner_greedy|k_corner_select|k_half_nearest|k_trk_|k_ba_build' -c 64 \
+    -k regex:'k_lk_track|k_ba_window|k_pose_only_lm|k_pyr_down|k_corner_response|k_corner_greedy|k_corner_select|k_half_nearest|k_trk_|k_ba_build' -c 128 \
     -o /tmp/${TAG}_full python $COMMON > $OUT/${TAG}_full_bench.log 2>&1
 echo "full exit $?"
 python scripts/ncu_summary.py /tmp/${TAG}_full.ncu-rep > $OUT/${TAG}_full_summary.csv

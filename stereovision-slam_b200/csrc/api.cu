@@ -33,6 +33,8 @@ cudaError_t svs_i_opt_in_smem(svs_ctx *c, const void *func)
     return e;
 }
 static std::atomic<int> g_live_ctx{0};
+long long svs_i_regrowths = 0;     // diagnostic counter (not atomic: an approximate count is enough)
+long long svs_buffer_regrowths(void) { return svs_i_regrowths; }
 
 int svs_i_zc_grid(const svs_ctx *c)
 {

@@ -38,8 +38,9 @@ __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1)
 #define LK_WARPS 4
 #define LK_MARGIN 6      // the next-image region staged per level extends this many pixels around the first window
 
-template <int WIN, int MINB>
-__global__ void __launch_bounds__(LK_WARPS * 32, WIN <= 11 ? MINB : 1)
+// (8 CTAs per SM at 64 registers compile without spills but measure the same as 6 at 80: the kernel is issue-bound.)
+template <int WIN>
+__global__ void __launch_bounds__(LK_WARPS * 32, WIN <= 11 ? 6 : 1)
 k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc next, const int32_t *__restrict__ pt_img, const float *__restrict__ prev_xy,
            float *__restrict__ next_xy, int n_pts, int max_iter, double eps2, uint8_t *__restrict__ status)
 {
@@ -321,12 +322,9 @@ int svs_i_lk(svs_ctx *c, const PyrDesc &prev, const PyrDesc &next, const int32_t
     int blocks = (n_pts + LK_WARPS - 1) / LK_WARPS;
 #define LK_CASE(WN)                                                                                          \
     case WN:                                                                                                 \
-        if (minb8) k_lk_track<WN, 8><<<blocks, LK_WARPS * 32, 0, c->stream>>>(prev, next, pt_img, prev_xy, next_xy, n_pts, \
-                                                                max_iter, eps2, status);                     \
-        else k_lk_track<WN, 6><<<blocks, LK_WARPS * 32, 0, c->stream>>>(prev, next, pt_img, prev_xy, next_xy, n_pts, \
+        k_lk_track<WN><<<blocks, LK_WARPS * 32, 0, c->stream>>>(prev, next, pt_img, prev_xy, next_xy, n_pts, \
                                                                 max_iter, eps2, status);                     \
         break;
-    static const bool minb8 = !getenv("SVS_LK_6");
     svs_i_prof_begin(c, KID_LK);
     switch (win) {
         LK_CASE(5) LK_CASE(7) LK_CASE(9) LK_CASE(11) LK_CASE(13) LK_CASE(15) LK_CASE(21)

@@ -26,7 +26,9 @@ struct PyrDesc {
     size_t off[SVS_MAX_LEVELS];
 };
 
-// Grow-only device / pinned-host buffers.
+// Grow-only device / pinned-host buffers.  svs_i_regrowths counts every (re)allocation: a regrowth frees and allocates, which
+// synchronises the whole device, so a steady-state step must not see one (bench.py reports the count per timed region).
+extern long long svs_i_regrowths;
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -35,6 +37,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = 2 * bytes + 4096;   // geometric growth: regrowing is a device-wide sync
+        svs_i_regrowths++;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -50,6 +53,7 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = 2 * bytes + 4096;
+        svs_i_regrowths++;
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
