@@ -535,6 +535,11 @@ class Rig:
     def region(self, steps, warmup, on_device, timing, barrier, dist=None, profile_window=False):
         torch, lib = self.torch, self.lib
         self.run_steps(warmup, on_device)
+        # steady state must not reallocate: a scratch-buffer regrowth is a device-wide synchronisation (a single one inside a
+        # 60-step region costs tens of milliseconds on every context).  Sizes fluctuate with the number of keyframe streams
+        # per step, so after priming + warm-up every buffer is grown once to 2 x the largest size it has been asked for.
+        for c in self.ctxs:
+            c.reserve_headroom(2.0)
         for c in self.ctxs:
             lib.svs_kernel_timing_reset(C.c_void_p(c.h))
             lib.svs_kernel_timing_enable(C.c_void_p(c.h), 1 if timing else 0)
@@ -583,8 +588,24 @@ class Rig:
         phases.update({"ba:host_build": bh1[0] - bh0[0], "ba:pack_enqueue": bh1[1] - bh0[1], "ba:device_wait_unpack": bh1[2] - bh0[2]})
         counts = {k: sum(c1[1][k] - c0[1][k] for c0, c1 in zip(cn0, cn1)) for k in cn1[0][1]}
         log("region (on_device=%s, instrumented=%s): %.2f ms/step" % (on_device, timing, ms / steps))
+        regrowths = int(lib.svs_buffer_regrowths() - rg0)
+        if dist is not None:      # every rank must take the same re-measure decision
+            t = torch.tensor([regrowths], device="cuda", dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            regrowths = int(t.item())
         return dict(ms=ms, wall=wall, launches=launches, phases=phases, counts=counts, kern=kern, lost=lost, cpu_s=cpu_s,
-                    regrowths=int(lib.svs_buffer_regrowths() - rg0))
+                    regrowths=regrowths)
+
+    def region_clean(self, *a, **k):
+        """region(), re-measured once if a scratch buffer had to regrow inside the timed steps (the regrowth's device-wide
+        synchronisation is an artefact of sizes not seen during warm-up, not steady-state behaviour)."""
+        r = self.region(*a, **k)
+        if r["regrowths"] > 0:
+            log("%d buffer regrowth(s) inside the timed region: re-measuring once" % r["regrowths"])
+            first = r["ms"]
+            r = self.region(*a, **k)
+            r["remeasured_after_regrowth_ms"] = first
+        return r
 
     def close(self):
         for s in self.slams:
@@ -603,8 +624,8 @@ def side_config(svslam, torch, dev, rank, cid, clip, clip_path, streams, steps, 
     rig = Rig(svslam, torch, dev, rank, clip, spec, streams, 1, max(1, cores), min(16, streams), args)
     barrier = lambda: torch.cuda.synchronize(dev)
     rig.run_steps(spec["priming"], True, stagger=True)
-    dev_pass = rig.region(steps, warmup, True, False, barrier)
-    e2e_pass = rig.region(steps, warmup, False, False, barrier)
+    dev_pass = rig.region_clean(steps, warmup, True, False, barrier)
+    e2e_pass = rig.region_clean(steps, warmup, False, False, barrier)
     kern_pass = rig.region(max(4, steps // 2), 1, True, True, barrier)
     P = (int(round(cor.W * 0.5)) * int(round(cor.H * 0.5))) if spec["half"] else cor.W * cor.H
     cnt = kern_pass["counts"]
@@ -901,10 +922,15 @@ def run_gpu(args, rank, world, local_rank):
     except Exception:
         cores = os.cpu_count() or 1
     my_cores = max(1, cores // max(1, local_world))
-    G = max(1, min(args.groups, args.streams, max(1, my_cores // 2)))     # a context group wants its driver thread + one helper
+    # Context groups: each is one host thread that drives its share of the streams, so that one group's keyframe bookkeeping
+    # overlaps the other groups' kernels.  Measured on one B200 (profiles/README.md): with 16 / 8 / 4 cores, one group per
+    # core up to 8 beats fewer groups with OpenMP helpers (8 cores: 172 k vs 156 k frames/s; 4 cores: 147 k vs 125 k).
+    gcap = my_cores if args.group_cap == "cores" else max(1, my_cores // 2)
+    G = max(1, min(args.groups, args.streams, gcap))
     host_threads = max(1, my_cores // G)
-    # host wait policy: with few cores per rank the pipeline threads sleep on a blocking-sync event instead of spinning
-    args.wait_block = (args.wait_mode == "block") or (args.wait_mode == "auto" and my_cores < 4 * G)
+    # host wait policy: a group thread spins on its stream while it has a core of its own (lowest wake-up latency); with more
+    # group threads than cores they sleep on a blocking-sync event instead
+    args.wait_block = (args.wait_mode == "block") or (args.wait_mode == "auto" and my_cores < G)
     spec = CONFIGS[2]
     log("rendering clip ...")
     clip = make_clip(spec["calib"], args.clip_frames)
@@ -937,8 +963,8 @@ def run_gpu(args, rank, world, local_rank):
         gpu_uuid = None
     sampler = ClockSampler(dev, args.sampler, uuid=gpu_uuid)
     sampler.start()
-    dev_pass = rig.region(args.steps, args.warmup, True, False, barrier, dist)
-    e2e_pass = rig.region(args.steps, args.warmup, False, False, barrier, dist)
+    dev_pass = rig.region_clean(args.steps, args.warmup, True, False, barrier, dist)
+    e2e_pass = rig.region_clean(args.steps, args.warmup, False, False, barrier, dist)
     clocks = sampler.stop()
     kern_pass = rig.region(args.steps, args.warmup, True, True, barrier, dist) if not args.no_kernel_pass else dev_pass
     distinct = rig.distinct
@@ -1028,9 +1054,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=int(os.environ.get("SVS_BENCH_STREAMS", "4096")))
-    ap.add_argument("--groups", type=int, default=int(os.environ.get("SVS_BENCH_GROUPS", "4")),
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("SVS_BENCH_GROUPS", "8")),
                     help="independent contexts (one CUDA stream pair + one driver thread each) the streams are split over: one "
                          "group's host keyframe bookkeeping overlaps the other group's kernels")
+    ap.add_argument("--group-cap", default=os.environ.get("SVS_BENCH_GROUP_CAP", "cores"), choices=["half", "cores"],
+                    help="upper bound of the context groups of a rank: half = cores / 2 (a driver thread + one helper each), cores = one per core")
     ap.add_argument("--variants", type=int, default=24, help="photometric variants of the clip (distinct frame bytes per stream)")
     ap.add_argument("--h2d-mode", type=int, default=2, choices=[0, 2, 3],
                     help="e2e transfer of the pinned host frames: 2 zero-copy kernel reads over PCIe, 0 staged DMA copies")

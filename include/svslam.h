@@ -49,9 +49,18 @@ SVS_API int svs_sync(svs_ctx *ctx);                       /* wait for the contex
  * stream (lowest wake-up latency, one busy core per waiting host thread); 1 = the thread sleeps on a blocking-sync event
  * (for hosts with fewer cores than waiting threads, e.g. 8 ranks x 2 contexts on a 32-core box).  Results are identical. */
 SVS_API int svs_set_wait_mode(svs_ctx *ctx, int mode);
+/* Scheduling of the window solver behind svs_ba_optimize (no effect on results).  high_priority 1: the solver runs on a
+ * high-priority stream of its own, so that its few long CTAs are placed ahead of the queued CTAs of machine-filling kernels
+ * launched by other contexts; threads_per_window 0 = automatic, 256 or 512 = force that CTA size (256 leaves half of an
+ * SM's registers to kernels of other contexts). */
+SVS_API int svs_set_ba_schedule(svs_ctx *ctx, int high_priority, int threads_per_window);
 /* Diagnostic: how many times an internal grow-only device / pinned buffer was (re)allocated in this process so far.  A
  * regrowth synchronises the device; a primed steady-state step does none. */
 SVS_API long long svs_buffer_regrowths(void);
+/* Grow every variable-size scratch buffer of the context (and of the frame sets / pipelines created on it) to
+ * factor x the largest size requested so far; call once after warm-up, when no call is in flight on the context.  Buffer
+ * contents are kept.  factor in [1, 64]. */
+SVS_API int svs_reserve_headroom(svs_ctx *ctx, double factor);
 SVS_API void *svs_stream(svs_ctx *ctx);                   /* the cudaStream_t, for event timing */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 SVS_API long long svs_launch_count(svs_ctx *ctx);

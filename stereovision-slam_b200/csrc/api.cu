@@ -152,6 +152,10 @@ svs_ctx *svs_create(int device)
         return nullptr;
     }
     g_live_ctx++;
+    {   // experiment knobs (the API is svs_set_ba_schedule)
+        const char *pz = getenv("SVS_BA_PRIO"), *tz = getenv("SVS_BA_THREADS");
+        if (pz || tz) svs_set_ba_schedule(c, pz ? atoi(pz) : 0, tz ? atoi(tz) : 0);
+    }
     return c;
 }
 
@@ -159,6 +163,45 @@ int svs_set_wait_mode(svs_ctx *c, int mode)
 {
     if (!c || (mode != 0 && mode != 1)) return SVS_ERR_ARG;
     c->wait_mode = mode;
+    return SVS_OK;
+}
+
+// Grow every variable-size scratch buffer of the context to factor x the largest request it has seen, once, at a quiet
+// point.  Buffers grow geometrically on demand, but a regrowth is a cudaFree + cudaMalloc, i.e. a device-wide synchronisation
+// that stalls every other context of the process for tens of milliseconds; a batch whose per-step sizes fluctuate (the
+// number of streams that insert a keyframe in a step) calls this after its warm-up so that steady state never regrows.
+int svs_reserve_headroom(svs_ctx *c, double factor)
+{
+    if (!c || !(factor >= 1.0) || factor > 64.0) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    SVS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->stream_in) SVS_CUDA(c, cudaStreamSynchronize(c->stream_in));
+    if (c->stream_ba) SVS_CUDA(c, cudaStreamSynchronize(c->stream_ba));
+    DevBuf *d[] = {&c->d_in, &c->d_in2, &c->d_out, &c->d_out2, &c->d_tmp, &c->d_tmp2, &c->d_tmp3, &c->d_tmp4, &c->d_tmp5, &c->d_tmp6, &c->d_tmp7, &c->d_tmp8};
+    std::vector<DevBuf *> dv(d, d + sizeof(d) / sizeof(d[0]));
+    dv.insert(dv.end(), c->reg_dev.begin(), c->reg_dev.end());
+    std::vector<PinBuf *> pv = {&c->h_in, &c->h_out};
+    pv.insert(pv.end(), c->reg_pin.begin(), c->reg_pin.end());
+    for (DevBuf *b : dv) if (b->hwm) SVS_CUDA(c, b->grow_keep((size_t)(factor * (double)b->hwm) + 4096));
+    for (PinBuf *b : pv) if (b->hwm) SVS_CUDA(c, b->grow_keep((size_t)(factor * (double)b->hwm) + 4096));
+    return SVS_OK;
+}
+
+int svs_set_ba_schedule(svs_ctx *c, int high_priority, int threads_per_window)
+{
+    if (!c || (threads_per_window != 0 && threads_per_window != 256 && threads_per_window != 512)) return SVS_ERR_ARG;
+    SVS_CUDA(c, cudaSetDevice(c->device));
+    c->ba_threads = threads_per_window;
+    if (high_priority && !c->stream_ba) {
+        int lo = 0, hi = 0;
+        SVS_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));      // numerically lower = higher priority
+        SVS_CUDA(c, cudaStreamCreateWithPriority(&c->stream_ba, cudaStreamNonBlocking, hi));
+        SVS_CUDA(c, cudaEventCreateWithFlags(&c->ev_ba, cudaEventDisableTiming));
+    } else if (!high_priority && c->stream_ba) {
+        SVS_CUDA(c, cudaStreamSynchronize(c->stream_ba));
+        cudaStreamDestroy(c->stream_ba); c->stream_ba = nullptr;
+        cudaEventDestroy(c->ev_ba); c->ev_ba = nullptr;
+    }
     return SVS_OK;
 }
 
@@ -175,6 +218,8 @@ void svs_destroy(svs_ctx *c)
     svs_i_ba_ws_free(c->ba_ws); c->ba_ws = nullptr;
     cudaStreamDestroy(c->stream);
     if (c->stream_in) cudaStreamDestroy(c->stream_in);
+    if (c->stream_ba) cudaStreamDestroy(c->stream_ba);
+    if (c->ev_ba) cudaEventDestroy(c->ev_ba);
     if (c->ev_wait) cudaEventDestroy(c->ev_wait);
     { std::lock_guard<std::mutex> lk(g_mutex); g_live_ctx--; }
     delete c;
@@ -224,6 +269,7 @@ svs_frameset *svs_frameset_create(svs_ctx *c, int n_streams, int in_w, int in_h,
                              SVS_CR_BOX_W, SVS_CR_BOX_H) != 0) fs->has_tmaps = false;
     }
     if (!fs->has_tmaps) { c->err = "frameset: cuTensorMapEncodeTiled failed"; svs_frameset_destroy(c, fs); return nullptr; }
+    c->reg_dev.push_back(&fs->staging); c->reg_dev.push_back(&fs->pf_staging);
     if (cudaEventCreateWithFlags(&fs->pf_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fs->pf_order, cudaEventDisableTiming) != cudaSuccess) {
         c->err = "frameset: cudaEventCreate failed";
@@ -237,6 +283,7 @@ void svs_frameset_destroy(svs_ctx *c, svs_frameset *fs)
 {
     if (!fs) return;
     if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); if (c->stream_in) cudaStreamSynchronize(c->stream_in); }
+    if (c) { c->unregister(&fs->staging); c->unregister(&fs->pf_staging); }
     for (int i = 0; i < 5; i++) fs->pyr[i].release();
     fs->staging.release();
     fs->ptr_table.release();

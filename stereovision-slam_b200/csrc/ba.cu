@@ -161,22 +161,6 @@ k_ba_window(BaArgs A)
     for (int i = tid; i < 3 * L; i += BT) lmT[i] = lms[i];
     __syncthreads();
 
-    // robust chi2 of a state (poses in shared memory, landmarks in global)
-    auto chi2_of = [&](const double *pz, const double *lz) -> double {
-        double acc = 0;
-        for (int l = tid; l < L; l += BT) {
-            for (int s = l_off[l]; s < l_off[l + 1]; s++) {
-                int e = l_edges[s], cam = edge_cam[e];
-                double er[2], a[3], c[3];
-                gd::ba_error(pz + 7 * edge_p[e], A.ext[cam], A.K[cam], lz + 3 * l, edge_uv + 2 * e, er, a, c);
-                double e2 = er[0] * er[0] + er[1] * er[1], r0, r1;
-                gd::huber(e2, hd, r0, r1);
-                acc += r0;
-            }
-        }
-        return block_sum<BT>(acc, red);
-    };
-
     int st_it = 0, st_tr = 0, st_lin = 0, st_sol = 0;
     double chi_init = 0;
     if (tid == 0) { s_lambda = 0; s_ni = 2; }
@@ -292,10 +276,12 @@ k_ba_window(BaArgs A)
                 int a = i / 36, r = (i % 36) / 6, c2 = i % 6;
                 S[(6 * a + r) * pitch + 6 * a + c2] = Hpp[i] + (r == c2 ? lambda : 0.0);
             }
-            // ---- V^-1 per landmark
+            // ---- V^-1 per landmark and W V^-1 for the landmark's groups (one pass: the thread that inverts a landmark's block
+            //      multiplies it into the landmark's own groups, so the inverse never makes a round trip through memory)
             for (int l = tid; l < L; l += BT) {
                 int s0 = l_off[l], s1 = l_off[l + 1];
                 if (s0 == s1) continue;
+                const int g0 = lg_off[l], g1 = lg_off[l + 1];
                 double D[9], Di[9];
 #pragma unroll
                 for (int x = 0; x < 9; x++) D[x] = Hll[9 * (size_t)l + x];
@@ -303,19 +289,20 @@ k_ba_window(BaArgs A)
                 if (!gd::inv3(D, Di)) s_flag = 0;
 #pragma unroll
                 for (int x = 0; x < 9; x++) Dinv[9 * (size_t)l + x] = Di[x];
-            }
-            __syncthreads();
-            // ---- per GROUP: W V^-1
-            for (int e = tid; e < G; e += BT) {
-                const double *Di = Dinv + 9 * (size_t)g_lm[e], *W = Hpl + 18 * (size_t)e;
-                double X[18];
+                for (int e = g0; e < g1; e++) {
+                    const double2 *W2 = reinterpret_cast<const double2 *>(Hpl + 18 * (size_t)e);
+                    double W[18];
 #pragma unroll
-                for (int x = 0; x < 6; x++)
+                    for (int x = 0; x < 9; x++) { double2 t = W2[x]; W[2 * x] = t.x; W[2 * x + 1] = t.y; }
+                    double X[18];
 #pragma unroll
-                    for (int y = 0; y < 3; y++) X[x * 3 + y] = W[x * 3] * Di[y] + W[x * 3 + 1] * Di[3 + y] + W[x * 3 + 2] * Di[6 + y];
-                double2 *O = reinterpret_cast<double2 *>(WD + 18 * (size_t)e);
+                    for (int x = 0; x < 6; x++)
 #pragma unroll
-                for (int x = 0; x < 9; x++) O[x] = make_double2(X[2 * x], X[2 * x + 1]);
+                        for (int y = 0; y < 3; y++) X[x * 3 + y] = W[x * 3] * Di[y] + W[x * 3 + 1] * Di[3 + y] + W[x * 3 + 2] * Di[6 + y];
+                    double2 *O = reinterpret_cast<double2 *>(WD + 18 * (size_t)e);
+#pragma unroll
+                    for (int x = 0; x < 9; x++) O[x] = make_double2(X[2 * x], X[2 * x + 1]);
+                }
             }
             __syncthreads();
             // ---- chunk partials: 4 threads per chunk, thread (qr, qc) accumulates the 3x3 quadrant
@@ -389,8 +376,12 @@ k_ba_window(BaArgs A)
             if (ok) ok = S2 ? block_ldlt_solve_pp<BT>(S, S2, pitch, np, g, xp, tr, tmp) : block_ldlt_solve<BT>(S, pitch, np, g, xp, tr, tmp, &s_piv);
             st_sol++;
             if (!ok) { for (int i = tid; i < np; i += BT) xp[i] = 0.0; __syncthreads(); }
-            // ---- back-substitution, trial state, scale term
-            double sc = 0;
+            // ---- trial poses first, then ONE landmark pass: back-substitution, trial landmark, scale term and the robust chi2
+            //      of the trial state (the thread that moves a landmark evaluates the landmark's edges: same thread -> landmark
+            //      map and edge order as the linearisation's chi2, so the sum is formed the same way; one pass and one barrier pair fewer per trial)
+            for (int a = tid; a < NA; a += BT) gd::se3_oplus(poseA + 7 * a, xp + 6 * a, poseT + 7 * a);
+            __syncthreads();
+            double sc = 0, acc_t = 0;
             for (int l = tid; l < L; l += BT) {
                 int s0 = l_off[l], s1 = l_off[l + 1];
                 if (s0 == s1) continue;
@@ -411,16 +402,25 @@ k_ba_window(BaArgs A)
 #pragma unroll
                     for (int x = 0; x < 3; x++) x3[x] = Di[x * 3] * c3[0] + Di[x * 3 + 1] * c3[1] + Di[x * 3 + 2] * c3[2];
                 }
+                double lt[3];
 #pragma unroll
                 for (int x = 0; x < 3; x++) {
                     xl[3 * (size_t)l + x] = x3[x];
-                    lmT[3 * (size_t)l + x] = lms[3 * (size_t)l + x] + x3[x];
+                    lt[x] = lms[3 * (size_t)l + x] + x3[x];
+                    lmT[3 * (size_t)l + x] = lt[x];
                     sc += x3[x] * (lambda * x3[x] + bl[3 * (size_t)l + x]);
                 }
+                for (int s = s0; s < s1; s++) {
+                    int e = l_edges[s], cam = edge_cam[e];
+                    double er[2], a[3], c[3];
+                    gd::ba_error(poseT + 7 * edge_p[e], A.ext[cam], A.K[cam], lt, edge_uv + 2 * e, er, a, c);
+                    double e2 = er[0] * er[0] + er[1] * er[1], r0, r1;
+                    gd::huber(e2, hd, r0, r1);
+                    acc_t += r0;
+                }
             }
-            for (int a = tid; a < NA; a += BT) gd::se3_oplus(poseA + 7 * a, xp + 6 * a, poseT + 7 * a);
-            double scl = block_sum<BT>(sc, red);     // also orders the trial-state writes before chi2_of reads them
-            double tmpchi = chi2_of(poseT, lmT);
+            double scl = block_sum<BT>(sc, red);
+            double tmpchi = block_sum<BT>(acc_t, red);
             if (warp == 0) {
                 double scp = 0;
                 for (int i = lane; i < np; i += 32) scp += xp[i] * (lambda * xp[i] + bp[i]);
@@ -673,11 +673,11 @@ struct BaHostWs {
 };
 void svs_i_ba_ws_free(void *p) { delete static_cast<BaHostWs *>(p); }
 
-extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, double *poses, const int32_t *lm_off, double *lms,
-                               const int32_t *e_off, const int32_t *edge_kf, const int32_t *edge_lm, const uint8_t *edge_cam,
-                               const double *edge_uv, const double K_left[4], const double K_right[4], const double ext_left[7],
-                               const double ext_right[7], double huber_delta, int max_iter, int jacobian_mode,
-                               double *edge_chi2_out, svs_ba_stats *stats)
+static int ba_optimize_on_stream(svs_ctx *c, int n_prob, const int32_t *kf_off, double *poses, const int32_t *lm_off, double *lms,
+                                 const int32_t *e_off, const int32_t *edge_kf, const int32_t *edge_lm, const uint8_t *edge_cam,
+                                 const double *edge_uv, const double K_left[4], const double K_right[4], const double ext_left[7],
+                                 const double ext_right[7], double huber_delta, int max_iter, int jacobian_mode,
+                                 double *edge_chi2_out, svs_ba_stats *stats)
 {
     if (!c || n_prob < 0 || !kf_off || !lm_off || !e_off || !K_left || !K_right || !ext_left || !ext_right) return SVS_ERR_ARG;
     if (n_prob == 0) return SVS_OK;
@@ -998,7 +998,9 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     A.huber_delta = huber_delta; A.max_iter = max_iter; A.jac_mode = jacobian_mode; A.smem_bytes = (int)max_smem;
     // more windows than SMs: 256-thread CTAs, two per SM, so that the launch is one wave (unless the windows are so large that
     // two reduced systems do not fit an SM's shared memory)
-    const bool two_per_sm = n_prob > c->sm_count && 2 * (max_smem + 1024) <= 220 * 1024 && !getenv("SVS_BA_ONE_PER_SM");
+    bool two_per_sm = n_prob > c->sm_count && 2 * (max_smem + 1024) <= 220 * 1024 && !getenv("SVS_BA_ONE_PER_SM");
+    if (c->ba_threads == 256 && 2 * (max_smem + 1024) <= 220 * 1024) two_per_sm = true;
+    if (c->ba_threads == 512) two_per_sm = false;
     if (two_per_sm) {
         SVS_CUDA(c, svs_i_opt_in_smem(c, reinterpret_cast<const void *>(k_ba_window<256>)));
         SVS_KERNEL(c, KID_BA_WINDOW, k_ba_window<256><<<n_prob, 256, max_smem, c->stream>>>(A));
@@ -1020,6 +1022,33 @@ extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, do
     const double t_end = now_s();
     c->ba_host_s[0] += t_built - t_begin; c->ba_host_s[1] += t_queued - t_built; c->ba_host_s[2] += t_end - t_queued;
     return SVS_OK;
+}
+
+// The window solver is latency-bound and long (milliseconds on a fraction of the SMs) while the per-frame kernels of the other
+// context groups are short and fill the machine: with svs_ctx::stream_ba (a high-priority stream) its CTAs are placed as
+// soon as an SM has room instead of queueing behind every CTA of an LK launch that was enqueued earlier.  The call is
+// synchronous (it ends with svs_i_wait on the stream it used), so swapping the context stream for its duration is safe.
+extern "C" int svs_ba_optimize(svs_ctx *c, int n_prob, const int32_t *kf_off, double *poses, const int32_t *lm_off, double *lms,
+                               const int32_t *e_off, const int32_t *edge_kf, const int32_t *edge_lm, const uint8_t *edge_cam,
+                               const double *edge_uv, const double K_left[4], const double K_right[4], const double ext_left[7],
+                               const double ext_right[7], double huber_delta, int max_iter, int jacobian_mode,
+                               double *edge_chi2_out, svs_ba_stats *stats)
+{
+    if (!c) return SVS_ERR_ARG;
+    cudaStream_t s_main = c->stream;
+    if (c->stream_ba && n_prob > 0) {
+        SVS_CUDA(c, cudaSetDevice(c->device));
+        SVS_CUDA(c, cudaEventRecord(c->ev_ba, s_main));
+        SVS_CUDA(c, cudaStreamWaitEvent(c->stream_ba, c->ev_ba, 0));
+        c->stream = c->stream_ba;
+    }
+    const int r = ba_optimize_on_stream(c, n_prob, kf_off, poses, lm_off, lms, e_off, edge_kf, edge_lm, edge_cam, edge_uv, K_left, K_right,
+                                        ext_left, ext_right, huber_delta, max_iter, jacobian_mode, edge_chi2_out, stats);
+    if (c->stream != s_main) {
+        if (r != SVS_OK) cudaStreamSynchronize(c->stream);      // an error return may leave work queued: drain before switching back
+        c->stream = s_main;
+    }
+    return r;
 }
 
 extern "C" int svs_ba_host_seconds(svs_ctx *c, double out[3])

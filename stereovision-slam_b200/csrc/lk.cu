@@ -35,6 +35,25 @@ __device__ __forceinline__ float warp_sum_scaled_exact(int s)
 __device__ __forceinline__ int cvfloor(float v) { return __float2int_rd(v); }
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
+// Word k of the staged next-image region (row k / RWORDS, bytes 4 (k % RWORDS) ..+3): pixels of the reflect-101-padded image
+// at (rx0 + 4q + i, ry0 + r).  Interior regions are aligned 32-bit loads; elsewhere the row is reflected once per word and
+// only words that straddle the left / right image border are assembled from reflected bytes.
+template <int RWORDS>
+__device__ __forceinline__ uint32_t lk_region_word(const uint8_t *__restrict__ J, int Jw, int Jh, int Js, int rx0, int ry0, int k, bool interior)
+{
+    const int r = k / RWORDS, q = k - r * RWORDS;
+    int y = ry0 + r;
+    const int x = rx0 + 4 * q;
+    if (interior) return __ldg(reinterpret_cast<const uint32_t *>(J + (size_t)y * Js + x));
+    y = lk_refl101(y, Jh);
+    const uint8_t *row = J + (size_t)y * Js;
+    if (x >= 0 && x + 4 <= Jw) return __ldg(reinterpret_cast<const uint32_t *>(row + x));
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) v |= (uint32_t)__ldg(row + lk_refl101(x + i, Jw)) << (8 * i);
+    return v;
+}
+
 #define LK_WARPS 4
 #define LK_MARGIN 6      // the next-image region staged per level extends this many pixels around the first window
 
@@ -112,21 +131,24 @@ k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc
 
         __syncwarp();
         // ---- issue the next-image region loads first (they are independent of everything below), then stage the
-        //      previous-image patch; both global round trips overlap
-        bool reg_valid = false;
+        //      previous-image patch; both global round trips overlap.  The region is a piece of the REFLECT-101-PADDED next
+        //      image (what OpenCV's border handling reads), so windows that hang over the image border sample from it like
+        //      interior ones: no per-iteration border path.
+        bool reg_valid = false, reg_interior = false;
         int rx0 = 0, ry0 = 0;
         uint32_t jr[RN];
         {
             int jx = cvfloor(nx), jy = cvfloor(ny);
-            if (jx >= 0 && jy >= 0 && jx + DW <= Jw && jy + DW <= Jh) {
+            if (jx >= -WIN && jx < Jw && jy >= -WIN && jy < Jh) {
                 ry0 = jy - LK_MARGIN; rx0 = (jx - LK_MARGIN) & ~3;
                 reg_valid = true;
+                reg_interior = rx0 >= 0 && ry0 >= 0 && rx0 + RP <= Jw && ry0 + RH <= Jh;
+                if (reg_interior) {      // the common case: aligned word loads into registers, stored after the patch below
 #pragma unroll
-                for (int u = 0; u < RN; u++) {
-                    int k = lane + 32 * u;
-                    int r = k / RWORDS, q = k - r * RWORDS;
-                    int y = min(max(ry0 + r, 0), Jh - 1), x = min(max(rx0 + 4 * q, 0), Js - 4);
-                    jr[u] = (k < RH * RWORDS) ? __ldg(reinterpret_cast<const uint32_t *>(J + (size_t)y * Js + x)) : 0u;
+                    for (int u = 0; u < RN; u++) {
+                        int k = lane + 32 * u;
+                        jr[u] = (k < RH * RWORDS) ? lk_region_word<RWORDS>(J, Jw, Jh, Js, rx0, ry0, k, true) : 0u;
+                    }
                 }
             }
         }
@@ -148,18 +170,22 @@ k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc
                 int k = lane + 32 * u;
                 if (k < PW * IWORDS) reinterpret_cast<uint32_t *>(mI)[k] = ir[u];
             }
-        } else {
-            for (int k = lane; k < PW * PW; k += 32) {
-                int j = k / PW, i = k - j * PW;
-                mI[j * IP + i] = __ldg(I + (size_t)lk_refl101(iy - 1 + j, Ih) * Is + lk_refl101(ix - 1 + i, Iw));
-            }
+        } else {        // the patch hangs over the border: the same word layout, rows / edge bytes reflected
+            ioff = (ix - 1) & 3;
+#pragma unroll 1
+            for (int k = lane; k < PW * IWORDS; k += 32)
+                reinterpret_cast<uint32_t *>(mI)[k] = lk_region_word<IWORDS>(I, Iw, Ih, Is, (ix - 1) & ~3, iy - 1, k, false);
         }
-        if (reg_valid) {
+        if (reg_interior) {
 #pragma unroll
             for (int u = 0; u < RN; u++) {
                 int k = lane + 32 * u;
                 if (k < RH * RWORDS) reinterpret_cast<uint32_t *>(mJ)[k] = jr[u];
             }
+        } else if (reg_valid) {          // the region hangs over the image border: reflected rows / bytes (rolled: rare, keeps the code small)
+#pragma unroll 1
+            for (int k = lane; k < RH * RWORDS; k += 32)
+                reinterpret_cast<uint32_t *>(mJ)[k] = lk_region_word<RWORDS>(J, Jw, Jh, Js, rx0, ry0, k, false);
         }
         __syncwarp();
         // Scharr derivative patch (zero outside the image: BORDER_CONSTANT on the derivative buffer), separable:
@@ -224,53 +250,37 @@ k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc
         if ((double)minEig < 1e-4 || D < FLT_EPSILON) { if (level == 0) st = false; continue; }
         D = __fdiv_rn(1.f, D);
         float pdx = 0.f, pdy = 0.f;
-        // window origins (jx, jy) that are interior AND covered by the staged region: one unsigned range test per axis
+        // window origins (jx, jy) that are in OpenCV's range ([-WIN, size)) AND covered by the staged region: one unsigned
+        // range test per axis
         int fx_lo = 0, fx_n = -1, fy_lo = 0, fy_n = -1;
-        if (reg_valid) {
-            fx_lo = max(0, rx0); fx_n = min(Jw - DW, rx0 + RP - DW) - fx_lo;
-            fy_lo = max(0, ry0); fy_n = min(Jh - DW, ry0 + RH - DW) - fy_lo;
+        auto set_fast_range = [&]() {
+            fx_lo = max(-WIN, rx0); fx_n = min(Jw - 1, rx0 + RP - DW) - fx_lo;
+            fy_lo = max(-WIN, ry0); fy_n = min(Jh - 1, ry0 + RH - DW) - fy_lo;
             if (fx_n < 0 || fy_n < 0) fx_n = fy_n = -1;
-        }
+        };
+        if (reg_valid) set_fast_range();
         for (int j = 0; j < max_iter; j++) {
             int jx = cvfloor(nx), jy = cvfloor(ny);
             const bool fast = fx_n >= 0 && (unsigned)(jx - fx_lo) <= (unsigned)fx_n && (unsigned)(jy - fy_lo) <= (unsigned)fy_n;
-            if (!fast && (jx < -WIN || jx >= Jw || jy < -WIN || jy >= Jh)) { if (level == 0) st = false; break; }
+            if (!fast) {
+                if (jx < -WIN || jx >= Jw || jy < -WIN || jy >= Jh) { if (level == 0) st = false; break; }
+                // the window left the staged region (or there is none yet): restage around the current window
+                __syncwarp();
+                ry0 = jy - LK_MARGIN; rx0 = (jx - LK_MARGIN) & ~3;
+                const bool interior = rx0 >= 0 && ry0 >= 0 && rx0 + RP <= Jw && ry0 + RH <= Jh;
+#pragma unroll 1
+                for (int k = lane; k < RH * RWORDS; k += 32)
+                    reinterpret_cast<uint32_t *>(mJ)[k] = lk_region_word<RWORDS>(J, Jw, Jh, Js, rx0, ry0, k, interior);
+                reg_valid = true;
+                set_fast_range();
+                __syncwarp();
+            }
             a = __fsub_rn(nx, (float)jx); b = __fsub_rn(ny, (float)jy);
             w00 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
             w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), (float)(1 << W_BITS)));
             w10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), (float)(1 << W_BITS)));
             w11 = (1 << W_BITS) - w00 - w01 - w10;
-            const uint8_t *pJ;
-            if (fast) {
-                pJ = mJ + (jy - ry0) * RP + (jx - rx0);
-            } else if (jx >= 0 && jy >= 0 && jx + DW <= Jw && jy + DW <= Jh) {
-                if (!(reg_valid && jx >= rx0 && jx + DW <= rx0 + RP && jy >= ry0 && jy + DW <= ry0 + RH)) {
-                    // the window left the staged region (or there is none yet): restage around the current window
-                    __syncwarp();
-                    ry0 = jy - LK_MARGIN; rx0 = (jx - LK_MARGIN) & ~3;
-                    for (int k = lane; k < RH * RWORDS; k += 32) {
-                        int r = k / RWORDS, q = k - r * RWORDS;
-                        int y = min(max(ry0 + r, 0), Jh - 1), x = min(max(rx0 + 4 * q, 0), Js - 4);
-                        reinterpret_cast<uint32_t *>(mJ)[k] = __ldg(reinterpret_cast<const uint32_t *>(J + (size_t)y * Js + x));
-                    }
-                    reg_valid = true;
-                    fx_lo = max(0, rx0); fx_n = min(Jw - DW, rx0 + RP - DW) - fx_lo;
-                    fy_lo = max(0, ry0); fy_n = min(Jh - DW, ry0 + RH - DW) - fy_lo;
-                    if (fx_n < 0 || fy_n < 0) fx_n = fy_n = -1;
-                    __syncwarp();
-                }
-                pJ = mJ + (jy - ry0) * RP + (jx - rx0);
-            } else {
-                __syncwarp();
-                for (int k = lane; k < DW * DW; k += 32) {
-                    int r = k / DW, i = k - r * DW;
-                    mJ[r * RP + i] = __ldg(J + (size_t)lk_refl101(jy + r, Jh) * Js + lk_refl101(jx + i, Jw));
-                }
-                reg_valid = false;
-                fx_n = fy_n = -1;
-                __syncwarp();
-                pJ = mJ;
-            }
+            const uint8_t *pJ = mJ + (jy - ry0) * RP + (jx - rx0);
             int pb1 = 0, pb2 = 0;
 #pragma unroll
             for (int q = 0; q < NPL; q++) {

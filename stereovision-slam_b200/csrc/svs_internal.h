@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 #include "../../include/svslam.h"
@@ -32,7 +33,9 @@ extern long long svs_i_regrowths;
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    size_t hwm = 0;     // largest request so far (svs_reserve_headroom sizes the buffer from it)
     cudaError_t reserve(size_t bytes) {
+        if (bytes > hwm) hwm = bytes;
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
@@ -42,13 +45,34 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // deliberate growth at a quiet point (the caller has synchronised the device): contents are kept
+    cudaError_t grow_keep(size_t want) {
+        if (want <= cap) return cudaSuccess;
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) return e;
+        if (p) { e = cudaMemcpy(q, p, cap, cudaMemcpyDeviceToDevice); cudaFree(p); }
+        p = q; cap = want;
+        return e;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 struct PinBuf {
     void *p = nullptr;
     size_t cap = 0;
+    size_t hwm = 0;
+    cudaError_t grow_keep(size_t want) {
+        if (want <= cap) return cudaSuccess;
+        void *q = nullptr;
+        cudaError_t e = cudaMallocHost(&q, want);
+        if (e != cudaSuccess) return e;
+        if (p) { memcpy(q, p, cap); cudaFreeHost(p); }
+        p = q; cap = want;
+        return cudaSuccess;
+    }
     cudaError_t reserve(size_t bytes) {
+        if (bytes > hwm) hwm = bytes;
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
@@ -83,6 +107,9 @@ struct svs_ctx {
     cudaEvent_t ev_wait = nullptr;
     int zc_ctas = 0;    // persistent grid of the zero-copy (PCIe) ingest kernel: 0 = automatic (svs_i_zc_grid), env SVS_ZC_CTAS overrides
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_ba = nullptr;   // optional high-priority stream of the window solver (svs_set_ba_schedule)
+    cudaEvent_t ev_ba = nullptr;
+    int ba_threads = 0;                 // 0 = automatic (512 per window, 256 x 2 per SM when a launch has more windows than SMs)
     cudaStream_t stream_in = nullptr;   // ingest stream: prefetch of the NEXT frame pair overlaps this step's compute
     std::string err;
     long long launches = 0;
@@ -91,6 +118,12 @@ struct svs_ctx {
     // scratch (named by user)
     DevBuf d_in, d_in2, d_out, d_out2, d_tmp, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_tmp6, d_tmp7, d_tmp8;
     PinBuf h_in, h_out;
+    // variable-size scratch buffers of objects created on this context (tracker uploads, frame-set staging): registered so
+    // that svs_reserve_headroom reaches them; the owner unregisters before it dies
+    std::vector<DevBuf *> reg_dev;
+    std::vector<PinBuf *> reg_pin;
+    void unregister(DevBuf *b) { for (size_t i = 0; i < reg_dev.size(); i++) if (reg_dev[i] == b) { reg_dev.erase(reg_dev.begin() + i); break; } }
+    void unregister(PinBuf *b) { for (size_t i = 0; i < reg_pin.size(); i++) if (reg_pin[i] == b) { reg_pin.erase(reg_pin.begin() + i); break; } }
 };
 
 struct svs_frameset {

@@ -236,13 +236,14 @@ svs_tracker *svs_i_trk_create(svs_ctx *c, const TrkParams &p)
     k_trk_init<<<(p.B + 127) / 128, 128, 0, c->stream>>>(d, p.cam_left.fx_, p.cam_left.fy_, p.cam_left.cx_, p.cam_left.cy_);
     c->launches++;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = "tracker: init failed"; svs_i_trk_destroy(c, t); return nullptr; }
+    c->reg_dev.push_back(&t->up_dev); c->reg_pin.push_back(&t->up_h);     // per-step upload scratch: svs_reserve_headroom sizes it
     return t;
 }
 
 void svs_i_trk_destroy(svs_ctx *c, svs_tracker *t)
 {
     if (!t) return;
-    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); c->unregister(&t->up_dev); c->unregister(&t->up_h); }
     t->mem.release(); t->up_dev.release();
     t->out_h.release(); t->kf_h.release(); t->off_h.release(); t->up_h.release();
     if (t->up_done) cudaEventDestroy(t->up_done);

@@ -106,7 +106,7 @@ private:
     std::vector<const uint8_t *> next_left_, next_right_, rptr_;
     bool has_next_ = false;
     // gather buffers
-    std::vector<int32_t> off_, off2_, off3_, ids_;
+    std::vector<int32_t> off_, off2_, off3_, ids_, det_ids_, host_ids_;
     std::vector<float> f0_, f1_, f2_;
     std::vector<uint8_t> u0_;
     std::vector<double> d0_, d1_, d2_, d3_, d4_;
@@ -335,10 +335,13 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         t1 = now_s(); t_phase[3] += t1 - t0; t0 = t1;
     }
     // ---------------- FindFeaturesInRight: LK current-left -> current-right (src/frontend.cpp:105-109)
-#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
-    for (int b = 0; b < B; b++) {
-        Stream &s = streams_[b];
-        if (!s.ran_detect) continue;
+    // the keyframe streams are a few per cent of the batch: the host sections below walk their id list, one stream per task
+    det_ids_.clear();
+    for (int b = 0; b < B; b++) if (streams_[b].ran_detect) det_ids_.push_back(b);
+    const int n_det = (int)det_ids_.size();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads_) if (n_det > 1)
+    for (int k = 0; k < n_det; k++) {
+        Stream &s = streams_[det_ids_[k]];
         s.frontend->finish_DetectFeatures(s.det);
         s.frontend->prepare_FindFeaturesInRight(s.lk);
     }
@@ -354,10 +357,9 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
     if ((rc = run_lk(1, [](const Stream &s) { return s.ran_detect; }))) return rc;
     t1 = now_s(); t_phase[4] += t1 - t0; t0 = t1;
     // ---------------- triangulation of new landmarks (src/frontend.cpp:174, :286)
-#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
-    for (int b = 0; b < B; b++) {
-        Stream &s = streams_[b];
-        if (!s.ran_detect) continue;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads_) if (n_det > 1)
+    for (int k = 0; k < n_det; k++) {
+        Stream &s = streams_[det_ids_[k]];
         s.frontend->finish_FindFeaturesInRight(s.lk);
         s.frontend->prepare_Triangulate(s.tri);
     }
@@ -388,10 +390,9 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         t1 = now_s(); t_phase[5] += t1 - t0; t0 = t1;
     }
     // ---------------- Backend::UpdateMap -> Optimize, synchronous schedule (src/backend.cpp:9-248)
-#pragma omp parallel for schedule(dynamic, 16) num_threads(threads_)
-    for (int b = 0; b < B; b++) {
-        Stream &s = streams_[b];
-        if (!s.ran_detect) continue;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads_) if (n_det > 1)
+    for (int k = 0; k < n_det; k++) {
+        Stream &s = streams_[det_ids_[k]];
         s.is_kf = s.frontend->finish_Triangulate(s.tri) != 0;
         if (s.is_kf && s.frontend->wants_backend()) s.ran_backend = s.backend->prepare_Optimize(s.ba);
     }
@@ -445,10 +446,12 @@ int StreamBatch::step(const uint8_t *const *left, const uint8_t *const *right, s
         t1 = now_s(); t_phase[6] += t1 - t0; t0 = t1;
     }
     long long nkf = 0;
-#pragma omp parallel for schedule(dynamic, 16) reduction(+ : nkf) num_threads(threads_)
-    for (int b = 0; b < B; b++) {
-        Stream &s = streams_[b];
-        if (!s.on_host) continue;           // device-resident tracking: this stream's frame never left the GPU
+    host_ids_.clear();                      // device-resident tracking: the other streams' frames never left the GPU
+    for (int b = 0; b < B; b++) if (streams_[b].on_host) host_ids_.push_back(b);
+    const int n_host = (int)host_ids_.size();
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nkf) num_threads(threads_) if (n_host > 1)
+    for (int k = 0; k < n_host; k++) {
+        Stream &s = streams_[host_ids_[k]];
         if (s.ran_backend) s.backend->finish_Optimize(s.ba);
         s.frontend->end_AddFrame();
         memcpy(s.out_pose, s.frontend->current_frame_->pose_.d, 56);

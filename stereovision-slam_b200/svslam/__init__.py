@@ -169,6 +169,16 @@ class Context:
         """0: blocking calls spin on the stream (default); 1: they sleep on a blocking-sync event (svs_set_wait_mode)."""
         self._chk(self.lib.svs_set_wait_mode(C.c_void_p(self.h), int(mode)))
 
+    def reserve_headroom(self, factor=2.0):
+        """Grow every variable-size scratch buffer to factor x its largest request so far (svs_reserve_headroom): call after
+        warm-up so that steady-state steps never reallocate (a regrowth synchronises the whole device)."""
+        self.lib.svs_reserve_headroom.argtypes = [C.c_void_p, C.c_double]
+        self._chk(self.lib.svs_reserve_headroom(C.c_void_p(self.h), float(factor)))
+
+    def set_ba_schedule(self, high_priority, threads_per_window=0):
+        """Window-solver scheduling (svs_set_ba_schedule): own high-priority stream, forced CTA size (0 = automatic)."""
+        self._chk(self.lib.svs_set_ba_schedule(C.c_void_p(self.h), int(high_priority), int(threads_per_window)))
+
     def stream_ptr(self):
         return self.lib.svs_stream(C.c_void_p(self.h))
 
