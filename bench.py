@@ -1054,7 +1054,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=int(os.environ.get("SVS_BENCH_STREAMS", "4096")))
-    ap.add_argument("--groups", type=int, default=int(os.environ.get("SVS_BENCH_GROUPS", "8")),
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("SVS_BENCH_GROUPS", "16")),
                     help="independent contexts (one CUDA stream pair + one driver thread each) the streams are split over: one "
                          "group's host keyframe bookkeeping overlaps the other group's kernels")
     ap.add_argument("--group-cap", default=os.environ.get("SVS_BENCH_GROUP_CAP", "cores"), choices=["half", "cores"],

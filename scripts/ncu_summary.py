@@ -17,7 +17,11 @@ COLS = OrderedDict([
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
-    ("sm__inst_executed.sum", "warp_inst"),
+    ("smsp__inst_executed.sum", "warp_inst"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "pipe_fma_pct"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "pipe_alu_pct"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "pipe_lsu_pct"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "pipe_xu_pct"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
     ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),

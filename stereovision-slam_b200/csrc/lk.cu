@@ -35,6 +35,30 @@ __device__ __forceinline__ float warp_sum_scaled_exact(int s)
 __device__ __forceinline__ int cvfloor(float v) { return __float2int_rd(v); }
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
+// Which window sample (row y, column x) is slot q of a lane.  All window sums are exact integers, so any assignment of the
+// WIN^2 samples to (lane, slot) gives the same result.  Generic: sample k = lane + 32 q in row-major order.  WIN = 11 (the
+// reference's window): lane = 11 g + x owns column x, rows g, g + 3, g + 6 (, g + 9) — slot q is a CONSTANT byte offset
+// (3 rows) from slot 0 in every staged buffer, so the inner loops address with immediates instead of one offset register per
+// slot; the column-10 samples of rows 2, 5, 8 (no lane 32) are slot 3 of lanes 22, 23, 24.
+template <int WIN>
+__device__ __forceinline__ void lk_sample_pos(int lane, int q, int &y, int &x)
+{
+    if (WIN == 11) {
+        const int g = lane / 11, xx = lane - 11 * g;
+        if (q < 3 || g < 2) { y = g + 3 * q; x = xx; }
+        else { y = 2 + 3 * min(lane - 22, 2); x = 10; }
+    } else {
+        const int k = lane + 32 * q;
+        y = k / WIN; x = k - y * WIN;
+    }
+}
+template <int WIN>
+__device__ __forceinline__ bool lk_sample_valid(int lane, int q)
+{
+    if (WIN == 11) return q < 3 || lane < 25;
+    return lane + 32 * q < WIN * WIN;
+}
+
 // Word k of the staged next-image region (row k / RWORDS, bytes 4 (k % RWORDS) ..+3): pixels of the reflect-101-padded image
 // at (rx0 + 4q + i, ry0 + r).  Interior regions are aligned 32-bit loads; elsewhere the row is reflected once per word and
 // only words that straddle the left / right image border are assembled from reflected bytes.
@@ -61,7 +85,7 @@ __device__ __forceinline__ uint32_t lk_region_word(const uint8_t *__restrict__ J
 template <int WIN>
 __global__ void __launch_bounds__(LK_WARPS * 32, WIN <= 11 ? 6 : 1)
 k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc next, const int32_t *__restrict__ pt_img, const float *__restrict__ prev_xy,
-           float *__restrict__ next_xy, int n_pts, int max_iter, double eps2, uint8_t *__restrict__ status)
+           float *__restrict__ next_xy, int n_pts, int max_iter, double eps2, float eps_lo, float eps_hi, uint8_t *__restrict__ status)
 {
     constexpr int PW = WIN + 3;                 // previous-image patch (window + bilinear + Scharr halo)
     constexpr int DW = WIN + 1;                 // derivative / next-image patch
@@ -104,11 +128,10 @@ k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc
     int offI[NPL], offJ[NPL], offD[NPL];
 #pragma unroll
     for (int q = 0; q < NPL; q++) {
-        int k = lane + 32 * q;
-        int y = k / WIN, x = k - y * WIN;
+        int y, x;
+        lk_sample_pos<WIN>(lane, q, y, x);
         offI[q] = (y + 1) * IP + (x + 1); offJ[q] = y * RP + x; offD[q] = y * DW + x;
     }
-    const float eps2f = (float)eps2, eps_lo = eps2f * 0.9999f, eps_hi = eps2f * 1.0001f;
 
     for (int level = nlev - 1; level >= 0; level--) {
         const uint8_t *I = prev.base + (size_t)img * prev.img_pitch + prev.off[level];
@@ -229,9 +252,8 @@ k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc
         int pA11 = 0, pA12 = 0, pA22 = 0;
 #pragma unroll
         for (int q = 0; q < NPL; q++) {
-            int k = lane + 32 * q;
             Iv[q] = 0; Ixv[q] = 0; Iyv[q] = 0;
-            if (k < WIN * WIN) {
+            if (lk_sample_valid<WIN>(lane, q)) {
                 const uint8_t *p = mI + offI[q] + ioff;
                 int ival = descale(p[0] * w00 + p[1] * w01 + p[IP] * w10 + p[IP + 1] * w11, W_BITS - 5);
                 const short2 *dp = mD + offD[q];
@@ -284,8 +306,7 @@ k_lk_track(const __grid_constant__ PyrDesc prev, const __grid_constant__ PyrDesc
             int pb1 = 0, pb2 = 0;
 #pragma unroll
             for (int q = 0; q < NPL; q++) {
-                int k = lane + 32 * q;
-                if (k < WIN * WIN) {
+                if (lk_sample_valid<WIN>(lane, q)) {
                     const uint8_t *p = pJ + offJ[q];
                     int diff = descale(p[0] * w00 + p[1] * w01 + p[RP] * w10 + p[RP + 1] * w11, W_BITS - 5) - Iv[q];
                     pb1 += diff * Ixv[q]; pb2 += diff * Iyv[q];
@@ -329,11 +350,14 @@ int svs_i_lk(svs_ctx *c, const PyrDesc &prev, const PyrDesc &next, const int32_t
     if (eps < 0) eps = 0;
     if (eps > 10) eps = 10;
     double eps2 = eps * eps;
+    // the kernel decides convergence from a float estimate outside [eps_lo, eps_hi] and evaluates OpenCV's double expression
+    // inside that band: the band edges are launch constants
+    const float eps2f = (float)eps2, eps_lo = eps2f * 0.9999f, eps_hi = eps2f * 1.0001f;
     int blocks = (n_pts + LK_WARPS - 1) / LK_WARPS;
 #define LK_CASE(WN)                                                                                          \
     case WN:                                                                                                 \
         k_lk_track<WN><<<blocks, LK_WARPS * 32, 0, c->stream>>>(prev, next, pt_img, prev_xy, next_xy, n_pts, \
-                                                                max_iter, eps2, status);                     \
+                                                                max_iter, eps2, eps_lo, eps_hi, status);     \
         break;
     svs_i_prof_begin(c, KID_LK);
     switch (win) {
