@@ -922,10 +922,13 @@ def run_gpu(args, rank, world, local_rank):
     except Exception:
         cores = os.cpu_count() or 1
     my_cores = max(1, cores // max(1, local_world))
-    # Context groups: each is one host thread that drives its share of the streams, so that one group's keyframe bookkeeping
-    # overlaps the other groups' kernels.  Measured on one B200 (profiles/README.md): with 16 / 8 / 4 cores, one group per
-    # core up to 8 beats fewer groups with OpenMP helpers (8 cores: 172 k vs 156 k frames/s; 4 cores: 147 k vs 125 k).
-    gcap = my_cores if args.group_cap == "cores" else max(1, my_cores // 2)
+    # Context groups: each is one host thread that drives its share of the streams, so that one group's serial chain (track
+    # kernels -> keyframe bookkeeping -> detect / right LK / triangulate -> BA -> bookkeeping) overlaps the other groups'
+    # kernels.  Measured on one B200 (profiles/README.md): 16 groups beat fewer groups at every core count, also with fewer
+    # cores than groups as long as the waiting threads sleep (4 cores: 184 k frames/s with 16 sleeping groups, 154 k with 4
+    # spinning ones, 125 k with 2 groups x 2 OpenMP threads); with a core per group spinning waits win (16 cores: e2e 164 k
+    # vs 153 k).
+    gcap = {"cores": my_cores, "half": max(1, my_cores // 2), "none": 1 << 30}[args.group_cap]
     G = max(1, min(args.groups, args.streams, gcap))
     host_threads = max(1, my_cores // G)
     # host wait policy: a group thread spins on its stream while it has a core of its own (lowest wake-up latency); with more
@@ -1057,8 +1060,8 @@ def main():
     ap.add_argument("--groups", type=int, default=int(os.environ.get("SVS_BENCH_GROUPS", "16")),
                     help="independent contexts (one CUDA stream pair + one driver thread each) the streams are split over: one "
                          "group's host keyframe bookkeeping overlaps the other group's kernels")
-    ap.add_argument("--group-cap", default=os.environ.get("SVS_BENCH_GROUP_CAP", "cores"), choices=["half", "cores"],
-                    help="upper bound of the context groups of a rank: half = cores / 2 (a driver thread + one helper each), cores = one per core")
+    ap.add_argument("--group-cap", default=os.environ.get("SVS_BENCH_GROUP_CAP", "none"), choices=["half", "cores", "none"],
+                    help="upper bound of the context groups of a rank: half = cores / 2 (a driver thread + one helper each), cores = one per core, none = as many as --groups asks for (more groups than cores: the threads sleep in their waits)")
     ap.add_argument("--variants", type=int, default=24, help="photometric variants of the clip (distinct frame bytes per stream)")
     ap.add_argument("--h2d-mode", type=int, default=2, choices=[0, 2, 3],
                     help="e2e transfer of the pinned host frames: 2 zero-copy kernel reads over PCIe, 0 staged DMA copies")
