@@ -19,7 +19,7 @@ python scripts/launch_summary.py $OUT/${TAG}_launches.csv "ncu --metrics gpu__ti
 head -20 $OUT/${TAG}_launches_summary.csv
 if [ -z "$SKIP_FULL" ]; then
 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:'k_lk_track|k_ba_window|k_pose_only_lm|k_pyr_down|k_corner_response|k_corner_greedy|k_corner_select|k_half_nearest|k_trk_|k_ba_build' -c 256 \
+    -k regex:'k_lk_track|k_ba_window|k_pose_only_lm|k_pyr_down|k_corner_response|k_corner_greedy|k_corner_select|k_half_nearest|k_trk_|k_ba_build' -c 96 \
     -o /tmp/${TAG}_full python $COMMON > $OUT/${TAG}_full_bench.log 2>&1
 echo "full exit $?"
 python scripts/ncu_summary.py /tmp/${TAG}_full.ncu-rep > $OUT/${TAG}_full_summary.csv
