@@ -486,7 +486,7 @@ class Rig:
             v = self.ptr_cache[key] = (self.svslam.Slam.ptr_array(lp), self.svslam.Slam.ptr_array(rp))
         return v
 
-    def run_steps(self, n, on_device, stagger=False):
+    def run_steps(self, n, on_device, stagger=False, serial=False):
         args = self.args
 
         def mode_of(g):      # e2e ingest: 2 = zero-copy kernel reads of the pinned host frames, 0 = staged strided DMA copies
@@ -514,6 +514,9 @@ class Rig:
 
         if self.G == 1:
             loop(0)
+        elif serial:        # one group after another: a launch's event bracket is then the kernel's own duration
+            for g in range(self.G):
+                loop(g)
         else:
             th = [threading.Thread(target=loop, args=(g,)) for g in range(self.G)]
             for t in th:
@@ -532,9 +535,9 @@ class Rig:
             tot += o
         return tot
 
-    def region(self, steps, warmup, on_device, timing, barrier, dist=None, profile_window=False):
+    def region(self, steps, warmup, on_device, timing, barrier, dist=None, profile_window=False, serial=False):
         torch, lib = self.torch, self.lib
-        self.run_steps(warmup, on_device)
+        self.run_steps(warmup, on_device, serial=serial)
         # steady state must not reallocate: a scratch-buffer regrowth is a device-wide synchronisation (a single one inside a
         # 60-step region costs tens of milliseconds on every context).  Sizes fluctuate with the number of keyframe streams
         # per step, so after priming + warm-up every buffer is grown once to 2 x the largest size it has been asked for.
@@ -555,7 +558,7 @@ class Rig:
         t0 = time.perf_counter()
         cpu0 = time.process_time()
         e0.record()
-        self.run_steps(steps, on_device)
+        self.run_steps(steps, on_device, serial=serial)
         torch.cuda.synchronize(self.dev)
         e1.record()
         cpu_s = time.process_time() - cpu0      # user + system time of every thread of this rank over the timed steps
@@ -594,7 +597,7 @@ class Rig:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             regrowths = int(t.item())
         return dict(ms=ms, wall=wall, launches=launches, phases=phases, counts=counts, kern=kern, lost=lost, cpu_s=cpu_s,
-                    regrowths=regrowths)
+                    regrowths=regrowths, steps=steps)
 
     def region_clean(self, *a, **k):
         """region(), re-measured once if a scratch buffer had to regrow inside the timed steps (the regrowth's device-wide
@@ -840,21 +843,39 @@ def build_report(args, world, B, G, cor, spec, dev_pass, e2e_pass, kern_pass, cl
     ingest = ("k_half_nearest", "k_pyr_down")     # launched on the ingest stream, overlapped with the other kernels
     if any(k in shares_ncu for k in kr):
         dom = max((k for k in kr), key=lambda k: shares_ncu.get(k, 0.0), default=None)
-        dom_src = "largest share of the serialised step in profiles/r02_launches_summary.csv (%.0f %%)" % (100 * shares_ncu.get(dom, 0.0))
+        dom_src = ("largest share of the serialised step in profiles/r02_launches_summary.csv (%.0f %%): the ncu launch list of this "
+                   "workload at 2 context groups, where every launch fills the machine and serialised time = SM time; at the bench's "
+                   "%d groups the small BA launches (<= 11 CTAs, ~3 ms) are the largest SERIALISED share (kernel_time_share, "
+                   "profiles/r02_launches_16groups_summary.csv) but run underneath the other groups' kernels"
+                   % (100 * shares_ncu.get(dom, 0.0), G))
     else:
         dom = max((k for k in kern if k in kr and k not in ingest), key=lambda k: kern[k][0], default=None)
         dom_src = "largest summed event-bracketed time among the compute-stream kernels"
     roof = None
     if dom:
         tr = traffic.get(dom)
+        # the ncu capture launched this kernel for 2048 streams at a time (2 context groups), the live run for B / G streams:
+        # DRAM bytes per launch are scaled by the units per launch (keypoints = 4 per CTA for LK, windows = CTAs for BA)
+        tr_bytes, tr_note = (tr["traffic"], "unscaled") if tr else (None, None)
+        per_cta = {"k_lk_track": 4 * 3700.0}.get(dom)
+        if tr and per_cta and tr.get("grid"):
+            try:
+                ncu_alg = float(tr["grid"]) * per_cta
+                tr_bytes = tr["traffic"] * kr[dom]["algorithmic_bytes_per_launch"] / ncu_alg
+                tr_note = "ncu bytes per launch x (live algorithmic bytes per launch / algorithmic bytes of the captured launch = %.3f)" % (
+                    kr[dom]["algorithmic_bytes_per_launch"] / ncu_alg)
+            except (ValueError, ZeroDivisionError):
+                pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": kr[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kr[dom]["frac"],
-                "traffic": tr["traffic"] if tr else None,
-                "traffic_source": "profiles/r02_ncu_full_summary.csv (ncu --set full of this configuration, mean per launch)" if tr else None,
+                "traffic": tr_bytes,
+                "traffic_source": ("profiles/r02_ncu_full_summary.csv (ncu --set full, mean DRAM read + write bytes per launch; %s)" % tr_note) if tr else None,
                 "avg_launch_ms": kr[dom]["avg_launch_ms"], "launches": kr[dom]["launches"],
                 "algorithmic_bytes_per_launch": kr[dom]["algorithmic_bytes_per_launch"], "peak_source": peak_src,
                 "dominant_by": dom_src,
-                "note": "launch durations from CUDA events on the launching stream, %d context group(s) overlapping; limiter: %s (DESIGN.md §4)"
-                        % (G, LIMITER.get(dom, "HBM streaming"))}
+                "note": "launch durations from CUDA events on the launching stream, %s; limiter: %s (DESIGN.md §4)"
+                        % ("the %d context groups stepped one after another in this instrumented pass (a bracket is the kernel's own "
+                           "duration)" % G if kern_pass.get("serial_groups") else "%d context group(s) overlapping" % G,
+                           LIMITER.get(dom, "HBM streaming"))}
     for k, v in kr.items():
         if k in traffic:
             v["ncu_standalone"] = traffic[k]
@@ -892,7 +913,8 @@ def build_report(args, world, B, G, cor, spec, dev_pass, e2e_pass, kern_pass, cl
         "detail": {"phase_seconds": {k: round(v, 4) for k, v in dev_pass["phases"].items()},
                    "e2e_phase_seconds": {k: round(v, 4) for k, v in e2e_pass["phases"].items()},
                    "counts": dev_pass["counts"], "kernel_ms": {k: [round(v[0], 3), v[1]] for k, v in kern.items()},
-                   "kernel_time_share": shares, "kernel_roofline": kr, "kernel_pass_ms_per_step": kern_pass["ms"] / args.steps,
+                   "kernel_time_share": shares, "kernel_roofline": kr, "kernel_pass_ms_per_step": kern_pass["ms"] / kern_pass.get("steps", args.steps),
+                   "kernel_pass": "context groups stepped one after another" if kern_pass.get("serial_groups") else "context groups overlapping",
                    "summed_kernel_ms_over_wall_ms": dev_total / kern_pass["ms"] if kern_pass["ms"] else None,
                    "lost_streams": dev_pass["lost"], "host_cores": cores, "host_cores_this_rank": my_cores, "host_threads_per_group": host_threads,
                    "buffer_regrowths_in_timed_regions": {"value": dev_pass.get("regrowths"), "e2e": e2e_pass.get("regrowths")},
@@ -969,7 +991,18 @@ def run_gpu(args, rank, world, local_rank):
     dev_pass = rig.region_clean(args.steps, args.warmup, True, False, barrier, dist)
     e2e_pass = rig.region_clean(args.steps, args.warmup, False, False, barrier, dist)
     clocks = sampler.stop()
-    kern_pass = rig.region(args.steps, args.warmup, True, True, barrier, dist) if not args.no_kernel_pass else dev_pass
+    # instrumented pass (feeds roofline / kernel_ms only): every launch bracketed by CUDA events on its stream, the context
+    # groups stepped ONE AFTER ANOTHER — with the groups overlapping, a bracket would also contain the time the launch waits
+    # for SMs held by the other groups' kernels
+    if args.no_kernel_pass:
+        kern_pass = dev_pass
+    else:
+        try:
+            kern_pass = rig.region(max(4, args.steps // 2), 2, True, True, barrier, dist, serial=True)
+            kern_pass["serial_groups"] = True
+        except Exception as e:      # never lose the bench line to the instrumented pass
+            log("serial instrumented pass failed (%r): concurrent pass instead" % (e,))
+            kern_pass = rig.region(args.steps, args.warmup, True, True, barrier, dist)
     distinct = rig.distinct
     V = rig.V
     rig.close()

@@ -84,7 +84,13 @@ def test_gpu_arm_report_block_dry_run():
     # (profiles/r02_launches_summary.csv), not the one with the largest event-bracketed time of the fabricated pass
     want = max(b.ncu_shares().items(), key=lambda kv: kv[1])[0] if b.ncu_shares() else "k_ba_window"
     assert r["kernel"] == want and r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    assert r["traffic"] == traffic[want]["traffic"] and "dominant_by" in r
+    # ncu's DRAM bytes per launch, scaled from the captured launch size (grid x 4 keypoints) to the live launch size
+    if want == "k_lk_track":
+        scale = r["algorithmic_bytes_per_launch"] / (300000 * 4 * 3700.0)
+        assert abs(r["traffic"] - traffic[want]["traffic"] * scale) <= 1e-9 * traffic[want]["traffic"]
+    else:
+        assert r["traffic"] == traffic[want]["traffic"]
+    assert "dominant_by" in r
     assert "k_lk_track" in out["detail"]["kernel_roofline"] and "ncu_standalone" in out["detail"]["kernel_roofline"]["k_lk_track"]
     assert out["detail"]["config_1"] == {"value": 1.0}
 

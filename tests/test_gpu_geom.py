@@ -104,6 +104,35 @@ def test_ba_structure_built_on_device_equals_host_build(ctx, monkeypatch):
     assert np.abs(chi2 - dev[0][2][perm]).max() < 1e-6 * max(1.0, dev[0][2].max())
 
 
+def test_ba_schedule_and_headroom_do_not_change_results(ctx):
+    """svs_set_ba_schedule (own high-priority stream, forced CTA size) and svs_reserve_headroom (scratch buffers grown once to
+    factor x their largest request, contents kept) are scheduling / allocation knobs: bit-identical results, and after the
+    head room a call that needs up to factor x the memory of the largest earlier call does not reallocate."""
+    import ctypes as C
+    lib = ctx.lib
+    lib.svs_buffer_regrowths.restype = C.c_longlong
+    small = [ba_problem(s, n_kf=10, n_lm=300)[0] for s in (0, 1, 2)]
+    base = ctx.ba_optimize(small, K05, K05, EXT_L, EXT_R)
+    for prio, threads in ((1, 0), (1, 256), (0, 512), (0, 256)):
+        ctx.set_ba_schedule(prio, threads)
+        got = ctx.ba_optimize(small, K05, K05, EXT_L, EXT_R)
+        for (P, L, chi2, st), (bP, bL, bchi2, bst) in zip(got, base):
+            assert np.array_equal(P, bP) and np.array_equal(L, bL) and np.array_equal(chi2, bchi2), (prio, threads)
+            assert (st.iterations, st.trials, st.chi2) == (bst.iterations, bst.trials, bst.chi2)
+    ctx.set_ba_schedule(0, 0)
+    with pytest.raises(Exception):
+        ctx.set_ba_schedule(0, 300)
+    ctx.reserve_headroom(2.5)
+    r0 = lib.svs_buffer_regrowths()
+    more = small + [ba_problem(s, n_kf=10, n_lm=300)[0] for s in (3, 4, 5)]      # twice the windows: inside the head room
+    got = ctx.ba_optimize(more, K05, K05, EXT_L, EXT_R)
+    assert lib.svs_buffer_regrowths() == r0
+    for (P, L, chi2, st), (bP, bL, bchi2, bst) in zip(got[:3], base):
+        assert np.array_equal(P, bP) and np.array_equal(L, bL) and np.array_equal(chi2, bchi2)
+    with pytest.raises(Exception):
+        ctx.reserve_headroom(0.5)
+
+
 def test_ba_large_window_global_S(ctx):
     pr = ba_problem(9, n_kf=30, n_lm=500)[0]          # 180x180 reduced system: beyond shared memory
     (P, L, chi2, st), = ctx.ba_optimize([pr], K05, K05, EXT_L, EXT_R)
