@@ -117,8 +117,12 @@ def test_ba_schedule_and_headroom_do_not_change_results(ctx):
         ctx.set_ba_schedule(prio, threads)
         got = ctx.ba_optimize(small, K05, K05, EXT_L, EXT_R)
         for (P, L, chi2, st), (bP, bL, bchi2, bst) in zip(got, base):
-            assert np.array_equal(P, bP) and np.array_equal(L, bL) and np.array_equal(chi2, bchi2), (prio, threads)
-            assert (st.iterations, st.trials, st.chi2) == (bst.iterations, bst.trials, bst.chi2)
+            assert (st.iterations, st.trials) == (bst.iterations, bst.trials), (prio, threads)
+            if threads == 256:      # another CTA size sums the per-thread chi2 partials in another order: last-bit differences
+                assert np.abs(P - bP).max() < 1e-9 and rel_to_norm(L, bL).max() < 1e-9 and abs(st.chi2 - bst.chi2) <= 1e-9 * bst.chi2
+            else:                   # the stream a kernel runs on cannot change its arithmetic
+                assert np.array_equal(P, bP) and np.array_equal(L, bL) and np.array_equal(chi2, bchi2), (prio, threads)
+                assert st.chi2 == bst.chi2
     ctx.set_ba_schedule(0, 0)
     with pytest.raises(Exception):
         ctx.set_ba_schedule(0, 300)
