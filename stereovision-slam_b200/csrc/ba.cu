@@ -150,7 +150,6 @@ k_ba_window(BaArgs A)
     double *Hpl = A.Hpl + 18 * (size_t)P.grp0, *WD = A.WD + 18 * (size_t)P.grp0;
     const int32_t *lg_off = A.lg_off + P.lgoff0, *g_lm = A.g_lm + P.grp0, *g_pose = A.g_pose + P.grp0;
     const int32_t *pg_off = A.pg_off + P.pgoff0, *pg_groups = A.pg_groups + P.grp0;
-    const int G = P.G;
     const double hd = A.huber_delta;
 
     for (int i = tid; i < 7 * NA; i += BT) {
